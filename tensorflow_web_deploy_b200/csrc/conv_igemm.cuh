@@ -1,0 +1,205 @@
+// Implicit-GEMM convolution + BatchNorm(scale/shift) + ReLU for sm_100a.
+//
+//   D[M = n*oh*ow, N = cout]  =  sum over (tap r,s ; channel block)  A_tap[M, 64] * W[N, 64]^T
+//
+// Restates ops.conv2d (/root/reference/inception/slim/ops.py:229-245): tf.nn.conv2d (NHWC x HWIO,
+// no bias) -> batch_norm inference branch (ops.py:122-128, folded to y = x*scale + shift) -> relu.
+//
+// * A tiles (128 output pixels x 64 input channels of ONE filter tap) are gathered by the TMA unit in
+//   im2col mode straight from the NHWC activation tensor: no im2col buffer exists in HBM, SAME padding
+//   and ragged channel counts are the unit's out-of-bounds zero fill.  1x1/stride-1 layers use the
+//   plain 2-D tiled mode on the [pixels, channels] view.
+// * W tiles ([n_tile x 64] of the packed K-major weight matrix) come in by 2-D tiled TMA.
+// * Both land in shared memory with the 128-byte swizzle and feed tcgen05.mma (kind::f16, M=128,
+//   N=n_tile<=256, K=16) issued by one thread; the fp32 accumulator lives in TMEM.
+// * 4 epilogue warps pull the accumulator with tcgen05.ld, apply scale/shift/ReLU in fp32, convert to
+//   bf16/fp16 and store directly into the channel slice of the (possibly concatenated) NHWC output —
+//   tf.concat (inception_model.py:125...) never runs as a kernel.
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace icp {
+
+constexpr int kBM = 128;                    // output pixels per CTA tile (UMMA M)
+constexpr int kBK = 64;                     // K elements per pipeline stage (one 128-B swizzle row)
+constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+
+struct ConvArgs {
+  int m_total;     // valid output pixels (n * oh * ow)
+  int oh, ow;      // output spatial size
+  int stride;
+  int pad_h, pad_w;
+  int kw;          // filter width (S)
+  int taps;        // R * S
+  int cblocks;     // ceil(cin / 64)
+  int n_tile;      // output channels per CTA, multiple of 16, <= 256
+  int tmem_cols;   // power of two >= max(32, n_tile)
+  int stages;
+  int im2col;      // 1: A via im2col TMA, 0: A via 2-D tiled TMA
+  int fmt;         // 0 fp16, 1 bf16
+  int relu;
+  void* out;       // NHWC output buffer (16-bit elements)
+  int ldo;         // channels in the output buffer (concat width)
+  int coff;        // first channel this layer owns in the output buffer
+  const float* scale;  // [cout] rsqrt(var + eps)
+  const float* shift;  // [cout] beta - mean * scale
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+  if (fmt) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kConvThreads)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-B alignment
+  uint8_t* gbase = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = base + a.stages * stage_bytes;
+  const uint32_t tmem_full_bar = bar_base + 16u * a.stages;
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+  float* s_scale = reinterpret_cast<float*>(gbase + a.stages * stage_bytes + 256);
+  float* s_shift = s_scale + 256;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
+
+  const int m0 = blockIdx.x * kBM;
+  const int n_base = blockIdx.y * a.n_tile;
+  const int num_kb = a.taps * a.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_b);
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      int bw = 0, bh = 0, bn = 0;
+      if (a.im2col) {
+        const int q = m0 % a.ow;
+        const int t = m0 / a.ow;
+        bw = q * a.stride - a.pad_w;
+        bh = (t % a.oh) * a.stride - a.pad_h;
+        bn = t / a.oh;
+      }
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % a.stages;
+        const uint32_t ph = (kb / a.stages) & 1;
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        ptx::mbar_expect_tx(full_bar(s), stage_bytes);
+        const uint32_t sa = base + s * stage_bytes;
+        if (a.im2col) {
+          const int r = tap / a.kw;
+          ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * kBK, bw, bh, bn, static_cast<uint16_t>(tap - r * a.kw),
+                                  static_cast<uint16_t>(r));
+        } else {
+          ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * kBK, m0);
+        }
+        ptx::tma_load_2d(sa + kABytes, &tm_b, full_bar(s), kb * kBK, n_base);
+        if (++cb == a.cblocks) { cb = 0; ++tap; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % a.stages;
+        const uint32_t ph = (kb / a.stages) & 1;
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = base + s * stage_bytes;
+        const uint64_t da = ptx::make_smem_desc_sw128(sa);
+        const uint64_t db = ptx::make_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // +32 B per K=16 slice inside the 128-B swizzle row: +2 in the (addr>>4) field
+          ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+        }
+        ptx::umma_commit(empty_bar(s));      // smem slot free once these MMAs retire
+      }
+      ptx::umma_commit(tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    const int et = threadIdx.x - 64;         // 0..127
+    for (int i = et; i < a.n_tile; i += 128) {
+      s_scale[i] = __ldg(a.scale + n_base + i);
+      s_shift[i] = __ldg(a.shift + n_base + i);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int quarter = warp & 3;            // TMEM lanes this warp may touch: [32q, 32q+32)
+    const int row = quarter * 32 + lane;
+    const int m = m0 + row;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(m) * a.ldo + a.coff + n_base;
+    const bool valid = m < a.m_total;
+    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(taddr + c0, v);
+      ptx::tmem_ld_wait();
+      uint32_t p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float x0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0 + 2 * j], s_shift[c0 + 2 * j]);
+        float x1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 2 * j + 1], s_shift[c0 + 2 * j + 1]);
+        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        p[j] = pack2(x0, x1, a.fmt);
+      }
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+        dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
+        dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+inline size_t conv_smem_bytes(int stages, int n_tile) {
+  return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + 256 + 2048;
+}
+
+}  // namespace icp

@@ -1,0 +1,1020 @@
+// libinception_b200.so — engine, tower plan and C ABI (include/inception_b200.h).
+//
+// The tower topology below restates /root/reference/inception/slim/inception_model.py:86-329 as a
+// static launch plan: every conv is one tcgen05 implicit-GEMM launch writing its channel slice of the
+// block's NHWC output (no concat kernels), pools and the head are HBM-bound kernels.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/inception_b200.h"
+#include "conv_igemm.cuh"
+#include "tower_kernels.cuh"
+
+namespace icp {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_tls_error;
+
+struct Fail {
+  int code;
+  std::string msg;
+};
+[[noreturn]] static void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Fail{code, buf};
+}
+#define CK(expr)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) fail(ICP_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                __FILE__, __LINE__);                                                \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ driver API
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static void load_driver_api() {
+  if (g_encode_tiled && g_encode_im2col) return;
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+  if (!f || q != cudaDriverEntryPointSuccess) fail(ICP_E_CUDA, "cuTensorMapEncodeTiled not available");
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(f);
+  f = nullptr;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q));
+  if (!f || q != cudaDriverEntryPointSuccess) fail(ICP_E_CUDA, "cuTensorMapEncodeIm2col not available");
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(f);
+  CK(cudaDriverGetVersion(&g_driver_version));
+}
+
+static CUtensorMapDataType tm_dtype(int fmt) {
+  return fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
+// 2-D row-major [rows, cols] 16-bit matrix, box [box_rows x 64 cols], 128-B swizzle.
+static CUtensorMap make_tm_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                              int fmt) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&m, tm_dtype(fmt), 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fail(ICP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
+         (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+  return m;
+}
+
+// NHWC activation [n,h,w,c] (channel stride ld) in im2col mode: 128 base pixels x 64 channels per load.
+static CUtensorMap make_tm_im2col(const void* ptr, int n, int h, int w, int c, int ld, int kh, int kw, int stride,
+                                  int pad_h, int pad_w, int fmt) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  int lower[2] = {-pad_w, -pad_h};
+  int upper[2] = {pad_w - (kw - 1), pad_h - (kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(&m, tm_dtype(fmt), 4, const_cast<void*>(ptr), dims, strides, lower, upper,
+                               /*channelsPerPixel=*/kBK, /*pixelsPerColumn=*/kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fail(ICP_E_CUDA, "cuTensorMapEncodeIm2col failed (%d) n=%d h=%d w=%d c=%d ld=%d k=%dx%d s=%d pad=%d,%d", (int)r,
+         n, h, w, c, ld, kh, kw, stride, pad_h, pad_w);
+  // Drivers <= 13.1 mis-set a descriptor bit for im2col maps over tensors smaller than 128 KiB (the
+  // same correction CUTLASS applies in cute/atom/copy_traits_sm90_im2col.hpp).
+  const size_t bytes = static_cast<size_t>(n) * h * w * ld * 2;
+  if (g_driver_version <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------ weights blob
+struct HostTensor {
+  std::vector<int> dims;
+  std::vector<float> data;
+};
+using Blob = std::map<std::string, HostTensor>;
+
+static Blob read_blob(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) fail(ICP_E_IO, "cannot open weight blob %s", path);
+  std::unique_ptr<FILE, int (*)(FILE*)> guard(f, fclose);
+  char magic[8];
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "ICPWv001", 8) != 0) fail(ICP_E_IO, "%s: bad magic", path);
+  uint32_t count = 0;
+  if (fread(&count, 4, 1, f) != 1) fail(ICP_E_IO, "%s: truncated", path);
+  Blob b;
+  for (uint32_t i = 0; i < count; ++i) {
+    uint16_t ln = 0;
+    if (fread(&ln, 2, 1, f) != 1) fail(ICP_E_IO, "%s: truncated", path);
+    std::string name(ln, '\0');
+    if (fread(&name[0], 1, ln, f) != ln) fail(ICP_E_IO, "%s: truncated", path);
+    uint8_t nd = 0;
+    if (fread(&nd, 1, 1, f) != 1 || nd > 8) fail(ICP_E_IO, "%s: bad rank for %s", path, name.c_str());
+    HostTensor t;
+    size_t n = 1;
+    for (int d = 0; d < nd; ++d) {
+      uint32_t v = 0;
+      if (fread(&v, 4, 1, f) != 1) fail(ICP_E_IO, "%s: truncated", path);
+      t.dims.push_back(static_cast<int>(v));
+      n *= v;
+    }
+    t.data.resize(n);
+    if (fread(t.data.data(), 4, n, f) != n) fail(ICP_E_IO, "%s: truncated in %s", path, name.c_str());
+    b.emplace(std::move(name), std::move(t));
+  }
+  return b;
+}
+
+static const HostTensor& blob_get(const Blob& b, const std::string& name, std::initializer_list<int> dims) {
+  auto it = b.find(name);
+  if (it == b.end()) fail(ICP_E_IO, "weight blob has no tensor '%s'", name.c_str());
+  if (it->second.dims != std::vector<int>(dims)) {
+    std::string got, want;
+    for (int d : it->second.dims) got += std::to_string(d) + ",";
+    for (int d : dims) want += std::to_string(d) + ",";
+    fail(ICP_E_IO, "tensor '%s' has shape [%s] expected [%s]", name.c_str(), got.c_str(), want.c_str());
+  }
+  return it->second;
+}
+
+static uint16_t host_f2h(float f, int fmt) {
+  if (fmt) {  // bf16 round-to-nearest-even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+  }
+  __half h = __float2half_rn(f);
+  uint16_t r;
+  memcpy(&r, &h, 2);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------ device memory
+struct DevicePool {
+  std::vector<void*> ptrs;
+  size_t total = 0;
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    bytes = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) fail(ICP_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    ptrs.push_back(p);
+    total += bytes;
+    return p;
+  }
+  ~DevicePool() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+};
+
+struct Act {   // NHWC 16-bit activation for max_batch images
+  uint16_t* p = nullptr;
+  int h = 0, w = 0, c = 0;   // c = channels in the buffer (row pitch)
+};
+
+// ------------------------------------------------------------------------------------------ conv layer
+struct ConvLayer {
+  std::string name;
+  CUtensorMap tm_a, tm_b;
+  ConvArgs args{};
+  int cout = 0;
+  int n_tiles = 1;
+  int pix_per_image = 0;   // oh * ow
+  size_t smem = 0;
+  long long macs_per_image = 0;
+};
+
+static int pick_n_tile(int cout) {
+  if (cout <= 256) return cout;
+  for (int parts = 2; parts <= 16; ++parts)
+    if (cout % parts == 0 && (cout / parts) % 16 == 0 && cout / parts <= 256) return cout / parts;
+  fail(ICP_E_INVALID, "no UMMA N tiling for cout=%d", cout);
+}
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+static bool g_conv_attr_set = false;
+
+// Packs HWIO fp32 weights into the K-major [cout][taps][cblocks*64] 16-bit matrix the B-operand TMA
+// reads, zero-filling the channel tail of every tap.
+static std::vector<uint16_t> pack_weights(const float* w, int kh, int kw, int cin, int cout, int fmt) {
+  const int cb = (cin + kBK - 1) / kBK;
+  const size_t kp = static_cast<size_t>(kh) * kw * cb * kBK;
+  std::vector<uint16_t> out(static_cast<size_t>(cout) * kp, 0);
+  for (int r = 0; r < kh; ++r)
+    for (int s = 0; s < kw; ++s)
+      for (int ci = 0; ci < cin; ++ci) {
+        const float* src = w + ((static_cast<size_t>(r) * kw + s) * cin + ci) * cout;
+        const size_t kidx = (static_cast<size_t>(r) * kw + s) * cb * kBK + ci;
+        for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(src[co], fmt);
+      }
+  return out;
+}
+
+// in: NHWC buffer (pitch in.c) of which channels [in_coff, in_coff+cin) feed the conv.
+static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n, const Act& in, int in_coff, int cin,
+                           const float* w_hwio, int kh, int kw, int cout, int stride, bool same, const float* scale,
+                           const float* shift, bool relu, const Act& out, int out_coff, int fmt) {
+  if (same && stride != 1) fail(ICP_E_INVALID, "%s: SAME padding is only supported with stride 1", name.c_str());
+  if (cout % 16) fail(ICP_E_INVALID, "%s: cout=%d is not a multiple of 16", name.c_str(), cout);
+  if (cin % 8 || in.c % 8 || in_coff % 8 || out.c % 8 || out_coff % 8)
+    fail(ICP_E_INVALID, "%s: channel counts/offsets must be multiples of 8", name.c_str());
+  const int pad_h = same ? (kh - 1) / 2 : 0, pad_w = same ? (kw - 1) / 2 : 0;
+  const int oh = (in.h + 2 * pad_h - kh) / stride + 1, ow = (in.w + 2 * pad_w - kw) / stride + 1;
+  if (oh != out.h || ow != out.w)
+    fail(ICP_E_INVALID, "%s: output geometry %dx%d != buffer %dx%d", name.c_str(), oh, ow, out.h, out.w);
+  ConvLayer L;
+  L.name = name;
+  L.cout = cout;
+  L.pix_per_image = oh * ow;
+  L.macs_per_image = static_cast<long long>(oh) * ow * cout * kh * kw * cin;
+  const int cb = (cin + kBK - 1) / kBK;
+  const int n_tile = pick_n_tile(cout);
+  L.n_tiles = cout / n_tile;
+  const int num_kb = kh * kw * cb;
+  const size_t stage_bytes = kABytes + static_cast<size_t>(n_tile) * 128;
+  const size_t budget = (n_tile <= 128) ? 100 * 1024 : 200 * 1024;
+  int stages = static_cast<int>(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > num_kb) stages = num_kb;
+  if (stages < 1) stages = 1;
+  static const bool force_im2col = getenv("ICP_FORCE_IM2COL") != nullptr;
+  const bool im2col = force_im2col || !(kh == 1 && kw == 1 && stride == 1);
+
+  // weights + BN vectors to the device
+  std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, fmt);
+  void* d_w = pool.alloc(wp.size() * 2);
+  CK(cudaMemcpy(d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  float* d_scale = static_cast<float*>(pool.alloc(cout * 4));
+  float* d_shift = static_cast<float*>(pool.alloc(cout * 4));
+  CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
+
+  const uint64_t kp = static_cast<uint64_t>(num_kb) * kBK;
+  L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile, fmt);
+  const uint16_t* a_ptr = in.p + in_coff;
+  if (im2col)
+    L.tm_a = make_tm_im2col(a_ptr, max_n, in.h, in.w, cin, in.c, kh, kw, stride, pad_h, pad_w, fmt);
+  else
+    L.tm_a = make_tm_2d(a_ptr, static_cast<uint64_t>(max_n) * in.h * in.w, cin, in.c, kBM, fmt);
+
+  ConvArgs& a = L.args;
+  a.m_total = 0;
+  a.oh = oh;
+  a.ow = ow;
+  a.stride = stride;
+  a.pad_h = pad_h;
+  a.pad_w = pad_w;
+  a.kw = kw;
+  a.taps = kh * kw;
+  a.cblocks = cb;
+  a.n_tile = n_tile;
+  a.tmem_cols = pow2_cols(n_tile);
+  a.stages = stages;
+  a.im2col = im2col ? 1 : 0;
+  a.fmt = fmt;
+  a.relu = relu ? 1 : 0;
+  a.out = out.p;
+  a.ldo = out.c;
+  a.coff = out_coff;
+  a.scale = d_scale;
+  a.shift = d_shift;
+  L.smem = conv_smem_bytes(stages, n_tile);
+  if (!g_conv_attr_set) {
+    CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    g_conv_attr_set = true;
+  }
+  return L;
+}
+
+static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
+  ConvArgs a = L.args;
+  a.m_total = n * L.pix_per_image;
+  dim3 grid((a.m_total + kBM - 1) / kBM, L.n_tiles);
+  conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
+  CK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ plan ops
+struct Op {
+  enum Kind { CONV, MAXPOOL, AVGPOOL } kind;
+  ConvLayer conv;                 // CONV
+  Act in, out;                    // pools
+  int c = 0, out_coff = 0;        // pools: channels pooled, channel offset in out
+  int k = 3, stride = 1, pad = 0;
+};
+
+struct Endpoint {
+  Act act;
+  int coff = 0, c = 0;      // 4-D taps
+  const float* vec = nullptr;   // device float [max_batch, c] taps (logits / predictions / aux_logits)
+};
+
+}  // namespace icp
+
+using namespace icp;
+
+// ------------------------------------------------------------------------------------------ engine
+struct icp_engine {
+  icp_config cfg{};
+  std::string weights_path;
+  int fmt = 1;
+  int S = 299;
+  int C = 0;
+  int max_batch = 0;
+  mutable std::string err;
+  DevicePool pool;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  int last_n = 0;
+
+  float* d_input = nullptr;         // [max_batch, S, S, 3] f32
+  uint8_t* d_rgb = nullptr;         // staging for icp_classify_rgb8
+  size_t d_rgb_cap = 0;
+  float* d_conv0_w = nullptr;       // [27][32]
+  float *d_conv0_scale = nullptr, *d_conv0_shift = nullptr;
+  Act conv0_out;
+  std::vector<Op> ops;              // everything after conv0 up to the last block
+  Act final_act;                    // 8x8x2048
+  float *d_fc_w = nullptr, *d_fc_b = nullptr;
+  float *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
+  int* d_topk_idx = nullptr;
+  // aux head
+  std::vector<Op> aux_ops;
+  Act aux_feat;                     // 1x1x768
+  float *d_aux_w = nullptr, *d_aux_b = nullptr, *d_aux_logits = nullptr;
+  std::map<std::string, Endpoint> endpoints;
+  std::map<int, cudaGraphExec_t> graphs;
+  int launches = 0;
+  long long conv_macs_per_image = 0;
+
+  ~icp_engine() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+    if (d_rgb) cudaFree(d_rgb);
+  }
+};
+
+namespace icp {
+
+struct Builder {
+  icp_engine& e;
+  const Blob& blob;
+  int fmt;
+  int maxn;
+
+  Act alloc_act(int h, int w, int c) {
+    Act a;
+    a.h = h; a.w = w; a.c = c;
+    a.p = static_cast<uint16_t*>(e.pool.alloc(static_cast<size_t>(maxn) * h * w * c * 2));
+    return a;
+  }
+  void bn_fold(const std::string& scope, int cout, std::vector<float>& scale, std::vector<float>& shift) {
+    // ops.batch_norm inference branch (ops.py:122-128): no gamma, eps inside the rsqrt
+    const HostTensor& beta = blob_get(blob, scope + "/BatchNorm/beta", {cout});
+    const HostTensor& mean = blob_get(blob, scope + "/BatchNorm/moving_mean", {cout});
+    const HostTensor& var = blob_get(blob, scope + "/BatchNorm/moving_variance", {cout});
+    scale.resize(cout);
+    shift.resize(cout);
+    for (int i = 0; i < cout; ++i) {
+      const float r = 1.0f / sqrtf(var.data[i] + 0.001f);
+      scale[i] = r;
+      shift[i] = beta.data[i] - mean.data[i] * r;
+    }
+  }
+  // conv + BN + ReLU writing channels [coff, coff+cout) of `out`
+  void conv(std::vector<Op>& ops, const std::string& scope, const Act& in, int cout, int kh, int kw, int stride,
+            bool same, const Act& out, int coff) {
+    const HostTensor& w = blob_get(blob, scope + "/weights", {kh, kw, in.c, cout});
+    std::vector<float> scale, shift;
+    bn_fold(scope, cout, scale, shift);
+    Op op;
+    op.kind = Op::CONV;
+    op.conv = make_conv(e.pool, scope, maxn, in, 0, in.c, w.data.data(), kh, kw, cout, stride, same, scale.data(),
+                        shift.data(), true, out, coff, fmt);
+    e.conv_macs_per_image += op.conv.macs_per_image;
+    ops.push_back(std::move(op));
+  }
+  Act conv_new(std::vector<Op>& ops, const std::string& scope, const Act& in, int cout, int kh, int kw, int stride = 1,
+               bool same = true) {
+    const int ph = same ? (kh - 1) / 2 : 0, pw = same ? (kw - 1) / 2 : 0;
+    Act out = alloc_act((in.h + 2 * ph - kh) / stride + 1, (in.w + 2 * pw - kw) / stride + 1, cout);
+    conv(ops, scope, in, cout, kh, kw, stride, same, out, 0);
+    return out;
+  }
+  void maxpool(std::vector<Op>& ops, const Act& in, const Act& out, int coff) {
+    Op op;
+    op.kind = Op::MAXPOOL;
+    op.in = in; op.out = out; op.c = in.c; op.out_coff = coff;
+    ops.push_back(std::move(op));
+  }
+  Act avgpool_new(std::vector<Op>& ops, const Act& in, int k, int stride, bool same) {
+    const int pad = same ? (k - 1) / 2 : 0;
+    Act out = alloc_act((in.h + 2 * pad - k) / stride + 1, (in.w + 2 * pad - k) / stride + 1, in.c);
+    Op op;
+    op.kind = Op::AVGPOOL;
+    op.in = in; op.out = out; op.c = in.c; op.k = k; op.stride = stride; op.pad = pad;
+    ops.push_back(std::move(op));
+    return out;
+  }
+  void tap(const std::string& name, const Act& a) {
+    Endpoint ep;
+    ep.act = a; ep.coff = 0; ep.c = a.c;
+    e.endpoints[name] = ep;
+  }
+
+  // mixed_35x35x* (inception_model.py:112-158)
+  Act block35(std::vector<Op>& ops, const std::string& s, const Act& x, int pool_c) {
+    Act out = alloc_act(x.h, x.w, 64 + 64 + 96 + pool_c);
+    conv(ops, s + "/branch1x1/Conv", x, 64, 1, 1, 1, true, out, 0);
+    Act t = conv_new(ops, s + "/branch5x5/Conv", x, 48, 1, 1);
+    conv(ops, s + "/branch5x5/Conv_1", t, 64, 5, 5, 1, true, out, 64);
+    t = conv_new(ops, s + "/branch3x3dbl/Conv", x, 64, 1, 1);
+    t = conv_new(ops, s + "/branch3x3dbl/Conv_1", t, 96, 3, 3);
+    conv(ops, s + "/branch3x3dbl/Conv_2", t, 96, 3, 3, 1, true, out, 128);
+    t = avgpool_new(ops, x, 3, 1, true);
+    conv(ops, s + "/branch_pool/Conv", t, pool_c, 1, 1, 1, true, out, 224);
+    tap(s, out);
+    return out;
+  }
+  // mixed_17x17x768a (:160-171)
+  Act block_red_a(std::vector<Op>& ops, const std::string& s, const Act& x) {
+    const int oh = (x.h - 3) / 2 + 1, ow = (x.w - 3) / 2 + 1;
+    Act out = alloc_act(oh, ow, 384 + 96 + x.c);
+    conv(ops, s + "/branch3x3/Conv", x, 384, 3, 3, 2, false, out, 0);
+    Act t = conv_new(ops, s + "/branch3x3dbl/Conv", x, 64, 1, 1);
+    t = conv_new(ops, s + "/branch3x3dbl/Conv_1", t, 96, 3, 3);
+    conv(ops, s + "/branch3x3dbl/Conv_2", t, 96, 3, 3, 2, false, out, 384);
+    maxpool(ops, x, out, 480);
+    tap(s, out);
+    return out;
+  }
+  // mixed_17x17x768b..e (:173-247)
+  Act block17(std::vector<Op>& ops, const std::string& s, const Act& x, int m) {
+    Act out = alloc_act(x.h, x.w, 768);
+    conv(ops, s + "/branch1x1/Conv", x, 192, 1, 1, 1, true, out, 0);
+    Act t = conv_new(ops, s + "/branch7x7/Conv", x, m, 1, 1);
+    t = conv_new(ops, s + "/branch7x7/Conv_1", t, m, 1, 7);
+    conv(ops, s + "/branch7x7/Conv_2", t, 192, 7, 1, 1, true, out, 192);
+    t = conv_new(ops, s + "/branch7x7dbl/Conv", x, m, 1, 1);
+    t = conv_new(ops, s + "/branch7x7dbl/Conv_1", t, m, 7, 1);
+    t = conv_new(ops, s + "/branch7x7dbl/Conv_2", t, m, 1, 7);
+    t = conv_new(ops, s + "/branch7x7dbl/Conv_3", t, m, 7, 1);
+    conv(ops, s + "/branch7x7dbl/Conv_4", t, 192, 1, 7, 1, true, out, 384);
+    t = avgpool_new(ops, x, 3, 1, true);
+    conv(ops, s + "/branch_pool/Conv", t, 192, 1, 1, 1, true, out, 576);
+    tap(s, out);
+    return out;
+  }
+  // mixed_17x17x1280a (:266-280)
+  Act block_red_b(std::vector<Op>& ops, const std::string& s, const Act& x) {
+    const int oh = (x.h - 3) / 2 + 1, ow = (x.w - 3) / 2 + 1;
+    Act out = alloc_act(oh, ow, 320 + 192 + x.c);
+    Act t = conv_new(ops, s + "/branch3x3/Conv", x, 192, 1, 1);
+    conv(ops, s + "/branch3x3/Conv_1", t, 320, 3, 3, 2, false, out, 0);
+    t = conv_new(ops, s + "/branch7x7x3/Conv", x, 192, 1, 1);
+    t = conv_new(ops, s + "/branch7x7x3/Conv_1", t, 192, 1, 7);
+    t = conv_new(ops, s + "/branch7x7x3/Conv_2", t, 192, 7, 1);
+    conv(ops, s + "/branch7x7x3/Conv_3", t, 192, 3, 3, 2, false, out, 320);
+    maxpool(ops, x, out, 512);
+    tap(s, out);
+    return out;
+  }
+  // mixed_8x8x2048a/b (:282-316); nested concats become adjacent channel slices
+  Act block8(std::vector<Op>& ops, const std::string& s, const Act& x) {
+    Act out = alloc_act(x.h, x.w, 2048);
+    conv(ops, s + "/branch1x1/Conv", x, 320, 1, 1, 1, true, out, 0);
+    Act t = conv_new(ops, s + "/branch3x3/Conv", x, 384, 1, 1);
+    conv(ops, s + "/branch3x3/Conv_1", t, 384, 1, 3, 1, true, out, 320);
+    conv(ops, s + "/branch3x3/Conv_2", t, 384, 3, 1, 1, true, out, 704);
+    t = conv_new(ops, s + "/branch3x3dbl/Conv", x, 448, 1, 1);
+    t = conv_new(ops, s + "/branch3x3dbl/Conv_1", t, 384, 3, 3);
+    conv(ops, s + "/branch3x3dbl/Conv_2", t, 384, 1, 3, 1, true, out, 1088);
+    conv(ops, s + "/branch3x3dbl/Conv_3", t, 384, 3, 1, 1, true, out, 1472);
+    t = avgpool_new(ops, x, 3, 1, true);
+    conv(ops, s + "/branch_pool/Conv", t, 192, 1, 1, 1, true, out, 1856);
+    tap(s, out);
+    return out;
+  }
+
+  void build() {
+    const int S = e.S;
+    // ---- stem (:86-107) ----
+    {
+      const HostTensor& w = blob_get(blob, "conv0/weights", {3, 3, 3, 32});
+      std::vector<float> scale, shift;
+      bn_fold("conv0", 32, scale, shift);
+      e.d_conv0_w = static_cast<float*>(e.pool.alloc(27 * 32 * 4));
+      e.d_conv0_scale = static_cast<float*>(e.pool.alloc(32 * 4));
+      e.d_conv0_shift = static_cast<float*>(e.pool.alloc(32 * 4));
+      CK(cudaMemcpy(e.d_conv0_w, w.data.data(), 27 * 32 * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(e.d_conv0_scale, scale.data(), 32 * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(e.d_conv0_shift, shift.data(), 32 * 4, cudaMemcpyHostToDevice));
+      const int o = (S - 3) / 2 + 1;
+      e.conv0_out = alloc_act(o, o, 32);
+      e.conv_macs_per_image += static_cast<long long>(o) * o * 32 * 27;
+      tap("conv0", e.conv0_out);
+    }
+    std::vector<Op>& ops = e.ops;
+    Act x = conv_new(ops, "conv1", e.conv0_out, 32, 3, 3, 1, false);
+    tap("conv1", x);
+    x = conv_new(ops, "conv2", x, 64, 3, 3, 1, true);
+    tap("conv2", x);
+    {
+      Act p = alloc_act((x.h - 3) / 2 + 1, (x.w - 3) / 2 + 1, x.c);
+      maxpool(ops, x, p, 0);
+      x = p;
+      tap("pool1", x);
+    }
+    x = conv_new(ops, "conv3", x, 80, 1, 1, 1, false);
+    tap("conv3", x);
+    x = conv_new(ops, "conv4", x, 192, 3, 3, 1, false);
+    tap("conv4", x);
+    {
+      Act p = alloc_act((x.h - 3) / 2 + 1, (x.w - 3) / 2 + 1, x.c);
+      maxpool(ops, x, p, 0);
+      x = p;
+      tap("pool2", x);
+    }
+    x = block35(ops, "mixed_35x35x256a", x, 32);
+    x = block35(ops, "mixed_35x35x288a", x, 64);
+    x = block35(ops, "mixed_35x35x288b", x, 64);
+    x = block_red_a(ops, "mixed_17x17x768a", x);
+    x = block17(ops, "mixed_17x17x768b", x, 128);
+    x = block17(ops, "mixed_17x17x768c", x, 160);
+    x = block17(ops, "mixed_17x17x768d", x, 160);
+    x = block17(ops, "mixed_17x17x768e", x, 192);
+    if (e.cfg.enable_aux) {
+      // aux_logits (:249-261): avg_pool 5x5/3 VALID -> 1x1 proj 128 -> full-size VALID conv 768 -> fc
+      const long long keep = e.conv_macs_per_image;
+      Act a = avgpool_new(e.aux_ops, x, 5, 3, false);
+      a = conv_new(e.aux_ops, "aux_logits/proj", a, 128, 1, 1);
+      a = conv_new(e.aux_ops, "aux_logits/Conv", a, 768, a.h, a.w, 1, false);
+      e.conv_macs_per_image = keep;   // aux is not part of the classify_image fetch (F7)
+      e.aux_feat = a;
+      const HostTensor& w = blob_get(blob, "aux_logits/FC/weights", {768, e.C});
+      const HostTensor& b = blob_get(blob, "aux_logits/FC/biases", {e.C});
+      e.d_aux_w = static_cast<float*>(e.pool.alloc(w.data.size() * 4));
+      e.d_aux_b = static_cast<float*>(e.pool.alloc(b.data.size() * 4));
+      e.d_aux_logits = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * e.C * 4));
+      CK(cudaMemcpy(e.d_aux_w, w.data.data(), w.data.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(e.d_aux_b, b.data.data(), b.data.size() * 4, cudaMemcpyHostToDevice));
+      Endpoint ep;
+      ep.vec = e.d_aux_logits; ep.c = e.C;
+      e.endpoints["aux_logits"] = ep;
+    }
+    x = block_red_b(ops, "mixed_17x17x1280a", x);
+    x = block8(ops, "mixed_8x8x2048a", x);
+    x = block8(ops, "mixed_8x8x2048b", x);
+    e.final_act = x;
+    // ---- head (:318-329) ----
+    const HostTensor& w = blob_get(blob, "logits/logits/weights", {x.c, e.C});
+    const HostTensor& b = blob_get(blob, "logits/logits/biases", {e.C});
+    e.d_fc_w = static_cast<float*>(e.pool.alloc(w.data.size() * 4));
+    e.d_fc_b = static_cast<float*>(e.pool.alloc(b.data.size() * 4));
+    CK(cudaMemcpy(e.d_fc_w, w.data.data(), w.data.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e.d_fc_b, b.data.data(), b.data.size() * 4, cudaMemcpyHostToDevice));
+    e.d_logits = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * e.C * 4));
+    e.d_probs = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * e.C * 4));
+    e.d_topk_val = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * 16 * 4));
+    e.d_topk_idx = static_cast<int*>(e.pool.alloc(static_cast<size_t>(maxn) * 16 * 4));
+    Endpoint lg; lg.vec = e.d_logits; lg.c = e.C;
+    Endpoint pr; pr.vec = e.d_probs; pr.c = e.C;
+    e.endpoints["logits"] = lg;
+    e.endpoints["predictions"] = pr;
+  }
+};
+
+static int run_op(const Op& op, int n, int fmt, cudaStream_t st) {
+  switch (op.kind) {
+    case Op::CONV:
+      launch_conv(op.conv, n, st);
+      return 1;
+    case Op::MAXPOOL: {
+      const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
+      maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, 0, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff, fmt);
+      CK(cudaGetLastError());
+      return 1;
+    }
+    case Op::AVGPOOL: {
+      const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
+      avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.out.p, op.out.h, op.out.w, op.out.c, op.k, op.stride, op.pad,
+          fmt);
+      CK(cudaGetLastError());
+      return 1;
+    }
+  }
+  return 0;
+}
+
+// Enqueue the whole tower for n images whose preprocessed fp32 input sits at x_dev.
+static int enqueue_tower(icp_engine& e, const float* x_dev, int n, int k, float* probs_dev, cudaStream_t st) {
+  int launches = 0;
+  const int fmt = e.fmt;
+  {
+    const Act& o = e.conv0_out;
+    const long long pix = static_cast<long long>(n) * o.h * o.w;
+    conv0_kernel<<<static_cast<unsigned>((pix + 127) / 128), 128, 0, st>>>(x_dev, n, e.S, e.S, e.d_conv0_w,
+                                                                            e.d_conv0_scale, e.d_conv0_shift, o.p, o.h,
+                                                                            o.w, fmt);
+    CK(cudaGetLastError());
+    ++launches;
+  }
+  for (const Op& op : e.ops) launches += run_op(op, n, fmt, st);
+  if (e.cfg.enable_aux) {
+    for (const Op& op : e.aux_ops) launches += run_op(op, n, fmt, st);
+    head_kernel<<<n, 256, (768 + e.C) * sizeof(float), st>>>(e.aux_feat.p, 1, 768, e.aux_feat.c, e.d_aux_w, e.d_aux_b,
+                                                             e.C, e.d_aux_logits, nullptr, nullptr, nullptr, 0, fmt);
+    CK(cudaGetLastError());
+    ++launches;
+  }
+  const Act& f = e.final_act;
+  head_kernel<<<n, 256, (f.c + e.C) * sizeof(float), st>>>(f.p, f.h * f.w, f.c, f.c, e.d_fc_w, e.d_fc_b, e.C,
+                                                           e.d_logits, probs_dev ? probs_dev : e.d_probs, e.d_topk_val,
+                                                           e.d_topk_idx, k, fmt);
+  CK(cudaGetLastError());
+  ++launches;
+  return launches;
+}
+
+static void run_tower(icp_engine& e, const float* x_dev, int n, int k, float* probs_dev, cudaStream_t st,
+                      bool timed) {
+  if (n < 1 || n > e.max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e.max_batch);
+  if (k < 0 || k > 16 || k > e.C) fail(ICP_E_INVALID, "k=%d outside [0, min(16, %d)]", k, e.C);
+  e.last_n = n;
+  if (timed) CK(cudaEventRecord(e.ev0, st));
+  const bool graphable = e.cfg.use_cuda_graph && x_dev == e.d_input && probs_dev == nullptr && k == 5;
+  if (graphable) {
+    auto it = e.graphs.find(n);
+    if (it == e.graphs.end()) {
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        e.launches = enqueue_tower(e, x_dev, n, k, nullptr, st);
+      } catch (...) {
+        cudaStreamEndCapture(st, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      CK(cudaStreamEndCapture(st, &g));
+      cudaGraphExec_t ge = nullptr;
+      CK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      it = e.graphs.emplace(n, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second, st));
+  } else {
+    e.launches = enqueue_tower(e, x_dev, n, k, probs_dev, st);
+  }
+  if (timed) CK(cudaEventRecord(e.ev1, st));
+}
+
+template <class F>
+static int guard(const icp_engine* e, F&& f) {
+  try {
+    f();
+    return ICP_OK;
+  } catch (const Fail& x) {
+    if (e) e->err = x.msg;
+    g_tls_error = x.msg;
+    return x.code;
+  } catch (const std::bad_alloc&) {
+    if (e) e->err = "out of host memory";
+    g_tls_error = "out of host memory";
+    return ICP_E_NOMEM;
+  } catch (const std::exception& x) {
+    if (e) e->err = x.what();
+    g_tls_error = x.what();
+    return ICP_E_INVALID;
+  }
+}
+
+static void require_device(int device) {
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    fail(ICP_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+         err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+  if (device < 0 || device >= count) fail(ICP_E_INVALID, "device %d outside [0, %d)", device, count);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    fail(ICP_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  CK(cudaSetDevice(device));
+  load_driver_api();
+}
+
+}  // namespace icp
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* icp_version(void) { return "inception_b200 0.1 (sm_100a, tcgen05 implicit-GEMM)"; }
+
+const char* icp_last_error(const icp_engine* e) { return e ? e->err.c_str() : g_tls_error.c_str(); }
+
+int icp_create(const icp_config* cfg, icp_engine** out) {
+  if (out) *out = nullptr;
+  std::unique_ptr<icp_engine> e;
+  int rc = guard(nullptr, [&] {
+    if (!cfg || !out || !cfg->weights_path) fail(ICP_E_INVALID, "icp_create: null argument");
+    if (cfg->num_classes < 2 || cfg->max_batch < 1) fail(ICP_E_INVALID, "icp_create: num_classes/max_batch invalid");
+    if (cfg->precision != ICP_PRECISION_FP16 && cfg->precision != ICP_PRECISION_BF16)
+      fail(ICP_E_INVALID, "icp_create: unknown precision %d", cfg->precision);
+    Blob blob = read_blob(cfg->weights_path);   // file errors first: they do not need a GPU
+    require_device(cfg->device);
+    e.reset(new icp_engine());
+    e->cfg = *cfg;
+    e->weights_path = cfg->weights_path;
+    e->cfg.weights_path = e->weights_path.c_str();
+    e->fmt = cfg->precision == ICP_PRECISION_BF16 ? 1 : 0;
+    e->S = cfg->image_size > 0 ? cfg->image_size : 299;
+    if (e->S < 75) fail(ICP_E_INVALID, "image_size %d too small for the tower", e->S);
+    e->C = cfg->num_classes;
+    e->max_batch = cfg->max_batch;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+    e->d_input = static_cast<float*>(e->pool.alloc(static_cast<size_t>(e->max_batch) * e->S * e->S * 3 * 4));
+    Builder b{*e, blob, e->fmt, e->max_batch};
+    b.build();
+    CK(cudaDeviceSynchronize());
+  });
+  if (rc == ICP_OK) *out = e.release();
+  return rc;
+}
+
+void icp_destroy(icp_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+int icp_forward_topk(icp_engine* e, const float* x_host, int n, int k, float* probs_out_host, float* topk_vals_host,
+                     int32_t* topk_idx_host) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!x_host) fail(ICP_E_INVALID, "null input");
+    CK(cudaSetDevice(e->cfg.device));
+    if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
+    const size_t in_bytes = static_cast<size_t>(n) * e->S * e->S * 3 * 4;
+    CK(cudaMemcpyAsync(e->d_input, x_host, in_bytes, cudaMemcpyHostToDevice, e->stream));
+    run_tower(*e, e->d_input, n, k > 0 ? k : (e->C < 5 ? e->C : 5), nullptr, e->stream, true);
+    const int kk = k > 0 ? k : 0;
+    if (probs_out_host)
+      CK(cudaMemcpyAsync(probs_out_host, e->d_probs, static_cast<size_t>(n) * e->C * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    if (kk && topk_vals_host)
+      CK(cudaMemcpyAsync(topk_vals_host, e->d_topk_val, static_cast<size_t>(n) * kk * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    if (kk && topk_idx_host)
+      CK(cudaMemcpyAsync(topk_idx_host, e->d_topk_idx, static_cast<size_t>(n) * kk * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+int icp_forward(icp_engine* e, const float* x_host, int n, float* probs_out_host) {
+  return icp_forward_topk(e, x_host, n, 0, probs_out_host, nullptr, nullptr);
+}
+
+int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_dev, void* stream) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!x_dev) fail(ICP_E_INVALID, "null input");
+    CK(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    run_tower(*e, x_dev, n, e->C < 5 ? e->C : 5, probs_dev, st, false);
+  });
+}
+
+static void preprocess_to_input(icp_engine* e, const uint8_t* rgb, int h, int w) {
+  if (!rgb || h < 16 || w < 16) fail(ICP_E_INVALID, "image %dx%d invalid", h, w);
+  const size_t bytes = static_cast<size_t>(h) * w * 3;
+  if (bytes > e->d_rgb_cap) {
+    if (e->d_rgb) cudaFree(e->d_rgb);
+    e->d_rgb = nullptr;
+    e->d_rgb_cap = 0;
+    CK(cudaMalloc(&e->d_rgb, bytes));
+    e->d_rgb_cap = bytes;
+  }
+  CK(cudaMemcpyAsync(e->d_rgb, rgb, bytes, cudaMemcpyHostToDevice, e->stream));
+  const int total = e->S * e->S;
+  preprocess_u8_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(e->d_rgb, h, w, e->d_input, e->S);
+  CK(cudaGetLastError());
+}
+
+int icp_preprocess_rgb8(icp_engine* e, const uint8_t* rgb, int h, int w, float* out_host) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!out_host) fail(ICP_E_INVALID, "null output");
+    CK(cudaSetDevice(e->cfg.device));
+    preprocess_to_input(e, rgb, h, w);
+    CK(cudaMemcpyAsync(out_host, e->d_input, static_cast<size_t>(e->S) * e->S * 3 * 4, cudaMemcpyDeviceToHost,
+                       e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int icp_classify_rgb8(icp_engine* e, const uint8_t* rgb, int h, int w, int k, float* topk_vals, int32_t* topk_idx) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!topk_vals || !topk_idx) fail(ICP_E_INVALID, "null output");
+    if (k < 1) fail(ICP_E_INVALID, "k must be >= 1");
+    CK(cudaSetDevice(e->cfg.device));
+    preprocess_to_input(e, rgb, h, w);
+    run_tower(*e, e->d_input, 1, k, nullptr, e->stream, true);
+    CK(cudaMemcpyAsync(topk_vals, e->d_topk_val, k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(topk_idx, e->d_topk_idx, k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+int icp_endpoint_shape(icp_engine* e, const char* name, int dims[4]) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!name || !dims) fail(ICP_E_INVALID, "null argument");
+    auto it = e->endpoints.find(name);
+    if (it == e->endpoints.end()) fail(ICP_E_INVALID, "unknown end point '%s'", name);
+    const Endpoint& ep = it->second;
+    dims[0] = e->last_n;
+    dims[1] = ep.vec ? 1 : ep.act.h;
+    dims[2] = ep.vec ? 1 : ep.act.w;
+    dims[3] = ep.c;
+  });
+}
+
+int icp_endpoint(icp_engine* e, const char* name, float* out_host) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!name || !out_host) fail(ICP_E_INVALID, "null argument");
+    if (e->last_n < 1) fail(ICP_E_INVALID, "no forward call has run yet");
+    CK(cudaSetDevice(e->cfg.device));
+    auto it = e->endpoints.find(name);
+    if (it == e->endpoints.end()) fail(ICP_E_INVALID, "unknown end point '%s'", name);
+    const Endpoint& ep = it->second;
+    CK(cudaStreamSynchronize(e->stream));
+    if (ep.vec) {
+      CK(cudaMemcpy(out_host, ep.vec, static_cast<size_t>(e->last_n) * ep.c * 4, cudaMemcpyDeviceToHost));
+      return;
+    }
+    const size_t pixels = static_cast<size_t>(e->last_n) * ep.act.h * ep.act.w;
+    float* tmp = nullptr;
+    CK(cudaMalloc(&tmp, pixels * ep.c * 4));
+    const size_t total = pixels * ep.c;
+    h16_to_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, e->stream>>>(ep.act.p, tmp, pixels, ep.c,
+                                                                                          ep.act.c, ep.coff, e->fmt);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(out_host, tmp, total * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(tmp);
+    if (err != cudaSuccess) fail(ICP_E_CUDA, "end point copy failed: %s", cudaGetErrorString(err));
+  });
+}
+
+int icp_last_forward_ms(icp_engine* e, float* ms) {
+  if (!e || !ms) return ICP_E_INVALID;
+  *ms = e->last_ms;
+  return ICP_OK;
+}
+
+int icp_launches_per_forward(icp_engine* e, int* launches) {
+  if (!e || !launches) return ICP_E_INVALID;
+  *launches = e->launches;
+  return ICP_OK;
+}
+
+void* icp_stream(icp_engine* e) { return e ? e->stream : nullptr; }
+
+int icp_conv2d_bn_relu(int device, int precision, const float* x, int n, int h, int w, int cin, const float* wgt,
+                       int kh, int kw, int cout, int stride, int same, const float* scale, const float* shift,
+                       int relu, float* y, int reps, float* ms_out) {
+  return guard(nullptr, [&] {
+    if (!x || !wgt || !scale || !shift || !y) fail(ICP_E_INVALID, "null argument");
+    if (n < 1 || h < 1 || w < 1 || cin < 1 || cout < 1 || kh < 1 || kw < 1 || stride < 1)
+      fail(ICP_E_INVALID, "bad geometry");
+    if (precision != ICP_PRECISION_FP16 && precision != ICP_PRECISION_BF16) fail(ICP_E_INVALID, "bad precision");
+    require_device(device);
+    const int fmt = precision == ICP_PRECISION_BF16 ? 1 : 0;
+    DevicePool pool;
+    cudaStream_t st = nullptr;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{st};
+    const int ph = same ? (kh - 1) / 2 : 0, pw = same ? (kw - 1) / 2 : 0;
+    const int oh = (h + 2 * ph - kh) / stride + 1, ow = (w + 2 * pw - kw) / stride + 1;
+    if (oh < 1 || ow < 1) fail(ICP_E_INVALID, "empty output");
+    Act in, out;
+    in.h = h; in.w = w; in.c = cin;
+    out.h = oh; out.w = ow; out.c = cout;
+    const size_t in_elems = static_cast<size_t>(n) * h * w * cin, out_elems = static_cast<size_t>(n) * oh * ow * cout;
+    float* d_xf = static_cast<float*>(pool.alloc(in_elems * 4));
+    in.p = static_cast<uint16_t*>(pool.alloc(in_elems * 2));
+    out.p = static_cast<uint16_t*>(pool.alloc(out_elems * 2));
+    float* d_yf = static_cast<float*>(pool.alloc(out_elems * 4));
+    CK(cudaMemcpyAsync(d_xf, x, in_elems * 4, cudaMemcpyHostToDevice, st));
+    f32_to_h16_kernel<<<static_cast<unsigned>((in_elems + 255) / 256), 256, 0, st>>>(d_xf, in.p, in_elems, fmt);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(out.p, 0xFF, out_elems * 2, st));   // NaN pattern: unwritten outputs are visible
+    ConvLayer L = make_conv(pool, "conv2d_bn_relu", n, in, 0, cin, wgt, kh, kw, cout, stride, same != 0, scale, shift,
+                            relu != 0, out, 0, fmt);
+    launch_conv(L, n, st);
+    h16_to_f32_kernel<<<static_cast<unsigned>((out_elems + 255) / 256), 256, 0, st>>>(out.p, d_yf,
+                                                                                     static_cast<size_t>(n) * oh * ow,
+                                                                                     cout, cout, 0, fmt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y, d_yf, out_elems * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (reps > 0 && ms_out) {
+      cudaEvent_t a, b;
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&b));
+      for (int i = 0; i < 3; ++i) launch_conv(L, n, st);
+      CK(cudaEventRecord(a, st));
+      for (int i = 0; i < reps; ++i) launch_conv(L, n, st);
+      CK(cudaEventRecord(b, st));
+      cudaError_t err = cudaStreamSynchronize(st);
+      float ms = 0.f;
+      if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, a, b);
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+      if (err != cudaSuccess) fail(ICP_E_CUDA, "timing failed: %s", cudaGetErrorString(err));
+      *ms_out = ms / reps;
+    }
+  });
+}
+
+int icp_pool2d(int device, int precision, int kind, const float* x, int n, int h, int w, int c, int k, int stride,
+               int same, float* y) {
+  return guard(nullptr, [&] {
+    if (!x || !y) fail(ICP_E_INVALID, "null argument");
+    if (c % 8) fail(ICP_E_INVALID, "channels must be a multiple of 8");
+    if (precision != ICP_PRECISION_FP16 && precision != ICP_PRECISION_BF16) fail(ICP_E_INVALID, "bad precision");
+    require_device(device);
+    const int fmt = precision == ICP_PRECISION_BF16 ? 1 : 0;
+    if (kind == 0) { k = 3; stride = 2; same = 0; }
+    const int pad = same ? (k - 1) / 2 : 0;
+    const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
+    if (oh < 1 || ow < 1) fail(ICP_E_INVALID, "empty output");
+    DevicePool pool;
+    const size_t in_elems = static_cast<size_t>(n) * h * w * c, out_elems = static_cast<size_t>(n) * oh * ow * c;
+    float* d_xf = static_cast<float*>(pool.alloc(in_elems * 4));
+    uint16_t* d_x = static_cast<uint16_t*>(pool.alloc(in_elems * 2));
+    uint16_t* d_y = static_cast<uint16_t*>(pool.alloc(out_elems * 2));
+    float* d_yf = static_cast<float*>(pool.alloc(out_elems * 4));
+    CK(cudaMemcpy(d_xf, x, in_elems * 4, cudaMemcpyHostToDevice));
+    f32_to_h16_kernel<<<static_cast<unsigned>((in_elems + 255) / 256), 256>>>(d_xf, d_x, in_elems, fmt);
+    const long long total = static_cast<long long>(n) * oh * ow * (c / 8);
+    if (kind == 0)
+      maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_x, n, h, w, c, c, 0, d_y, oh, ow, c, 0,
+                                                                             fmt);
+    else
+      avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_x, n, h, w, c, c, d_y, oh, ow, c, k, stride,
+                                                                          pad, fmt);
+    h16_to_f32_kernel<<<static_cast<unsigned>((out_elems + 255) / 256), 256>>>(d_y, d_yf,
+                                                                               static_cast<size_t>(n) * oh * ow, c, c, 0,
+                                                                               fmt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(y, d_yf, out_elems * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+// HBM-bound kernels of the tower: preprocessing, the Cin=3 stem conv, pools, classifier head.
+// All activations are NHWC 16-bit (bf16 or fp16 selected by `fmt`: 0 = fp16, 1 = bf16), 8 channels
+// (16 B) per thread access; every channel count in the tower is a multiple of 8.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cfloat>
+#include <cstdint>
+
+namespace icp {
+
+__device__ __forceinline__ float h2f(uint16_t h, int fmt) {
+  if (fmt) return __bfloat162float(__ushort_as_bfloat16(h));
+  return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ uint16_t f2h(float f, int fmt) {
+  if (fmt) return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  return __half_as_ushort(__float2half_rn(f));
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8], int fmt) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = h2f(static_cast<uint16_t>(w[i] & 0xFFFFu), fmt);
+    f[2 * i + 1] = h2f(static_cast<uint16_t>(w[i] >> 16), fmt);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int fmt) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = static_cast<uint32_t>(f2h(f[2 * i], fmt)) | (static_cast<uint32_t>(f2h(f[2 * i + 1], fmt)) << 16);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Preprocess one decoded image: uint8 HWC -> float32 [out,out,3] in [-1,1].
+// PyClassification.py:152 (x * 1/255), :196 central_crop(0.875) => offset = dim // 16,
+// :199-201 resize_bilinear(align_corners=False) = legacy TF1 kernel (src = dst * in/out, no
+// half-pixel), :154-155 (x - 0.5) * 2.
+// ---------------------------------------------------------------------------------------------
+__global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, int H, int W, float* __restrict__ out,
+                                     int osz) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= osz * osz) return;
+  const int ox = idx % osz, oy = idx / osz;
+  const int y0 = H / 16, x0 = W / 16;
+  const int ch = H - 2 * y0, cw = W - 2 * x0;
+  const float sy = static_cast<float>(ch) / static_cast<float>(osz);
+  const float sx = static_cast<float>(cw) / static_cast<float>(osz);
+  const float fy = oy * sy, fx = ox * sx;
+  const int ylo = static_cast<int>(floorf(fy)), xlo = static_cast<int>(floorf(fx));
+  const int yhi = min(ylo + 1, ch - 1), xhi = min(xlo + 1, cw - 1);
+  const float ly = fy - ylo, lx = fx - xlo;
+  const float k = 0.003921568859368563f;  // float32(1/255), the constant in the reference graph
+  const uint8_t* r0 = img + (static_cast<size_t>(y0 + ylo) * W + x0) * 3;
+  const uint8_t* r1 = img + (static_cast<size_t>(y0 + yhi) * W + x0) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float tl = r0[xlo * 3 + c] * k, tr = r0[xhi * 3 + c] * k;
+    const float bl = r1[xlo * 3 + c] * k, br = r1[xhi * 3 + c] * k;
+    const float top = tl + (tr - tl) * lx;
+    const float bot = bl + (br - bl) * lx;
+    const float v = top + (bot - top) * ly;
+    out[static_cast<size_t>(idx) * 3 + c] = (v - 0.5f) * 2.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv0: 3x3 / stride 2 / VALID, Cin = 3 -> Cout = 32, + BN + ReLU (inception_model.py:86-87).
+// K = 27 is too small and 3 channels too narrow for TMA/UMMA; it is 0.3 % of the tower's MACs and
+// HBM-bound (reads fp32 input once, writes 16-bit output once).  One thread = one output pixel,
+// 32 fp32 accumulators; weights [27][32] broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+conv0_kernel(const float* __restrict__ in, int N, int H, int W, const float* __restrict__ wgt /*[27][32]*/,
+             const float* __restrict__ scale, const float* __restrict__ shift, uint16_t* __restrict__ out, int OH,
+             int OW, int fmt) {
+  __shared__ float sw[27 * 32];
+  __shared__ float ssc[32], ssh[32];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = wgt[i];
+  if (threadIdx.x < 32) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
+  __syncthreads();
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * OH * OW;
+  if (pix >= total) return;
+  const int ox = static_cast<int>(pix % OW);
+  const int oy = static_cast<int>((pix / OW) % OH);
+  const int n = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  const float* ip = in + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float x[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) x[j] = __ldg(ip + static_cast<size_t>(r) * W * 3 + j);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const float* wr = sw + (r * 9 + j) * 32;   // HWIO flattened: ((r*3+s)*3+ci)*32 + co, j = s*3+ci
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = fmaf(x[j], wr[c], acc[c]);
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * 32);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(acc[g * 8 + j], ssc[g * 8 + j], ssh[g * 8 + j]), 0.f);
+    op[g] = pack8(f, fmt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// max_pool 3x3 / stride 2 / VALID (ops.py:367-370).  Output may be a channel slice of a concat
+// buffer (ldo/coff).  One thread = one output pixel x 8 channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
+                                  uint16_t* __restrict__ out, int OH, int OW, int ldo, int coff, int fmt) {
+  const int cg = C / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * OH * OW * cg;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % cg);
+  const long long pix = idx / cg;
+  const int ox = static_cast<int>(pix % OW);
+  const int oy = static_cast<int>((pix / OW) % OH);
+  const int n = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const size_t off = ((static_cast<size_t>(n) * H + oy * 2 + r) * W + ox * 2 + s) * ldi + cin_off + g * 8;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + off));
+      float f[8];
+      unpack8(v, f, fmt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    }
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + coff + g * 8) = pack8(m, fmt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// avg_pool k x k, stride s; SAME (pad (k-1)/2, stride 1) divides by the number of in-bounds taps —
+// tf.nn.avg_pool semantics (ops.py:397-400) — VALID is a plain mean.  fp32 accumulation.
+// ---------------------------------------------------------------------------------------------
+__global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi,
+                               uint16_t* __restrict__ out, int OH, int OW, int ldo, int k, int stride, int pad,
+                               int fmt) {
+  const int cg = C / 8;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * OH * OW * cg;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % cg);
+  const long long pix = idx / cg;
+  const int ox = static_cast<int>(pix % OW);
+  const int oy = static_cast<int>((pix / OW) % OH);
+  const int n = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  int cnt = 0;
+  for (int r = 0; r < k; ++r) {
+    const int iy = oy * stride - pad + r;
+    if (iy < 0 || iy >= H) continue;
+    for (int s = 0; s < k; ++s) {
+      const int ix = ox * stride - pad + s;
+      if (ix < 0 || ix >= W) continue;
+      const size_t off = ((static_cast<size_t>(n) * H + iy) * W + ix) * ldi + g * 8;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + off));
+      float f[8];
+      unpack8(v, f, fmt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      ++cnt;
+    }
+  }
+  const float inv = 1.0f / static_cast<float>(cnt);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] *= inv;
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + g * 8) = pack8(acc, fmt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head (inception_model.py:318-329 + PyClassification.py:163-164): global average pool over
+// HW -> flatten -> fc [F, C] + bias -> softmax -> top-k of the probabilities (descending, ties to
+// the lower index).  One CTA per image, 256 threads.  Generic over F (2048 main head, 768 aux
+// head with hw = 1) and C; `probs == nullptr` skips softmax/top-k (aux logits only).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_kernel(const uint16_t* __restrict__ feat_map, int hw, int F, int ld, const float* __restrict__ fc_w /*[F][C]*/,
+            const float* __restrict__ fc_b, int C, float* __restrict__ logits, float* __restrict__ probs,
+            float* __restrict__ topk_val, int* __restrict__ topk_idx, int k, int fmt) {
+  extern __shared__ float sm[];
+  float* feat = sm;            // [F]
+  float* lg = sm + F;          // [C]
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const float inv = 1.0f / static_cast<float>(hw);
+  for (int g = tid; g < F / 8; g += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < hw; ++p) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(feat_map + (static_cast<size_t>(n) * hw + p) * ld + g * 8));
+      float f[8];
+      unpack8(v, f, fmt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) feat[g * 8 + j] = acc[j] * inv;
+  }
+  __syncthreads();
+  // fc: one warp per class, lanes stride the feature dimension (fc_w is [F][C], class fastest)
+  for (int c = warp; c < C; c += 8) {
+    float acc = 0.f;
+    for (int f = lane; f < F; f += 32) acc = fmaf(feat[f], __ldg(fc_w + static_cast<size_t>(f) * C + c), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      acc += fc_b[c];
+      lg[c] = acc;
+      logits[static_cast<size_t>(n) * C + c] = acc;
+    }
+  }
+  __syncthreads();
+  if (probs == nullptr) return;
+  // softmax (max-subtracted, fp32)
+  float mx = -FLT_MAX;
+  for (int c = tid; c < C; c += blockDim.x) mx = fmaxf(mx, lg[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float e = expf(lg[c] - mx);
+    lg[c] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  __syncthreads();
+  const float rs = 1.0f / sum;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float p = lg[c] * rs;
+    lg[c] = p;
+    probs[static_cast<size_t>(n) * C + c] = p;
+  }
+  __syncthreads();
+  // top-k by k rounds of block arg-max; taken entries are overwritten with -1 (probs are >= 0)
+  for (int i = 0; i < k; ++i) {
+    float bv = -2.f;
+    int bi = 0x7fffffff;
+    for (int c = tid; c < C; c += blockDim.x) {
+      const float v = lg[c];
+      if (v > bv || (v == bv && c < bi)) { bv = v; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red[warp] = bv; redi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float v = red[0];
+      int ix = redi[0];
+      for (int w = 1; w < 8; ++w)
+        if (red[w] > v || (red[w] == v && redi[w] < ix)) { v = red[w]; ix = redi[w]; }
+      topk_val[static_cast<size_t>(n) * k + i] = v;
+      topk_idx[static_cast<size_t>(n) * k + i] = ix;
+      lg[ix] = -1.f;
+    }
+    __syncthreads();
+  }
+}
+
+// dtype conversion helpers (host-facing debug taps and the single-layer entry point)
+__global__ void f32_to_h16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, size_t n, int fmt) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = f2h(in[i], fmt);
+}
+// strided gather of a channel slice: out[pix][c] = in[pix*ld + coff + c]
+__global__ void h16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, size_t pixels, int C,
+                                  int ld, int coff, int fmt) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= pixels * C) return;
+  const size_t p = i / C;
+  const int c = static_cast<int>(i % C);
+  out[i] = h2f(in[p * ld + coff + c], fmt);
+}
+
+}  // namespace icp
