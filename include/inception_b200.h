@@ -64,6 +64,26 @@ int icp_forward(icp_engine* e, const float* x_host, int n, float* probs_out_host
 int icp_forward_topk(icp_engine* e, const float* x_host, int n, int k, float* probs_out_host,
                      float* topk_vals_host, int32_t* topk_idx_host);
 
+/* Tower on host uint8 images already at network size (x[n,S,S,3], 0..255): the reference's
+ * convert_image_dtype and (x-0.5)*2 (PyClassification.py:152,154-155) are fused into the first
+ * conv; a quarter of icp_forward's host->device bytes.  Outputs as icp_forward_topk (k may be 0). */
+int icp_forward_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host,
+                   float* topk_vals_host, int32_t* topk_idx_host);
+
+/* Per-launch profile of the tower: op i of icp_num_ops() is one kernel launch.  icp_op_info gives its
+ * reference scope name, kind (ICP_OP_*), algorithmic FLOPs and algorithmic HBM bytes per image;
+ * icp_profile_forward runs the tower `reps` times on the engine's resident input with a CUDA event
+ * between consecutive launches and returns the mean device milliseconds of each. */
+#define ICP_OP_CONV0 0
+#define ICP_OP_CONV_IGEMM 1
+#define ICP_OP_MAXPOOL 2
+#define ICP_OP_AVGPOOL 3
+#define ICP_OP_HEAD 4
+int icp_num_ops(icp_engine* e, int* num_ops);
+int icp_op_info(icp_engine* e, int i, char* name, int name_cap, int* kind, double* flops_per_image,
+                double* bytes_per_image);
+int icp_profile_forward(icp_engine* e, int n, int reps, float* ms_per_op);
+
 /* Device-resident variant for batching / multi-GPU callers: x_dev float32 [n,S,S,3] and probs_dev
  * float32 [n,C] are device pointers on the engine's device; work is enqueued on `stream`
  * (a cudaStream_t, NULL = the engine's own stream) and NOT synchronised. */

@@ -211,6 +211,7 @@ struct ConvLayer {
   int pix_per_image = 0;   // oh * ow
   size_t smem = 0;
   long long macs_per_image = 0;
+  long long in_elems_per_image = 0;
 };
 
 static int pick_n_tile(int cout) {
@@ -259,6 +260,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.cout = cout;
   L.pix_per_image = oh * ow;
   L.macs_per_image = static_cast<long long>(oh) * ow * cout * kh * kw * cin;
+  L.in_elems_per_image = static_cast<long long>(in.h) * in.w * cin;
   const int cb = (cin + kBK - 1) / kBK;
   const int n_tile = pick_n_tile(cout);
   L.n_tiles = cout / n_tile;
@@ -361,6 +363,8 @@ struct icp_engine {
   int last_n = 0;
 
   float* d_input = nullptr;         // [max_batch, S, S, 3] f32
+  uint8_t* d_input_u8 = nullptr;    // [max_batch, S, S, 3] u8 (icp_forward_u8)
+  int graph_k = 5;
   uint8_t* d_rgb = nullptr;         // staging for icp_classify_rgb8
   size_t d_rgb_cap = 0;
   float* d_conv0_w = nullptr;       // [27][32]
@@ -644,20 +648,42 @@ static int run_op(const Op& op, int n, int fmt, cudaStream_t st) {
 }
 
 // Enqueue the whole tower for n images whose preprocessed fp32 input sits at x_dev.
-static int enqueue_tower(icp_engine& e, const float* x_dev, int n, int k, float* probs_dev, cudaStream_t st) {
+struct OpTimer {   // optional per-launch CUDA events (icp_profile_forward)
+  std::vector<cudaEvent_t>* ev = nullptr;
+  cudaStream_t st = nullptr;
+  void mark() {
+    if (!ev) return;
+    cudaEvent_t x;
+    CK(cudaEventCreate(&x));
+    ev->push_back(x);
+    CK(cudaEventRecord(x, st));
+  }
+};
+
+static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, int k, float* probs_dev,
+                         cudaStream_t st, OpTimer* tm = nullptr) {
   int launches = 0;
   const int fmt = e.fmt;
+  if (tm) tm->mark();
   {
     const Act& o = e.conv0_out;
     const long long pix = static_cast<long long>(n) * o.h * o.w;
-    conv0_kernel<<<static_cast<unsigned>((pix + 127) / 128), 128, 0, st>>>(x_dev, n, e.S, e.S, e.d_conv0_w,
-                                                                            e.d_conv0_scale, e.d_conv0_shift, o.p, o.h,
-                                                                            o.w, fmt);
+    const unsigned grid = static_cast<unsigned>((pix + 127) / 128);
+    if (x_is_u8)
+      conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev), n, e.S, e.S, e.d_conv0_w,
+                                                  e.d_conv0_scale, e.d_conv0_shift, o.p, o.h, o.w, fmt);
+    else
+      conv0_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x_dev), n, e.S, e.S, e.d_conv0_w,
+                                                e.d_conv0_scale, e.d_conv0_shift, o.p, o.h, o.w, fmt);
     CK(cudaGetLastError());
     ++launches;
+    if (tm) tm->mark();
   }
-  for (const Op& op : e.ops) launches += run_op(op, n, fmt, st);
-  if (e.cfg.enable_aux) {
+  for (const Op& op : e.ops) {
+    launches += run_op(op, n, fmt, st);
+    if (tm) tm->mark();
+  }
+  if (e.cfg.enable_aux && !tm) {
     for (const Op& op : e.aux_ops) launches += run_op(op, n, fmt, st);
     head_kernel<<<n, 256, (768 + e.C) * sizeof(float), st>>>(e.aux_feat.p, 1, 768, e.aux_feat.c, e.d_aux_w, e.d_aux_b,
                                                              e.C, e.d_aux_logits, nullptr, nullptr, nullptr, 0, fmt);
@@ -670,23 +696,25 @@ static int enqueue_tower(icp_engine& e, const float* x_dev, int n, int k, float*
                                                            e.d_topk_idx, k, fmt);
   CK(cudaGetLastError());
   ++launches;
+  if (tm) tm->mark();
   return launches;
 }
 
-static void run_tower(icp_engine& e, const float* x_dev, int n, int k, float* probs_dev, cudaStream_t st,
-                      bool timed) {
+static void run_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, int k, float* probs_dev,
+                      cudaStream_t st, bool timed) {
   if (n < 1 || n > e.max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e.max_batch);
   if (k < 0 || k > 16 || k > e.C) fail(ICP_E_INVALID, "k=%d outside [0, min(16, %d)]", k, e.C);
   e.last_n = n;
   if (timed) CK(cudaEventRecord(e.ev0, st));
-  const bool graphable = e.cfg.use_cuda_graph && x_dev == e.d_input && probs_dev == nullptr && k == 5;
+  const bool graphable = e.cfg.use_cuda_graph && (x_dev == e.d_input || x_dev == e.d_input_u8) &&
+                         probs_dev == nullptr && k == e.graph_k;
   if (graphable) {
-    auto it = e.graphs.find(n);
+    auto it = e.graphs.find(n * 2 + (x_is_u8 ? 1 : 0));
     if (it == e.graphs.end()) {
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       try {
-        e.launches = enqueue_tower(e, x_dev, n, k, nullptr, st);
+        e.launches = enqueue_tower(e, x_dev, x_is_u8, n, k, nullptr, st);
       } catch (...) {
         cudaStreamEndCapture(st, &g);
         if (g) cudaGraphDestroy(g);
@@ -696,11 +724,11 @@ static void run_tower(icp_engine& e, const float* x_dev, int n, int k, float* pr
       cudaGraphExec_t ge = nullptr;
       CK(cudaGraphInstantiate(&ge, g, 0));
       cudaGraphDestroy(g);
-      it = e.graphs.emplace(n, ge).first;
+      it = e.graphs.emplace(n * 2 + (x_is_u8 ? 1 : 0), ge).first;
     }
     CK(cudaGraphLaunch(it->second, st));
   } else {
-    e.launches = enqueue_tower(e, x_dev, n, k, probs_dev, st);
+    e.launches = enqueue_tower(e, x_dev, x_is_u8, n, k, probs_dev, st);
   }
   if (timed) CK(cudaEventRecord(e.ev1, st));
 }
@@ -772,6 +800,8 @@ int icp_create(const icp_config* cfg, icp_engine** out) {
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
     e->d_input = static_cast<float*>(e->pool.alloc(static_cast<size_t>(e->max_batch) * e->S * e->S * 3 * 4));
+    e->d_input_u8 = static_cast<uint8_t*>(e->pool.alloc(static_cast<size_t>(e->max_batch) * e->S * e->S * 3));
+    e->graph_k = e->C < 5 ? e->C : 5;
     Builder b{*e, blob, e->fmt, e->max_batch};
     b.build();
     CK(cudaDeviceSynchronize());
@@ -796,7 +826,7 @@ int icp_forward_topk(icp_engine* e, const float* x_host, int n, int k, float* pr
     if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
     const size_t in_bytes = static_cast<size_t>(n) * e->S * e->S * 3 * 4;
     CK(cudaMemcpyAsync(e->d_input, x_host, in_bytes, cudaMemcpyHostToDevice, e->stream));
-    run_tower(*e, e->d_input, n, k > 0 ? k : (e->C < 5 ? e->C : 5), nullptr, e->stream, true);
+    run_tower(*e, e->d_input, false, n, k > 0 ? k : e->graph_k, nullptr, e->stream, true);
     const int kk = k > 0 ? k : 0;
     if (probs_out_host)
       CK(cudaMemcpyAsync(probs_out_host, e->d_probs, static_cast<size_t>(n) * e->C * 4, cudaMemcpyDeviceToHost,
@@ -822,7 +852,7 @@ int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_de
     if (!x_dev) fail(ICP_E_INVALID, "null input");
     CK(cudaSetDevice(e->cfg.device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
-    run_tower(*e, x_dev, n, e->C < 5 ? e->C : 5, probs_dev, st, false);
+    run_tower(*e, x_dev, false, n, e->graph_k, probs_dev, st, false);
   });
 }
 
@@ -861,11 +891,117 @@ int icp_classify_rgb8(icp_engine* e, const uint8_t* rgb, int h, int w, int k, fl
     if (k < 1) fail(ICP_E_INVALID, "k must be >= 1");
     CK(cudaSetDevice(e->cfg.device));
     preprocess_to_input(e, rgb, h, w);
-    run_tower(*e, e->d_input, 1, k, nullptr, e->stream, true);
+    run_tower(*e, e->d_input, false, 1, k, nullptr, e->stream, true);
     CK(cudaMemcpyAsync(topk_vals, e->d_topk_val, k * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(topk_idx, e->d_topk_idx, k * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+int icp_forward_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host, float* topk_vals_host,
+                   int32_t* topk_idx_host) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!x_host) fail(ICP_E_INVALID, "null input");
+    CK(cudaSetDevice(e->cfg.device));
+    if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
+    const size_t in_bytes = static_cast<size_t>(n) * e->S * e->S * 3;
+    CK(cudaMemcpyAsync(e->d_input_u8, x_host, in_bytes, cudaMemcpyHostToDevice, e->stream));
+    run_tower(*e, e->d_input_u8, true, n, k > 0 ? k : e->graph_k, nullptr, e->stream, true);
+    const int kk = k > 0 ? k : 0;
+    if (probs_out_host)
+      CK(cudaMemcpyAsync(probs_out_host, e->d_probs, static_cast<size_t>(n) * e->C * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    if (kk && topk_vals_host)
+      CK(cudaMemcpyAsync(topk_vals_host, e->d_topk_val, static_cast<size_t>(n) * kk * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    if (kk && topk_idx_host)
+      CK(cudaMemcpyAsync(topk_idx_host, e->d_topk_idx, static_cast<size_t>(n) * kk * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+int icp_num_ops(icp_engine* e, int* num_ops) {
+  if (!e || !num_ops) return ICP_E_INVALID;
+  *num_ops = static_cast<int>(e->ops.size()) + 2;   // conv0 + plan + head
+  return ICP_OK;
+}
+
+int icp_op_info(icp_engine* e, int i, char* name, int name_cap, int* kind, double* flops_per_image,
+                double* bytes_per_image) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    const int nops = static_cast<int>(e->ops.size()) + 2;
+    if (i < 0 || i >= nops) fail(ICP_E_INVALID, "op index %d outside [0, %d)", i, nops);
+    std::string nm;
+    int kd = 0;
+    double fl = 0, by = 0;
+    if (i == 0) {
+      const Act& o = e->conv0_out;
+      nm = "conv0"; kd = ICP_OP_CONV0;
+      fl = 2.0 * o.h * o.w * 32 * 27;
+      by = static_cast<double>(e->S) * e->S * 3 * 4 + static_cast<double>(o.h) * o.w * 32 * 2;
+    } else if (i == nops - 1) {
+      const Act& f = e->final_act;
+      nm = "head"; kd = ICP_OP_HEAD;
+      fl = 2.0 * f.c * e->C;
+      by = static_cast<double>(f.h) * f.w * f.c * 2;
+    } else {
+      const Op& op = e->ops[i - 1];
+      if (op.kind == Op::CONV) {
+        const ConvLayer& L = op.conv;
+        nm = L.name; kd = ICP_OP_CONV_IGEMM;
+        fl = 2.0 * static_cast<double>(L.macs_per_image);
+        const double k = static_cast<double>(L.macs_per_image) / (static_cast<double>(L.pix_per_image) * L.cout);
+        // algorithmic traffic: input read once + output written once (weights amortised over the batch)
+        by = static_cast<double>(L.in_elems_per_image) * 2 + static_cast<double>(L.pix_per_image) * L.cout * 2;
+        (void)k;
+      } else {
+        nm = op.kind == Op::MAXPOOL ? "max_pool" : "avg_pool"; kd = op.kind == Op::MAXPOOL ? ICP_OP_MAXPOOL : ICP_OP_AVGPOOL;
+        fl = 0;
+        by = static_cast<double>(op.in.h) * op.in.w * op.c * 2 + static_cast<double>(op.out.h) * op.out.w * op.c * 2;
+      }
+    }
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", nm.c_str());
+    if (kind) *kind = kd;
+    if (flops_per_image) *flops_per_image = fl;
+    if (bytes_per_image) *bytes_per_image = by;
+  });
+}
+
+int icp_profile_forward(icp_engine* e, int n, int reps, float* ms_per_op) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!ms_per_op || reps < 1) fail(ICP_E_INVALID, "bad argument");
+    if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
+    CK(cudaSetDevice(e->cfg.device));
+    const int nops = static_cast<int>(e->ops.size()) + 2;
+    std::vector<double> acc(nops, 0.0);
+    for (int r = 0; r < reps; ++r) {
+      std::vector<cudaEvent_t> ev;
+      OpTimer tm{&ev, e->stream};
+      cudaError_t err = cudaSuccess;
+      try {
+        enqueue_tower(*e, e->d_input, false, n, e->graph_k, nullptr, e->stream, &tm);
+        err = cudaStreamSynchronize(e->stream);
+      } catch (...) {
+        for (cudaEvent_t x : ev) cudaEventDestroy(x);
+        throw;
+      }
+      if (err == cudaSuccess && static_cast<int>(ev.size()) == nops + 1) {
+        for (int i = 0; i < nops; ++i) {
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+          acc[i] += ms;
+        }
+      }
+      for (cudaEvent_t x : ev) cudaEventDestroy(x);
+      if (err != cudaSuccess) fail(ICP_E_CUDA, "profile run failed: %s", cudaGetErrorString(err));
+    }
+    for (int i = 0; i < nops; ++i) ms_per_op[i] = static_cast<float>(acc[i] / reps);
   });
 }
 

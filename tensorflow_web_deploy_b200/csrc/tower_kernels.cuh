@@ -72,8 +72,20 @@ __global__ void preprocess_u8_kernel(const uint8_t* __restrict__ img, int H, int
 // HBM-bound (reads fp32 input once, writes 16-bit output once).  One thread = one output pixel,
 // 32 fp32 accumulators; weights [27][32] broadcast from shared memory.
 // ---------------------------------------------------------------------------------------------
+// TIn = float: input already normalised to [-1,1]; TIn = uint8_t: raw pixels, the reference's
+// convert_image_dtype + (x-0.5)*2 (PyClassification.py:152,154-155) is applied on the fly.
+template <typename TIn>
+__device__ __forceinline__ float conv0_load(const TIn* p);
+template <>
+__device__ __forceinline__ float conv0_load<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float conv0_load<uint8_t>(const uint8_t* p) {
+  return (static_cast<float>(__ldg(p)) * 0.003921568859368563f - 0.5f) * 2.0f;
+}
+
+template <typename TIn>
 __global__ void __launch_bounds__(128)
-conv0_kernel(const float* __restrict__ in, int N, int H, int W, const float* __restrict__ wgt /*[27][32]*/,
+conv0_kernel(const TIn* __restrict__ in, int N, int H, int W, const float* __restrict__ wgt /*[27][32]*/,
              const float* __restrict__ scale, const float* __restrict__ shift, uint16_t* __restrict__ out, int OH,
              int OW, int fmt) {
   __shared__ float sw[27 * 32];
@@ -90,12 +102,12 @@ conv0_kernel(const float* __restrict__ in, int N, int H, int W, const float* __r
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-  const float* ip = in + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
+  const TIn* ip = in + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     float x[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) x[j] = __ldg(ip + static_cast<size_t>(r) * W * 3 + j);
+    for (int j = 0; j < 9; ++j) x[j] = conv0_load<TIn>(ip + static_cast<size_t>(r) * W * 3 + j);
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const float* wr = sw + (r * 9 + j) * 32;   // HWIO flattened: ((r*3+s)*3+ci)*32 + co, j = s*3+ci

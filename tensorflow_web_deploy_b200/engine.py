@@ -44,6 +44,11 @@ SIGNATURES = {
     "icp_destroy": (None, [C.c_void_p]),
     "icp_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, _f32p]),
     "icp_forward_topk": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _i32p]),
+    "icp_forward_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p, _f32p, _i32p]),
+    "icp_num_ops": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "icp_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                              C.POINTER(C.c_double)]),
+    "icp_profile_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p]),
     "icp_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "icp_classify_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _f32p, _i32p]),
     "icp_preprocess_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p]),
@@ -130,6 +135,41 @@ class Engine:
         _check(self._lib.icp_forward_topk(self._h, _f32(x), n, k, _f32(probs), _f32(vals),
                                           idx.ctypes.data_as(_i32p)), self._h)
         return probs, vals, idx
+
+    def forward_u8(self, x: np.ndarray, k: int = 5) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """x uint8 [n,S,S,3] (0..255, already at network size) -> (probs [n,C], vals [n,k], idx [n,k])."""
+        x = np.ascontiguousarray(x, np.uint8)
+        s = self.image_size
+        if x.ndim != 4 or x.shape[1:] != (s, s, 3):
+            raise ValueError("expected uint8 [n,%d,%d,3], got %s" % (s, s, x.shape))
+        n = x.shape[0]
+        probs = np.empty((n, self.num_classes), np.float32)
+        vals = np.empty((n, k), np.float32)
+        idx = np.empty((n, k), np.int32)
+        _check(self._lib.icp_forward_u8(self._h, x.ctypes.data_as(_u8p), n, k, _f32(probs), _f32(vals),
+                                        idx.ctypes.data_as(_i32p)), self._h)
+        return probs, vals, idx
+
+    def op_table(self):
+        """[(name, kind, flops_per_image, bytes_per_image)] for every launch of one forward pass."""
+        n = C.c_int()
+        _check(self._lib.icp_num_ops(self._h, C.byref(n)), self._h)
+        out = []
+        for i in range(n.value):
+            buf = C.create_string_buffer(160)
+            kind, fl, by = C.c_int(), C.c_double(), C.c_double()
+            _check(self._lib.icp_op_info(self._h, i, buf, 160, C.byref(kind), C.byref(fl), C.byref(by)), self._h)
+            out.append((buf.value.decode(), kind.value, fl.value, by.value))
+        return out
+
+    def profile_forward(self, n: int, reps: int = 5) -> np.ndarray:
+        """Mean device milliseconds of each launch (CUDA events between launches) at batch n, on the
+        input of the previous forward call."""
+        nops = C.c_int()
+        _check(self._lib.icp_num_ops(self._h, C.byref(nops)), self._h)
+        ms = np.zeros(nops.value, np.float32)
+        _check(self._lib.icp_profile_forward(self._h, n, reps, _f32(ms)), self._h)
+        return ms
 
     def forward_device(self, x_ptr: int, n: int, probs_ptr: int = 0, stream: int = 0) -> None:
         """Enqueue (no sync) on device pointers; see icp_forward_device."""
