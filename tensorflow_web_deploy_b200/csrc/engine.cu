@@ -14,6 +14,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/inception_b200.h"
@@ -348,6 +349,17 @@ struct Endpoint {
 using namespace icp;
 
 // ------------------------------------------------------------------------------------------ engine
+struct GraphKey {
+  int n;
+  const void* x;
+  bool u8;
+  const void* probs;
+  int k;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(n, x, u8, probs, k) < std::tie(o.n, o.x, o.u8, o.probs, o.k);
+  }
+};
+
 struct icp_engine {
   icp_config cfg{};
   std::string weights_path;
@@ -380,7 +392,7 @@ struct icp_engine {
   Act aux_feat;                     // 1x1x768
   float *d_aux_w = nullptr, *d_aux_b = nullptr, *d_aux_logits = nullptr;
   std::map<std::string, Endpoint> endpoints;
-  std::map<int, cudaGraphExec_t> graphs;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
   int launches = 0;
   long long conv_macs_per_image = 0;
 
@@ -706,15 +718,20 @@ static void run_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, int
   if (k < 0 || k > 16 || k > e.C) fail(ICP_E_INVALID, "k=%d outside [0, min(16, %d)]", k, e.C);
   e.last_n = n;
   if (timed) CK(cudaEventRecord(e.ev0, st));
-  const bool graphable = e.cfg.use_cuda_graph && (x_dev == e.d_input || x_dev == e.d_input_u8) &&
-                         probs_dev == nullptr && k == e.graph_k;
-  if (graphable) {
-    auto it = e.graphs.find(n * 2 + (x_is_u8 ? 1 : 0));
+  if (e.cfg.use_cuda_graph) {
+    // one captured graph per distinct (batch, input buffer, output buffer, k): replay removes the
+    // ~110 launch latencies that dominate small batches
+    const GraphKey key{n, x_dev, x_is_u8, probs_dev, k};
+    auto it = e.graphs.find(key);
     if (it == e.graphs.end()) {
+      if (e.graphs.size() >= 64) {
+        for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+        e.graphs.clear();
+      }
       cudaGraph_t g = nullptr;
       CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       try {
-        e.launches = enqueue_tower(e, x_dev, x_is_u8, n, k, nullptr, st);
+        e.launches = enqueue_tower(e, x_dev, x_is_u8, n, k, probs_dev, st);
       } catch (...) {
         cudaStreamEndCapture(st, &g);
         if (g) cudaGraphDestroy(g);
@@ -724,7 +741,7 @@ static void run_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, int
       cudaGraphExec_t ge = nullptr;
       CK(cudaGraphInstantiate(&ge, g, 0));
       cudaGraphDestroy(g);
-      it = e.graphs.emplace(n * 2 + (x_is_u8 ? 1 : 0), ge).first;
+      it = e.graphs.emplace(key, ge).first;
     }
     CK(cudaGraphLaunch(it->second, st));
   } else {

@@ -1,0 +1,274 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  `pytest -m gpu` on a B200.
+
+Tolerances (the north_star's bar is top-k labels equal and scores within 1e-3):
+  * fp16 mode: |dprob| <= 1e-3 on every class, top-5 labels identical  — the parity mode;
+  * bf16 mode: |dprob| <= 6e-3 (8-bit mantissa through 47 conv layers gives ~1 % relative feature
+    error; measured 2.7e-3), top-5 labels identical on these inputs;
+  * single layers: inputs/weights pre-rounded to the storage type, so only the fp32 accumulation
+    order and the final 16-bit rounding differ: 1 ulp of the storage type.
+"""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = {"fp16": 1e-3, "bf16": 6e-3}
+LAYER_TOL = {"fp16": 2e-3, "bf16": 1.6e-2}      # relative to (1 + |ref|): one ulp of fp16 / bf16
+
+
+def round16(a, precision):
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(torch.float32).numpy()
+
+
+def ref_conv(x, w, scale, shift, stride, same, precision):
+    xq, wq = round16(x, precision), round16(w, precision)
+    kh, kw = w.shape[:2]
+    pad = ((kh - 1) // 2, (kw - 1) // 2) if same else (0, 0)
+    y = F.conv2d(torch.from_numpy(xq.transpose(0, 3, 1, 2).copy()), torch.from_numpy(wq.transpose(3, 2, 0, 1).copy()),
+                 None, stride, pad)
+    y = torch.relu(y * torch.from_numpy(scale).view(1, -1, 1, 1) + torch.from_numpy(shift).view(1, -1, 1, 1))
+    return round16(y.numpy().transpose(0, 2, 3, 1), precision)
+
+
+def _layer_shapes():
+    from tensorflow_web_deploy_b200 import tower_spec as T
+    seen, out = set(), []
+    for L in T.conv_layers():
+        if L.name == "conv0":
+            continue
+        key = (L.in_h, L.in_w, L.cin, L.kh, L.kw, L.cout, L.stride, L.same)
+        if key not in seen:
+            seen.add(key)
+            out.append(pytest.param(key, id="%s_%dx%dx%d_k%dx%d_o%d_s%d_%s" % (
+                L.name.replace("/", "."), L.in_h, L.in_w, L.cin, L.kh, L.kw, L.cout, L.stride, "S" if L.same else "V")))
+    return out
+
+
+@pytest.fixture(scope="module")
+def eng_mod(built_lib):
+    from tensorflow_web_deploy_b200 import engine
+    return engine
+
+
+@pytest.mark.parametrize("shape", _layer_shapes())
+def test_every_tower_layer_shape(eng_mod, shape):
+    """BASELINE configs[2] sweep: each distinct conv+BN+ReLU layer geometry of the tower, one image."""
+    h, w, cin, kh, kw, cout, stride, same = shape
+    rng = np.random.default_rng(hash(shape) % (2 ** 32))
+    x = rng.standard_normal((1, h, w, cin), dtype=np.float32)
+    wt = rng.standard_normal((kh, kw, cin, cout), dtype=np.float32) * np.float32(np.sqrt(2.0 / (kh * kw * cin)))
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    precision = "fp16"
+    y, _ = eng_mod.conv2d_bn_relu(x, wt, scale, shift, stride, same, True, precision)
+    ref = ref_conv(x, wt, scale, shift, stride, same, precision)
+    assert y.shape == ref.shape
+    assert not np.isnan(y).any()
+    assert (np.abs(y - ref) <= LAYER_TOL[precision] * (1 + np.abs(ref))).all()
+
+
+EDGE_CASES = [
+    # n, h, w, cin, kh, kw, cout, stride, same   — ragged M tiles, channel tails, tiny maps, multi-image wrap
+    (1, 8, 16, 64, 1, 1, 64, 1, True),          # exactly one 128-row tile
+    (3, 17, 17, 768, 1, 1, 192, 1, True),       # M = 867: tile straddles images
+    (2, 35, 35, 48, 5, 5, 64, 1, True),         # Cin = 48 < 64: TMA zero-fills the channel tail
+    (1, 25, 25, 80, 3, 3, 192, 1, False),       # Cin = 80: one full + one partial channel block
+    (2, 35, 35, 288, 3, 3, 384, 2, False),      # stride 2, two N tiles
+    (5, 8, 8, 448, 3, 3, 384, 1, True),
+    (1, 3, 3, 64, 3, 3, 32, 1, True),           # map smaller than the filter's reach
+    (3, 5, 5, 128, 5, 5, 768, 1, False),        # full-size VALID kernel -> 1x1 output, three N tiles
+    (2, 17, 17, 160, 7, 1, 192, 1, True),
+    (2, 17, 17, 128, 1, 7, 128, 1, True),
+    (1, 1, 1, 64, 1, 1, 16, 1, True),           # single pixel, smallest legal N
+    (7, 9, 11, 24, 3, 3, 48, 1, True),          # Cin = 24 (multiple of 8 only)
+]
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", EDGE_CASES, ids=lambda c: "n%d_%dx%dx%d_k%dx%d_o%d_s%d_%s" % (c[:8] + ("S" if c[8] else "V",)))
+def test_conv_edge_cases(eng_mod, case, precision):
+    n, h, w, cin, kh, kw, cout, stride, same = case
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, h, w, cin), dtype=np.float32)
+    wt = rng.standard_normal((kh, kw, cin, cout), dtype=np.float32) * np.float32(np.sqrt(2.0 / (kh * kw * cin)))
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    y, _ = eng_mod.conv2d_bn_relu(x, wt, scale, shift, stride, same, True, precision)
+    ref = ref_conv(x, wt, scale, shift, stride, same, precision)
+    assert not np.isnan(y).any()
+    assert (np.abs(y - ref) <= LAYER_TOL[precision] * (1 + np.abs(ref))).all()
+
+
+def test_conv_linearity_and_no_relu(eng_mod):
+    """Size-independent property: without ReLU/shift the layer is linear in its input (exactly so for
+    power-of-two scalings of the 16-bit input)."""
+    rng = np.random.default_rng(5)
+    x = round16(rng.standard_normal((2, 17, 17, 128), dtype=np.float32), "fp16")
+    wt = rng.standard_normal((1, 7, 128, 128), dtype=np.float32) * 0.05
+    one, zero = np.ones(128, np.float32), np.zeros(128, np.float32)
+    y1, _ = eng_mod.conv2d_bn_relu(x, wt, one, zero, 1, True, False, "fp16")
+    y2, _ = eng_mod.conv2d_bn_relu(2 * x, wt, one, zero, 1, True, False, "fp16")
+    assert (y1 < 0).any()                                     # ReLU really was off
+    np.testing.assert_array_equal(y2, 2 * y1)
+    y3, _ = eng_mod.conv2d_bn_relu(x, wt, 0.5 * one, zero, 1, True, False, "fp16")
+    np.testing.assert_allclose(y3, 0.5 * y1, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_pools(eng_mod, precision):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 17, 17, 64), dtype=np.float32)
+    xq = torch.from_numpy(round16(x, precision).transpose(0, 3, 1, 2).copy())
+    y = eng_mod.pool2d(x, "max", precision=precision)                       # ops.py:367-370
+    np.testing.assert_array_equal(y, F.max_pool2d(xq, 3, 2).numpy().transpose(0, 2, 3, 1))
+    y = eng_mod.pool2d(x, "avg", 3, 1, True, precision=precision)           # SAME: exclude-pad divisor
+    ref = round16(F.avg_pool2d(xq, 3, 1, 1, count_include_pad=False).numpy().transpose(0, 2, 3, 1), precision)
+    assert (np.abs(y - ref) <= LAYER_TOL[precision] * (1 + np.abs(ref))).all()
+    y = eng_mod.pool2d(x, "avg", 5, 3, False, precision=precision)          # aux head 5x5/3 VALID
+    ref = round16(F.avg_pool2d(xq, 5, 3).numpy().transpose(0, 2, 3, 1), precision)
+    assert (np.abs(y - ref) <= LAYER_TOL[precision] * (1 + np.abs(ref))).all()
+    ones = eng_mod.pool2d(np.ones((1, 5, 5, 8), np.float32), "avg", 3, 1, True, precision=precision)
+    np.testing.assert_array_equal(ones, 1.0)                                # corners are 4/4, not 4/9
+
+
+# ----------------------------------------------------------------------------------------------- tower
+@pytest.fixture(scope="module")
+def oracle_run(synth6):
+    from oracle import inception_oracle as O
+    _, W = synth6
+    x = np.random.default_rng(0).uniform(-1, 1, (2, 299, 299, 3)).astype(np.float32)
+    tw = O.Tower(W)
+    logits, pred = tw.forward(x, 6, with_aux=True)
+    return x, tw.end_points, pred
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_tower_matches_oracle_and_golden(eng_mod, synth6, oracle_run, precision):
+    from oracle import inception_oracle as O
+    x, ep, pred = oracle_run
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=2, precision=precision, enable_aux=True)
+    probs, vals, idx = eng.forward_topk(x, 5)
+    ov, oi = O.top_k(pred, 5)
+    assert np.abs(probs - pred).max() <= PROB_TOL[precision]
+    np.testing.assert_array_equal(idx, oi)                      # top-k labels identical
+    assert np.abs(vals - ov).max() <= PROB_TOL[precision]
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
+    g = np.load(os.path.join(GOLDEN, "oracle_c6.npz"))          # committed fixture, same seeds
+    assert np.abs(probs - g["predictions"]).max() <= PROB_TOL[precision]
+    np.testing.assert_array_equal(idx, g["topk_idx"])
+    rel_lim = 2.5e-3 if precision == "fp16" else 2e-2
+    for k in ep:                                                # every end point of the reference's dict
+        got = eng.endpoint(k)
+        ref = ep[k]
+        assert got.shape == ref.shape, k
+        assert not np.isnan(got).any(), k
+        rel = np.sqrt(((got - ref) ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-12)
+        assert rel <= rel_lim, (k, rel)
+    assert eng.launches_per_forward >= 100
+    eng.close()
+
+
+def test_ragged_batches_and_batch_invariance(eng_mod, synth6):
+    """Each image's result is independent of the batch it rides in (inference BN, ops.py:122-125):
+    bit-exact across batch sizes, positions, CUDA-graph replay and input dtype path."""
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-1, 1, (5, 299, 299, 3)).astype(np.float32)
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=5, precision="fp16")
+    full = eng.forward(x)
+    for n in (1, 3):                                            # ragged: n < max_batch, M tiles partially filled
+        np.testing.assert_array_equal(eng.forward(x[:n]), full[:n])
+    perm = np.array([3, 0, 4, 2, 1])
+    np.testing.assert_array_equal(eng.forward(x[perm]), full[perm])
+    np.testing.assert_array_equal(eng.forward(x[4:5]), full[4:5])
+    geng = eng_mod.Engine(synth6[0], 6, max_batch=5, precision="fp16", use_cuda_graph=True)
+    for _ in range(2):                                          # capture, then replay
+        np.testing.assert_array_equal(geng.forward(x), full)
+    np.testing.assert_array_equal(geng.forward(x[:2]), full[:2])
+    with pytest.raises(eng_mod.EngineError) as ei:
+        eng.forward(np.zeros((6, 299, 299, 3), np.float32))     # > max_batch
+    assert ei.value.code == -1
+    with pytest.raises(ValueError):
+        eng.forward(np.zeros((1, 64, 64, 3), np.float32))
+    eng.close(); geng.close()
+
+
+def test_u8_entry_matches_float_entry(eng_mod, synth6):
+    rng = np.random.default_rng(6)
+    u8 = rng.integers(0, 256, (3, 299, 299, 3), dtype=np.uint8)
+    xf = (u8.astype(np.float32) * np.float32(1.0 / 255) - np.float32(0.5)) * np.float32(2.0)   # PyClassification.py:152-155
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=3, precision="fp16")
+    pf = eng.forward(xf)
+    pu, vals, idx = eng.forward_u8(u8, 5)
+    assert np.abs(pf - pu).max() <= 2e-4
+    np.testing.assert_array_equal(idx, np.argsort(-pu, axis=1, kind="stable")[:, :5])
+    np.testing.assert_array_equal(vals, np.take_along_axis(pu, idx, 1))
+    eng.close()
+
+
+def test_full_size_batch_properties(eng_mod, synth6):
+    """BASELINE size (128 images, bf16): size-independent properties instead of a 4-minute oracle run."""
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1, 1, (128, 299, 299, 3)).astype(np.float32)
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=128, precision="bf16", use_cuda_graph=True)
+    p = eng.forward(x)
+    assert p.shape == (128, 6) and np.isfinite(p).all()
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
+    for i in (0, 77, 127):                                      # an image alone == the image in the batch
+        np.testing.assert_array_equal(eng.forward(x[i:i + 1]), p[i:i + 1])
+    perm = rng.permutation(128)
+    np.testing.assert_array_equal(eng.forward(x[perm]), p[perm])
+    eng.close()
+
+
+# ----------------------------------------------------------------------------------------------- request path
+def test_preprocess_and_classify_request(eng_mod, synth6):
+    from oracle import inception_oracle as O
+    g = np.load(os.path.join(GOLDEN, "oracle_c6.npz"))
+    img = g["pre_img"]                                          # 500x375, the geometry of the reference's sample.jpg
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=1, precision="fp16")
+    pre = eng.preprocess_rgb8(img)
+    ref = O.preprocess_u8(img)[0]
+    assert np.abs(pre - ref).max() <= 2e-6                      # fp32 both sides; FMA contraction only
+    vals, idx = eng.classify_rgb8(img, 5)
+    np.testing.assert_array_equal(idx, g["pre_topk_idx"][0])
+    assert np.abs(vals - g["pre_topk_vals"][0]).max() <= 1e-3
+    for shape in ((16, 16, 3), (299, 299, 3), (1000, 37, 3)):   # odd geometries
+        im = np.random.default_rng(9).integers(0, 256, shape, dtype=np.uint8)
+        assert np.abs(eng.preprocess_rgb8(im) - O.preprocess_u8(im)[0]).max() <= 2e-6
+    with pytest.raises(eng_mod.EngineError):
+        eng.classify_rgb8(np.zeros((4, 4, 3), np.uint8), 5)
+    eng.close()
+
+
+def test_imagenet_classifier_drop_in(synth6, tmp_path, built_lib):
+    """configs[0]: a JPEG through ImagenetClassifier.classify_image (PyClassification.py:205-218)."""
+    from PIL import Image
+    from oracle import inception_oracle as O
+    from tensorflow_web_deploy_b200 import PyClassification as P
+    path, W = synth6
+    labels = tmp_path / "synset.txt"
+    labels.write_text("daisy\ndandelion\nroses\nsunflowers\ntulips\n")      # the reference's flowers-5 label set
+    g = np.load(os.path.join(GOLDEN, "oracle_c6.npz"))
+    buf = io.BytesIO()
+    Image.fromarray(g["pre_img"]).save(buf, "JPEG", quality=92)
+    jpeg = buf.getvalue()
+    clf = P.ImagenetClassifier(path, str(labels))
+    out = clf.classify_image(jpeg)
+    assert out is not None
+    names, probs, secs, acc = out
+    decoded = np.asarray(Image.open(io.BytesIO(jpeg)).convert("RGB"))
+    onames, oprobs, oacc = O.OracleClassifier(W, clf.label_names, 6).classify_decoded(decoded)
+    assert names == onames and set(names) <= set(clf.label_names)
+    assert np.abs(probs - oprobs).max() <= 1e-3 and abs(acc - oacc) <= 2e-3
+    assert probs.dtype == np.float32 and len(probs) == 3 and secs > 0
+    assert acc == pytest.approx(float(np.sum(np.sort(np.float32(
+        clf.engine.classify_rgb8(decoded, 5)[0])))), abs=1e-6)
+    assert clf.classify_image(b"garbage") is None

@@ -1,0 +1,79 @@
+"""Host-side mirror of PyClassification.ImagenetClassifier (reference :133-218) with the engine faked:
+the drop-in contract — return tuple, label table, None-on-error — does not need a GPU."""
+import io
+
+import numpy as np
+import pytest
+
+from tensorflow_web_deploy_b200 import PyClassification as P
+
+
+class FakeEngine:
+    def __init__(self, *a, **k):
+        self.args, self.kw = a, k
+        self.calls = []
+
+    def classify_rgb8(self, rgb, k):
+        self.calls.append(rgb.shape)
+        return np.float32([0.5, 0.25, 0.125, 0.0625, 0.03125])[:k], np.int32([3, 0, 5, 1, 2])[:k]
+
+    def preprocess_rgb8(self, rgb):
+        return np.zeros((299, 299, 3), np.float32)
+
+
+def _jpeg(h=60, w=80, mode="RGB"):
+    from PIL import Image
+    arr = np.random.default_rng(0).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    im = Image.fromarray(arr).convert(mode)
+    buf = io.BytesIO()
+    im.save(buf, "JPEG")
+    return buf.getvalue()
+
+
+@pytest.fixture
+def clf(monkeypatch, tmp_path):
+    monkeypatch.setattr(P._engine, "Engine", FakeEngine)
+    labels = tmp_path / "synset.txt"
+    labels.write_text("daisy\ndandelion\nroses\nsunflowers\ntulips\n")
+    model = tmp_path / "model"
+    model.write_bytes(b"x")
+    return P.ImagenetClassifier(str(model), str(labels))
+
+
+def test_label_table_and_engine_config(clf):
+    assert clf.label_names == ["none", "daisy", "dandelion", "roses", "sunflowers", "tulips"]   # :175-178
+    assert clf.engine.kw["num_classes"] == 6                                                    # NUM_CLASSES + 1
+    assert P.NUM_CLASSES == 5 and P.NUM_TOP_CLASSES == 5
+    assert set(P.ImagenetClassifier.default_args) == {"model_def_file", "class_labels_file"}
+
+
+def test_classify_image_return_contract(clf):
+    out = clf.classify_image(_jpeg())
+    names, probs, secs, acc = out                     # callers unpack 4 values (:54)
+    assert names == ["roses", "none", "tulips"]       # label_names[idx[0..2]]
+    assert isinstance(probs, np.ndarray) and probs.dtype == np.float32 and probs.tolist() == [0.5, 0.25, 0.125]
+    assert isinstance(secs, float) and secs >= 0
+    assert acc == pytest.approx(0.96875)              # sum of the top-5 probabilities (:215)
+    assert clf.engine.calls == [(60, 80, 3)]
+    assert list(zip(names, probs))                    # handlers zip them (:78,111)
+
+
+def test_grayscale_jpeg_is_expanded_to_rgb(clf):
+    assert clf.classify_image(_jpeg(mode="L")) is not None
+    assert clf.engine.calls[-1] == (60, 80, 3)        # decode_jpeg(channels=3)
+
+
+def test_errors_return_none(clf, monkeypatch):
+    assert clf.classify_image(b"definitely not a jpeg") is None        # :216-218
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.new("RGB", (8, 8)).save(buf, "PNG")
+    assert clf.classify_image(buf.getvalue()) is None                   # graph only has DecodeJpeg
+    monkeypatch.setattr(clf.engine, "classify_rgb8", lambda *a: (_ for _ in ()).throw(RuntimeError("gpu")))
+    assert clf.classify_image(_jpeg()) is None
+
+
+def test_missing_files_raise(monkeypatch, tmp_path):
+    monkeypatch.setattr(P._engine, "Engine", FakeEngine)
+    with pytest.raises(Exception, match="missing"):
+        P.ImagenetClassifier(str(tmp_path / "nope"), str(tmp_path / "nope2"))     # :140-143

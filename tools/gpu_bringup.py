@@ -11,6 +11,7 @@ import argparse
 import json
 import os
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -150,7 +151,7 @@ def cmd_pools(args):
 
 def _weights_file(num_classes):
     from tensorflow_web_deploy_b200 import weights
-    path = os.path.join(OUT, "synthetic_c%d.icpw" % num_classes)
+    path = os.path.join(tempfile.gettempdir(), "icp_synthetic_c%d.icpw" % num_classes)
     W = weights.synthetic_weights(num_classes)
     if not os.path.exists(path):
         weights.save_blob(path, W)
@@ -217,6 +218,36 @@ def cmd_speed(args):
     return 0
 
 
+def cmd_profile(args):
+    """Per-launch device times (CUDA events between launches) + achieved TFLOP/s / GB/s per op."""
+    from tensorflow_web_deploy_b200 import engine
+    C = 6
+    path, _ = _weights_file(C)
+    n = args.n
+    x = np.random.default_rng(1).uniform(-1, 1, (n, 299, 299, 3)).astype(np.float32)
+    eng = engine.Engine(path, C, max_batch=n, precision=args.precision)
+    for _ in range(2):
+        eng.forward(x)
+    ms = eng.profile_forward(n, args.reps)
+    table = eng.op_table()
+    rows = []
+    tot = float(ms.sum())
+    conv_ms = conv_fl = 0.0
+    for (name, kind, fl, by), t in zip(table, ms):
+        tf = fl * n / (t * 1e-3) / 1e12 if t > 0 else 0.0
+        gb = by * n / (t * 1e-3) / 1e9 if t > 0 else 0.0
+        rows.append({"name": name, "kind": kind, "ms": float(t), "tflops": tf, "gbs": gb, "share": float(t) / tot})
+        if kind == 1:
+            conv_ms += float(t); conv_fl += fl * n
+        print("OP %-44s kind=%d ms=%8.4f share=%5.1f%% %8.1f TF/s %8.1f GB/s" % (name, kind, t, 100 * t / tot, tf, gb),
+              flush=True)
+    print("PROFILE n=%d %s: sum=%.3f ms ; conv_igemm %.3f ms (%.1f%%) -> %.1f TFLOP/s" % (
+        n, args.precision, tot, conv_ms, 100 * conv_ms / tot, conv_fl / (conv_ms * 1e-3) / 1e12), flush=True)
+    with open(os.path.join(OUT, "profile_ops_n%d_%s.json" % (n, args.precision)), "w") as f:
+        json.dump({"n": n, "precision": args.precision, "sum_ms": tot, "conv_igemm_ms": conv_ms, "ops": rows}, f, indent=1)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -226,8 +257,10 @@ def main():
     p.add_argument("--graph", action="store_true")
     p = sub.add_parser("speed"); p.add_argument("--precision", default="bf16"); p.add_argument("--n", type=int, default=128)
     p.add_argument("--iters", type=int, default=10); p.add_argument("--graph", action="store_true")
+    p = sub.add_parser("profile"); p.add_argument("--precision", default="bf16"); p.add_argument("--n", type=int, default=128)
+    p.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
-    rc = {"conv": cmd_conv, "pools": cmd_pools, "tower": cmd_tower, "speed": cmd_speed}[args.cmd](args)
+    rc = {"profile": cmd_profile, "conv": cmd_conv, "pools": cmd_pools, "tower": cmd_tower, "speed": cmd_speed}[args.cmd](args)
     sys.exit(rc)
 
 
