@@ -55,10 +55,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -67,10 +67,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
@@ -83,15 +83,34 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
-def oracle_images_per_s(images, threads):
+def host_cores():
+    """Cores this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+_ORACLE_W = None
+
+
+def oracle_images_per_s(images, threads, warm=True):
     """CPU restatement of the reference path on `images` preprocessed images; returns (img/s, seconds)."""
+    global _ORACLE_W
     import torch
     from oracle import inception_oracle as O
     from tensorflow_web_deploy_b200 import weights
     torch.set_num_threads(threads)
-    W = weights.synthetic_weights(NUM_CLASSES)
+    if _ORACLE_W is None:
+        _ORACLE_W = weights.synthetic_weights(NUM_CLASSES)
+    W = _ORACLE_W
     x = np.random.default_rng(1).uniform(-1, 1, (images, 299, 299, 3)).astype(np.float32)
-    O.Tower(W).forward(x[:1], NUM_CLASSES, with_aux=False)          # warm-up (oneDNN primitive creation)
+    if warm:
+        O.Tower(W).forward(x[:1], NUM_CLASSES, with_aux=False)      # warm-up (oneDNN primitive creation)
     t0 = time.perf_counter()
     for i in range(images):                                         # batch 1, as the reference serves
         pred = O.Tower(W).forward(x[i:i + 1], NUM_CLASSES, with_aux=False)[1]
@@ -105,19 +124,22 @@ def run_reference(args, rank, world):
     (SURVEY 8(c)), so this is the oracle port on all host threads; rank 0 only."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_step = 4
-    for _ in range(max(args.warmup, 1) - 1):
-        oracle_images_per_s(1, cores)
+    cores = min(host_cores(), 32)
+    per_step = 2
+    for _ in range(args.warmup):
+        oracle_images_per_s(1, cores, warm=False)
     t0 = time.perf_counter()
     tot_img = 0
     for _ in range(args.steps):
-        _, dt = oracle_images_per_s(per_step, cores)
+        _, dt = oracle_images_per_s(per_step, cores, warm=False)
         tot_img += per_step
+        if time.perf_counter() - t0 > 150:      # bounded sample: never more than a few minutes
+            break
     wall = time.perf_counter() - t0
     v = tot_img / wall
+    done_steps = tot_img // per_step
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "steps": done_steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(done_steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "classify path, batch 1 x %d images per step, CPU oracle port of the reference "
                                    "TF graph (reference itself not runnable: no TensorFlow/Python2/checkpoint)" % per_step,
@@ -259,7 +281,7 @@ def main():
         lat.close()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = min(host_cores(), 32)
             ips, secs = oracle_images_per_s(12, cores)
             cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "12 images, batch 1 each (as the reference serves), torch fp32 CPU oracle, %.1f s" % secs,

@@ -49,6 +49,14 @@ struct ConvArgs {
   int coff;        // first channel this layer owns in the output buffer
   const float* scale;  // [cout] rsqrt(var + eps)
   const float* shift;  // [cout] beta - mean * scale
+  // Horizontally fused sibling 1x1 convs (one GEMM over the concatenated output channels):
+  // columns >= n_split go to a second buffer (out2/ldo2/coff2); `floor` (nullable) is a per-channel
+  // activation floor — 0 for ReLU channels, -inf for channels that stay linear (pool-after-projection).
+  void* out2;
+  int ldo2;
+  int coff2;
+  int n_split;         // multiple of 16; >= cout when there is no second destination
+  const float* floor;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
@@ -77,6 +85,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const uint32_t tmem_slot = tmem_full_bar + 8u;
   float* s_scale = reinterpret_cast<float*>(gbase + a.stages * stage_bytes + 256);
   float* s_shift = s_scale + 256;
+  float* s_floor = s_shift + 256;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
 
@@ -159,6 +168,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     for (int i = et; i < a.n_tile; i += 128) {
       s_scale[i] = __ldg(a.scale + n_base + i);
       s_shift[i] = __ldg(a.shift + n_base + i);
+      s_floor[i] = a.floor ? __ldg(a.floor + n_base + i) : (a.relu ? 0.f : -INFINITY);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     const int quarter = warp & 3;            // TMEM lanes this warp may touch: [32q, 32q+32)
@@ -168,6 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     ptx::tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(m) * a.ldo + a.coff + n_base;
+    uint16_t* orow2 = reinterpret_cast<uint16_t*>(a.out2) + static_cast<size_t>(m) * a.ldo2 + a.coff2 + n_base - a.n_split;
     const bool valid = m < a.m_total;
     for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
       uint32_t v[16];
@@ -178,11 +189,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int j = 0; j < 8; ++j) {
         float x0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0 + 2 * j], s_shift[c0 + 2 * j]);
         float x1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 2 * j + 1], s_shift[c0 + 2 * j + 1]);
-        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        x0 = fmaxf(x0, s_floor[c0 + 2 * j]);
+        x1 = fmaxf(x1, s_floor[c0 + 2 * j + 1]);
         p[j] = pack2(x0, x1, a.fmt);
       }
       if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+        uint4* dst = reinterpret_cast<uint4*>((n_base + c0 < a.n_split ? orow : orow2) + c0);
         dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
         dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
       }
@@ -199,7 +211,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 }
 
 inline size_t conv_smem_bytes(int stages, int n_tile) {
-  return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + 256 + 2048;
+  return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + 256 + 3072;
 }
 
 }  // namespace icp

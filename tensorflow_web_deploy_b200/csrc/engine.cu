@@ -19,6 +19,7 @@
 
 #include "../../include/inception_b200.h"
 #include "conv_igemm.cuh"
+#include "conv_halo.cuh"
 #include "tower_kernels.cuh"
 
 namespace icp {
@@ -89,6 +90,43 @@ static CUtensorMap make_tm_2d(const void* ptr, uint64_t rows, uint64_t cols, uin
   if (r != CUDA_SUCCESS)
     fail(ICP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
          (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
+  return m;
+}
+
+static CUtensorMapSwizzle tm_swizzle(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 2-D K-major weight matrix with rows of `row_bytes` per box (halo kernel's B operand).
+static CUtensorMap make_tm_2d_rows(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int row_bytes,
+                                   int fmt) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(row_bytes / 2), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&m, tm_dtype(fmt), 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, tm_swizzle(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(ICP_E_CUDA, "cuTensorMapEncodeTiled(B rows) failed (%d)", (int)r);
+  return m;
+}
+
+// NHWC activation as a 4-D tiled map whose box is a halo strip: {ck channels, wp columns, rows, 1 image}.
+static CUtensorMap make_tm_strip(const void* ptr, int n, int h, int w, int c, int ld, int wp, int rows, int row_bytes,
+                                 int fmt) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)wp, (cuuint32_t)rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(&m, tm_dtype(fmt), 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, tm_swizzle(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fail(ICP_E_CUDA, "cuTensorMapEncodeTiled(strip) failed (%d) n=%d h=%d w=%d c=%d ld=%d wp=%d rows=%d rb=%d", (int)r, n,
+         h, w, c, ld, wp, rows, row_bytes);
   return m;
 }
 
@@ -213,6 +251,8 @@ struct ConvLayer {
   size_t smem = 0;
   long long macs_per_image = 0;
   long long in_elems_per_image = 0;
+  bool halo = false;       // conv_halo_kernel instead of conv_igemm_kernel
+  HaloArgs hargs{};
 };
 
 static int pick_n_tile(int cout) {
@@ -244,10 +284,37 @@ static std::vector<uint16_t> pack_weights(const float* w, int kh, int kw, int ci
   return out;
 }
 
+// Halo kernel's B operand: K index = ((chunk * taps + tap) * ck + j), channel = chunk*ck + j.
+static std::vector<uint16_t> pack_weights_halo(const float* w, int kh, int kw, int cin, int cout, int ck, int fmt) {
+  const int chunks = (cin + ck - 1) / ck, taps = kh * kw;
+  const size_t kp = static_cast<size_t>(chunks) * taps * ck;
+  std::vector<uint16_t> out(static_cast<size_t>(cout) * kp, 0);
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = w + (static_cast<size_t>(t) * cin + ci) * cout;
+      const size_t kidx = (static_cast<size_t>(ci / ck) * taps + t) * ck + (ci % ck);
+      for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(src[co], fmt);
+    }
+  return out;
+}
+
+static int pick_row_bytes(int cin) {
+  int best = 128, best_pad = 1 << 30;
+  for (int rb : {128, 64, 32}) {
+    const int ck = rb / 2;
+    const int padded = (cin + ck - 1) / ck * ck;
+    if (padded < best_pad) { best_pad = padded; best = rb; }
+  }
+  return best;
+}
+static bool g_halo_attr_set = false;
+
 // in: NHWC buffer (pitch in.c) of which channels [in_coff, in_coff+cin) feed the conv.
 static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n, const Act& in, int in_coff, int cin,
                            const float* w_hwio, int kh, int kw, int cout, int stride, bool same, const float* scale,
-                           const float* shift, bool relu, const Act& out, int out_coff, int fmt) {
+                           const float* shift, bool relu, const Act& out, int out_coff, int fmt,
+                           const float* floor = nullptr, const Act* out2 = nullptr, int out2_coff = 0,
+                           int n_split = 0) {
   if (same && stride != 1) fail(ICP_E_INVALID, "%s: SAME padding is only supported with stride 1", name.c_str());
   if (cout % 16) fail(ICP_E_INVALID, "%s: cout=%d is not a multiple of 16", name.c_str(), cout);
   if (cin % 8 || in.c % 8 || in_coff % 8 || out.c % 8 || out_coff % 8)
@@ -256,6 +323,9 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   const int oh = (in.h + 2 * pad_h - kh) / stride + 1, ow = (in.w + 2 * pad_w - kw) / stride + 1;
   if (oh != out.h || ow != out.w)
     fail(ICP_E_INVALID, "%s: output geometry %dx%d != buffer %dx%d", name.c_str(), oh, ow, out.h, out.w);
+  if (out2 && (n_split % 16 || n_split <= 0 || n_split >= cout || out2->h != oh || out2->w != ow || out2->c % 8 ||
+               out2_coff % 8))
+    fail(ICP_E_INVALID, "%s: bad second destination", name.c_str());
   ConvLayer L;
   L.name = name;
   L.cout = cout;
@@ -274,6 +344,46 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   if (stages < 1) stages = 1;
   static const bool force_im2col = getenv("ICP_FORCE_IM2COL") != nullptr;
   const bool im2col = force_im2col || !(kh == 1 && kw == 1 && stride == 1);
+  // Large stride-1 maps with a real filter footprint: read the input once per tile (conv_halo.cuh).
+  static const bool no_halo = getenv("ICP_NO_HALO") != nullptr;
+  static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 30;
+  if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256) {
+    const int rb = pick_row_bytes(cin), ck = rb / 2;
+    const int wp = in.w + 2 * pad_w;
+    const int chunks = (cin + ck - 1) / ck;
+    const int strip_rows = (kh - 1) + 1 + (wp - 1 + (kBM - 1) + (kw - 1)) / wp;
+    const int strip_bytes = ((strip_rows * wp * rb) + 1023) & ~1023;
+    const size_t b_stride = (static_cast<size_t>(n_tile) * rb + 1023) & ~size_t(1023);
+    int b_stages = 4;
+    while (b_stages > 2 && halo_smem_bytes(strip_bytes, b_stages, n_tile, rb) > 110 * 1024) --b_stages;
+    const size_t smem = halo_smem_bytes(strip_bytes, b_stages, n_tile, rb);
+    if (smem <= 220 * 1024) {
+      (void)b_stride;
+      std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt);
+      void* d_w = pool.alloc(wp_host.size() * 2);
+      CK(cudaMemcpy(d_w, wp_host.data(), wp_host.size() * 2, cudaMemcpyHostToDevice));
+      float* d_scale = static_cast<float*>(pool.alloc(cout * 4));
+      float* d_shift = static_cast<float*>(pool.alloc(cout * 4));
+      CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
+      const uint64_t kp = static_cast<uint64_t>(chunks) * kh * kw * ck;
+      L.halo = true;
+      L.tm_b = make_tm_2d_rows(d_w, cout, kp, n_tile, rb, fmt);
+      L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
+      HaloArgs& h = L.hargs;
+      h.oh = oh; h.ow = ow; h.wp = wp; h.pad_h = pad_h; h.pad_w = pad_w; h.kh = kh; h.kw = kw;
+      h.chunks = chunks; h.row_bytes = rb; h.strip_rows = strip_rows; h.strip_bytes = strip_bytes;
+      h.tiles_per_image = (oh * wp + kBM - 1) / kBM;
+      h.n_tile = n_tile; h.tmem_cols = pow2_cols(n_tile); h.b_stages = b_stages; h.fmt = fmt; h.relu = relu ? 1 : 0;
+      h.out = out.p; h.ldo = out.c; h.coff = out_coff; h.scale = d_scale; h.shift = d_shift;
+      L.smem = smem;
+      if (!g_halo_attr_set) {
+        CK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        g_halo_attr_set = true;
+      }
+      return L;
+    }
+  }
 
   // weights + BN vectors to the device
   std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, fmt);
@@ -313,6 +423,16 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.coff = out_coff;
   a.scale = d_scale;
   a.shift = d_shift;
+  a.floor = nullptr;
+  if (floor) {
+    float* d_floor = static_cast<float*>(pool.alloc(cout * 4));
+    CK(cudaMemcpy(d_floor, floor, cout * 4, cudaMemcpyHostToDevice));
+    a.floor = d_floor;
+  }
+  a.out2 = out2 ? out2->p : nullptr;
+  a.ldo2 = out2 ? out2->c : 0;
+  a.coff2 = out2_coff;
+  a.n_split = out2 ? n_split : (1 << 30);
   L.smem = conv_smem_bytes(stages, n_tile);
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -322,6 +442,12 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
 }
 
 static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
+  if (L.halo) {
+    dim3 grid(L.hargs.tiles_per_image * n, L.n_tiles);
+    conv_halo_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.hargs);
+    CK(cudaGetLastError());
+    return;
+  }
   ConvArgs a = L.args;
   a.m_total = n * L.pix_per_image;
   dim3 grid((a.m_total + kBM - 1) / kBM, L.n_tiles);
@@ -334,8 +460,11 @@ struct Op {
   enum Kind { CONV, MAXPOOL, AVGPOOL } kind;
   ConvLayer conv;                 // CONV
   Act in, out;                    // pools
-  int c = 0, out_coff = 0;        // pools: channels pooled, channel offset in out
+  int c = 0, in_coff = 0, out_coff = 0;   // pools: channels pooled, channel offsets in `in` / `out`
   int k = 3, stride = 1, pad = 0;
+  const float* scale = nullptr;   // AVGPOOL after a linear 1x1 projection: that layer's BN + ReLU
+  const float* shift = nullptr;
+  std::string name;
 };
 
 struct Endpoint {
@@ -473,17 +602,115 @@ struct Builder {
     e.endpoints[name] = ep;
   }
 
+  // ---- horizontally fused sibling 1x1 convs -------------------------------------------------------
+  // All 1x1 convs of a block read the same input, so they run as ONE GEMM over the concatenated output
+  // channels: [branch1x1 | branch temps ... | pool-branch projection].  branch1x1's columns land in the
+  // block's concat buffer, the rest in a fused temp buffer whose channel slices feed the k>1 convs.
+  // The pool branch is projected FIRST (linear part only: scale 1, shift 0, no ReLU) and average-pooled
+  // afterwards, with its BatchNorm + ReLU applied on the pooled value: avg_pool and a 1x1 conv commute
+  // (both linear; inception_model.py:122-124 order is pool -> conv -> BN -> relu), and pooling 32..192
+  // projected channels instead of 192..2048 input channels removes ~80 % of the pool traffic.
+  struct Sib {
+    std::string scope;
+    int cout;
+    bool pool_proj;     // true: keep linear (BN/ReLU deferred to the pool)
+  };
+  struct Fused {
+    Act temp;                      // fused temp buffer (channels after the first destination)
+    std::vector<int> temp_off;     // channel offset of sibling i inside `temp` (-1 for the first-destination sibling)
+    std::vector<float> pool_scale, pool_shift;   // deferred BN of the pool-projection sibling
+  };
+  // sibs[0] goes to (out, out_coff) when `first_to_out`, everything else to the fused temp.
+  Fused fused_1x1(std::vector<Op>& ops, const std::string& block, const Act& x, const std::vector<Sib>& sibs,
+                  bool first_to_out, const Act& out, int out_coff) {
+    int total = 0;
+    for (const Sib& sb : sibs) total += sb.cout;
+    const int cin = x.c;
+    std::vector<float> w(static_cast<size_t>(cin) * total), scale(total), shift(total), floor(total);
+    Fused f;
+    int col = 0, tcol = 0;
+    std::string name = block + "/{";
+    for (size_t i = 0; i < sibs.size(); ++i) {
+      const Sib& sb = sibs[i];
+      const HostTensor& wi = blob_get(blob, sb.scope + "/weights", {1, 1, cin, sb.cout});
+      for (int ci = 0; ci < cin; ++ci)
+        memcpy(&w[static_cast<size_t>(ci) * total + col], &wi.data[static_cast<size_t>(ci) * sb.cout], sb.cout * 4);
+      std::vector<float> sc, sh;
+      bn_fold(sb.scope, sb.cout, sc, sh);
+      for (int j = 0; j < sb.cout; ++j) {
+        scale[col + j] = sb.pool_proj ? 1.0f : sc[j];
+        shift[col + j] = sb.pool_proj ? 0.0f : sh[j];
+        floor[col + j] = sb.pool_proj ? -INFINITY : 0.0f;
+      }
+      if (sb.pool_proj) { f.pool_scale = sc; f.pool_shift = sh; }
+      if (i == 0 && first_to_out) {
+        f.temp_off.push_back(-1);
+      } else {
+        f.temp_off.push_back(tcol);
+        tcol += sb.cout;
+      }
+      col += sb.cout;
+      name += (i ? "," : "") + sb.scope.substr(block.size() + 1);
+      e.conv_macs_per_image += static_cast<long long>(x.h) * x.w * cin * sb.cout;
+    }
+    name += "}[fused 1x1]";
+    f.temp = alloc_act(x.h, x.w, tcol);
+    Op op;
+    op.kind = Op::CONV;
+    if (first_to_out)
+      op.conv = make_conv(e.pool, name, maxn, x, 0, cin, w.data(), 1, 1, total, 1, true, scale.data(), shift.data(),
+                          true, out, out_coff, fmt, floor.data(), &f.temp, 0, sibs[0].cout);
+    else
+      op.conv = make_conv(e.pool, name, maxn, x, 0, cin, w.data(), 1, 1, total, 1, true, scale.data(), shift.data(),
+                          true, f.temp, 0, fmt, floor.data());
+    ops.push_back(std::move(op));
+    return f;
+  }
+  // conv reading channels [in_coff, in_coff+cin) of a fused temp
+  void conv_slice(std::vector<Op>& ops, const std::string& scope, const Act& in, int in_coff, int cin, int cout, int kh,
+                  int kw, int stride, bool same, const Act& out, int coff) {
+    const HostTensor& w = blob_get(blob, scope + "/weights", {kh, kw, cin, cout});
+    std::vector<float> scale, shift;
+    bn_fold(scope, cout, scale, shift);
+    Op op;
+    op.kind = Op::CONV;
+    op.conv = make_conv(e.pool, scope, maxn, in, in_coff, cin, w.data.data(), kh, kw, cout, stride, same, scale.data(),
+                        shift.data(), true, out, coff, fmt);
+    e.conv_macs_per_image += op.conv.macs_per_image;
+    ops.push_back(std::move(op));
+  }
+  Act conv_slice_new(std::vector<Op>& ops, const std::string& scope, const Act& in, int in_coff, int cin, int cout,
+                     int kh, int kw) {
+    Act out = alloc_act(in.h, in.w, cout);      // SAME, stride 1
+    conv_slice(ops, scope, in, in_coff, cin, cout, kh, kw, 1, true, out, 0);
+    return out;
+  }
+  // 3x3/1 SAME average pool of the projected pool branch + its deferred BN + ReLU, into the concat slice
+  void pool_after_projection(std::vector<Op>& ops, const std::string& scope, const Fused& f, int temp_off, int c,
+                             const Act& out, int coff) {
+    Op op;
+    op.kind = Op::AVGPOOL;
+    op.name = scope + "[avg_pool after 1x1 + BN + ReLU]";
+    op.in = f.temp; op.in_coff = temp_off; op.out = out; op.out_coff = coff; op.c = c;
+    op.k = 3; op.stride = 1; op.pad = 1;
+    float* d_sc = static_cast<float*>(e.pool.alloc(c * 4));
+    float* d_sh = static_cast<float*>(e.pool.alloc(c * 4));
+    CK(cudaMemcpy(d_sc, f.pool_scale.data(), c * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sh, f.pool_shift.data(), c * 4, cudaMemcpyHostToDevice));
+    op.scale = d_sc; op.shift = d_sh;
+    ops.push_back(std::move(op));
+  }
+
   // mixed_35x35x* (inception_model.py:112-158)
   Act block35(std::vector<Op>& ops, const std::string& s, const Act& x, int pool_c) {
     Act out = alloc_act(x.h, x.w, 64 + 64 + 96 + pool_c);
-    conv(ops, s + "/branch1x1/Conv", x, 64, 1, 1, 1, true, out, 0);
-    Act t = conv_new(ops, s + "/branch5x5/Conv", x, 48, 1, 1);
-    conv(ops, s + "/branch5x5/Conv_1", t, 64, 5, 5, 1, true, out, 64);
-    t = conv_new(ops, s + "/branch3x3dbl/Conv", x, 64, 1, 1);
-    t = conv_new(ops, s + "/branch3x3dbl/Conv_1", t, 96, 3, 3);
+    Fused f = fused_1x1(ops, s, x, {{s + "/branch1x1/Conv", 64, false}, {s + "/branch5x5/Conv", 48, false},
+                                    {s + "/branch3x3dbl/Conv", 64, false}, {s + "/branch_pool/Conv", pool_c, true}},
+                        true, out, 0);
+    conv_slice(ops, s + "/branch5x5/Conv_1", f.temp, f.temp_off[1], 48, 64, 5, 5, 1, true, out, 64);
+    Act t = conv_slice_new(ops, s + "/branch3x3dbl/Conv_1", f.temp, f.temp_off[2], 64, 96, 3, 3);
     conv(ops, s + "/branch3x3dbl/Conv_2", t, 96, 3, 3, 1, true, out, 128);
-    t = avgpool_new(ops, x, 3, 1, true);
-    conv(ops, s + "/branch_pool/Conv", t, pool_c, 1, 1, 1, true, out, 224);
+    pool_after_projection(ops, s + "/branch_pool", f, f.temp_off[3], pool_c, out, 224);
     tap(s, out);
     return out;
   }
@@ -502,17 +729,16 @@ struct Builder {
   // mixed_17x17x768b..e (:173-247)
   Act block17(std::vector<Op>& ops, const std::string& s, const Act& x, int m) {
     Act out = alloc_act(x.h, x.w, 768);
-    conv(ops, s + "/branch1x1/Conv", x, 192, 1, 1, 1, true, out, 0);
-    Act t = conv_new(ops, s + "/branch7x7/Conv", x, m, 1, 1);
-    t = conv_new(ops, s + "/branch7x7/Conv_1", t, m, 1, 7);
+    Fused f = fused_1x1(ops, s, x, {{s + "/branch1x1/Conv", 192, false}, {s + "/branch7x7/Conv", m, false},
+                                    {s + "/branch7x7dbl/Conv", m, false}, {s + "/branch_pool/Conv", 192, true}},
+                        true, out, 0);
+    Act t = conv_slice_new(ops, s + "/branch7x7/Conv_1", f.temp, f.temp_off[1], m, m, 1, 7);
     conv(ops, s + "/branch7x7/Conv_2", t, 192, 7, 1, 1, true, out, 192);
-    t = conv_new(ops, s + "/branch7x7dbl/Conv", x, m, 1, 1);
-    t = conv_new(ops, s + "/branch7x7dbl/Conv_1", t, m, 7, 1);
+    t = conv_slice_new(ops, s + "/branch7x7dbl/Conv_1", f.temp, f.temp_off[2], m, m, 7, 1);
     t = conv_new(ops, s + "/branch7x7dbl/Conv_2", t, m, 1, 7);
     t = conv_new(ops, s + "/branch7x7dbl/Conv_3", t, m, 7, 1);
     conv(ops, s + "/branch7x7dbl/Conv_4", t, 192, 1, 7, 1, true, out, 384);
-    t = avgpool_new(ops, x, 3, 1, true);
-    conv(ops, s + "/branch_pool/Conv", t, 192, 1, 1, 1, true, out, 576);
+    pool_after_projection(ops, s + "/branch_pool", f, f.temp_off[3], 192, out, 576);
     tap(s, out);
     return out;
   }
@@ -520,10 +746,10 @@ struct Builder {
   Act block_red_b(std::vector<Op>& ops, const std::string& s, const Act& x) {
     const int oh = (x.h - 3) / 2 + 1, ow = (x.w - 3) / 2 + 1;
     Act out = alloc_act(oh, ow, 320 + 192 + x.c);
-    Act t = conv_new(ops, s + "/branch3x3/Conv", x, 192, 1, 1);
-    conv(ops, s + "/branch3x3/Conv_1", t, 320, 3, 3, 2, false, out, 0);
-    t = conv_new(ops, s + "/branch7x7x3/Conv", x, 192, 1, 1);
-    t = conv_new(ops, s + "/branch7x7x3/Conv_1", t, 192, 1, 7);
+    Fused f = fused_1x1(ops, s, x, {{s + "/branch3x3/Conv", 192, false}, {s + "/branch7x7x3/Conv", 192, false}}, false,
+                        out, 0);
+    conv_slice(ops, s + "/branch3x3/Conv_1", f.temp, f.temp_off[0], 192, 320, 3, 3, 2, false, out, 0);
+    Act t = conv_slice_new(ops, s + "/branch7x7x3/Conv_1", f.temp, f.temp_off[1], 192, 192, 1, 7);
     t = conv_new(ops, s + "/branch7x7x3/Conv_2", t, 192, 7, 1);
     conv(ops, s + "/branch7x7x3/Conv_3", t, 192, 3, 3, 2, false, out, 320);
     maxpool(ops, x, out, 512);
@@ -533,16 +759,15 @@ struct Builder {
   // mixed_8x8x2048a/b (:282-316); nested concats become adjacent channel slices
   Act block8(std::vector<Op>& ops, const std::string& s, const Act& x) {
     Act out = alloc_act(x.h, x.w, 2048);
-    conv(ops, s + "/branch1x1/Conv", x, 320, 1, 1, 1, true, out, 0);
-    Act t = conv_new(ops, s + "/branch3x3/Conv", x, 384, 1, 1);
-    conv(ops, s + "/branch3x3/Conv_1", t, 384, 1, 3, 1, true, out, 320);
-    conv(ops, s + "/branch3x3/Conv_2", t, 384, 3, 1, 1, true, out, 704);
-    t = conv_new(ops, s + "/branch3x3dbl/Conv", x, 448, 1, 1);
-    t = conv_new(ops, s + "/branch3x3dbl/Conv_1", t, 384, 3, 3);
+    Fused f = fused_1x1(ops, s, x, {{s + "/branch1x1/Conv", 320, false}, {s + "/branch3x3/Conv", 384, false},
+                                    {s + "/branch3x3dbl/Conv", 448, false}, {s + "/branch_pool/Conv", 192, true}},
+                        true, out, 0);
+    conv_slice(ops, s + "/branch3x3/Conv_1", f.temp, f.temp_off[1], 384, 384, 1, 3, 1, true, out, 320);
+    conv_slice(ops, s + "/branch3x3/Conv_2", f.temp, f.temp_off[1], 384, 384, 3, 1, 1, true, out, 704);
+    Act t = conv_slice_new(ops, s + "/branch3x3dbl/Conv_1", f.temp, f.temp_off[2], 448, 384, 3, 3);
     conv(ops, s + "/branch3x3dbl/Conv_2", t, 384, 1, 3, 1, true, out, 1088);
     conv(ops, s + "/branch3x3dbl/Conv_3", t, 384, 3, 1, 1, true, out, 1472);
-    t = avgpool_new(ops, x, 3, 1, true);
-    conv(ops, s + "/branch_pool/Conv", t, 192, 1, 1, 1, true, out, 1856);
+    pool_after_projection(ops, s + "/branch_pool", f, f.temp_off[3], 192, out, 1856);
     tap(s, out);
     return out;
   }
@@ -650,8 +875,8 @@ static int run_op(const Op& op, int n, int fmt, cudaStream_t st) {
     case Op::AVGPOOL: {
       const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
       avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.out.p, op.out.h, op.out.w, op.out.c, op.k, op.stride, op.pad,
-          fmt);
+          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff,
+          op.k, op.stride, op.pad, op.scale, op.shift, 1, fmt);
       CK(cudaGetLastError());
       return 1;
     }
@@ -977,7 +1202,8 @@ int icp_op_info(icp_engine* e, int i, char* name, int name_cap, int* kind, doubl
         by = static_cast<double>(L.in_elems_per_image) * 2 + static_cast<double>(L.pix_per_image) * L.cout * 2;
         (void)k;
       } else {
-        nm = op.kind == Op::MAXPOOL ? "max_pool" : "avg_pool"; kd = op.kind == Op::MAXPOOL ? ICP_OP_MAXPOOL : ICP_OP_AVGPOOL;
+        nm = !op.name.empty() ? op.name : (op.kind == Op::MAXPOOL ? "max_pool" : "avg_pool");
+        kd = op.kind == Op::MAXPOOL ? ICP_OP_MAXPOOL : ICP_OP_AVGPOOL;
         fl = 0;
         by = static_cast<double>(op.in.h) * op.in.w * op.c * 2 + static_cast<double>(op.out.h) * op.out.w * op.c * 2;
       }
@@ -1160,8 +1386,8 @@ int icp_pool2d(int device, int precision, int kind, const float* x, int n, int h
       maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_x, n, h, w, c, c, 0, d_y, oh, ow, c, 0,
                                                                              fmt);
     else
-      avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_x, n, h, w, c, c, d_y, oh, ow, c, k, stride,
-                                                                          pad, fmt);
+      avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_x, n, h, w, c, c, 0, d_y, oh, ow, c, 0, k,
+                                                                          stride, pad, nullptr, nullptr, 0, fmt);
     h16_to_f32_kernel<<<static_cast<unsigned>((out_elems + 255) / 256), 256>>>(d_y, d_yf,
                                                                                static_cast<size_t>(n) * oh * ow, c, c, 0,
                                                                                fmt);

@@ -58,6 +58,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h,
+                                            int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
 // 4-D im2col load: coordinates (c, w, h, n) name the first *base* pixel (top-left of the filter
 // window, i.e. ow*stride - pad) and the channel offset; (off_w, off_h) is the filter tap.  The
 // unit walks `pixelsPerColumn` base pixels along W, then H, then N inside the bounding box given
@@ -137,6 +144,20 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Same, for operand rows of `row_bytes` in {32, 64, 128} written by TMA with SWIZZLE_{32,64,128}B:
+// 8-row groups are 8*row_bytes apart; layout code 6 / 4 / 2.  `smem_addr` only needs 16-B alignment:
+// the swizzle XOR is a function of the absolute shared-memory address (as it is for TMA), which is what
+// lets a K slice (+32 B) or a pixel row (+row_bytes) be selected by moving the start address.
+__device__ __forceinline__ uint64_t make_smem_desc_rows(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8u * row_bytes) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= layout << 61;
   return d;
 }
 // Instruction descriptor for kind::f16, fp32 accumulate, A and B K-major.

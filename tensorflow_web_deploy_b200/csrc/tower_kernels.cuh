@@ -161,9 +161,12 @@ __global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, int N, int H,
 // avg_pool k x k, stride s; SAME (pad (k-1)/2, stride 1) divides by the number of in-bounds taps —
 // tf.nn.avg_pool semantics (ops.py:397-400) — VALID is a plain mean.  fp32 accumulation.
 // ---------------------------------------------------------------------------------------------
-__global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi,
-                               uint16_t* __restrict__ out, int OH, int OW, int ldo, int k, int stride, int pad,
+__global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
+                               uint16_t* __restrict__ out, int OH, int OW, int ldo, int coff, int k, int stride,
+                               int pad, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                                int fmt) {
+  // scale/shift (nullable): the pool runs AFTER a linear 1x1 projection (avg-pool and a 1x1 conv
+  // commute), so the projection's BatchNorm + ReLU (ops.py:231-245) are applied here, on the pooled value.
   const int cg = C / 8;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(N) * OH * OW * cg;
@@ -183,7 +186,7 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, in
     for (int s = 0; s < k; ++s) {
       const int ix = ox * stride - pad + s;
       if (ix < 0 || ix >= W) continue;
-      const size_t off = ((static_cast<size_t>(n) * H + iy) * W + ix) * ldi + g * 8;
+      const size_t off = ((static_cast<size_t>(n) * H + iy) * W + ix) * ldi + cin_off + g * 8;
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + off));
       float f[8];
       unpack8(v, f, fmt);
@@ -195,7 +198,14 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, in
   const float inv = 1.0f / static_cast<float>(cnt);
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] *= inv;
-  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + g * 8) = pack8(acc, fmt);
+  if (scale != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] = fmaf(acc[j], __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j));
+      if (relu) acc[j] = fmaxf(acc[j], 0.f);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + coff + g * 8) = pack8(acc, fmt);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -68,6 +68,15 @@ CONV_CASES = [
     ("3x3_s2_valid_k192_n320", 2, 17, 17, 192, 3, 3, 320, 2, False),
     ("5x5_full_valid_k128_n768", 3, 5, 5, 128, 5, 5, 768, 1, False),
     ("3x3_same_tiny", 1, 3, 3, 64, 3, 3, 32, 1, True),
+    # halo-resident kernel (large stride-1 maps)
+    ("halo_conv1_149_k32_n32_valid", 1, 149, 149, 32, 3, 3, 32, 1, False),
+    ("halo_conv2_147_k32_n64_same", 2, 147, 147, 32, 3, 3, 64, 1, True),
+    ("halo_conv4_73_k80_n192_valid", 2, 73, 73, 80, 3, 3, 192, 1, False),
+    ("halo_35_k48_5x5_n64", 3, 35, 35, 48, 5, 5, 64, 1, True),
+    ("halo_35_k96_3x3_n96", 3, 35, 35, 96, 3, 3, 96, 1, True),
+    ("halo_40x33_k64_3x3_n128", 2, 40, 33, 64, 3, 3, 128, 1, True),
+    ("halo_31x50_k24_1x7_n48", 2, 31, 50, 24, 1, 7, 48, 1, True),
+    ("halo_50x31_k136_7x1_n64", 2, 50, 31, 136, 7, 1, 64, 1, True),
 ]
 
 
