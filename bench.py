@@ -193,7 +193,8 @@ def main():
     x_dev = torch.empty((B, 299, 299, 3), device=dev, dtype=torch.float32).uniform_(-1, 1, generator=gen)
     probs = torch.empty((B, C), device=dev, dtype=torch.float32)
     gathered = torch.empty((B * world, C), device=dev, dtype=torch.float32)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: the engine enqueues on the handle we pass
+    torch.cuda.set_stream(stream)
 
     def step():
         eng.forward_device(x_dev.data_ptr(), B, probs.data_ptr(), stream.cuda_stream)

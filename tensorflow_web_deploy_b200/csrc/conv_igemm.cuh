@@ -210,6 +210,194 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent, cross-tile pipelined version (the one the tower uses).
+//
+// One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (t -> m_tile = t / n_tiles,
+// n_tile index = t % n_tiles, so CTAs running side by side share A and W tiles in L2).  The three roles
+// run their own tile loops and meet only through mbarriers, so
+//   * the TMA producer runs ahead across tile boundaries through the smem ring (loads for tile i+1 are in
+//     flight while tile i is still multiplying) — this is what hides HBM/L2 latency for the short-K layers,
+//   * the accumulator is double-buffered in TMEM (2 x tmem_cols columns): the epilogue of tile i
+//     (tcgen05.ld -> BN/ReLU -> stores) overlaps the MMAs of tile i+1,
+//   * barrier init, TMEM allocation and descriptor prefetch are paid once per SM, not once per tile.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                             const ConvArgs a, const int m_tiles, const int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar_base = base + a.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
+  const uint32_t acc_bar = bar_base + 16u * a.stages;          // tmem_full[2], tmem_empty[2]
+  auto tmem_full = [&](int i) { return acc_bar + 8u * i; };
+  auto tmem_empty = [&](int i) { return acc_bar + 16u + 8u * i; };
+  const uint32_t tmem_slot = acc_bar + 32u;
+  float* s_scale = reinterpret_cast<float*>(gbase + a.stages * stage_bytes + 256);
+  float* s_shift = s_scale + 256;
+  float* s_floor = s_shift + 256;
+
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_kb = a.taps * a.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_b);
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tmem_full(i), 1);
+      ptx::mbar_init(tmem_empty(i), 128);      // every epilogue thread arrives
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * kBM;
+        const int n_base = (t % n_tiles) * a.n_tile;
+        int bw = 0, bh = 0, bn = 0;
+        if (a.im2col) {
+          const int q = m0 % a.ow;
+          const int r = m0 / a.ow;
+          bw = q * a.stride - a.pad_w;
+          bh = (r % a.oh) * a.stride - a.pad_h;
+          bn = r / a.oh;
+        }
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          ptx::mbar_expect_tx(full_bar(s), stage_bytes);
+          const uint32_t sa = base + s * stage_bytes;
+          if (a.im2col) {
+            const int r = tap / a.kw;
+            ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * kBK, bw, bh, bn,
+                                    static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
+          } else {
+            ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * kBK, m0);
+          }
+          ptx::tma_load_2d(sa + kABytes, &tm_b, full_bar(s), kb * kBK, n_base);
+          if (++cb == a.cblocks) { cb = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const uint32_t as = lt & 1u;
+        ptx::mbar_wait(tmem_empty(as), ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t tacc = tmem_base + as * a.tmem_cols;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(full_bar(s), ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = base + s * stage_bytes;
+          const uint64_t da = ptx::make_smem_desc_sw128(sa);
+          const uint64_t db = ptx::make_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(empty_bar(s));
+        }
+        ptx::umma_commit(tmem_full(as));
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 2..5) ----------------
+    const int et = threadIdx.x - 64;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t lt = 0;
+    int loaded_n_base = -1;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int m0 = (t / n_tiles) * kBM;
+      const int n_base = (t % n_tiles) * a.n_tile;
+      if (n_base != loaded_n_base) {             // uniform across the 128 epilogue threads
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < a.n_tile; i += 128) {
+          s_scale[i] = __ldg(a.scale + n_base + i);
+          s_shift[i] = __ldg(a.shift + n_base + i);
+          s_floor[i] = a.floor ? __ldg(a.floor + n_base + i) : (a.relu ? 0.f : -INFINITY);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        loaded_n_base = n_base;
+      }
+      const uint32_t as = lt & 1u;
+      ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int m = m0 + row;
+      const bool valid = m < a.m_total;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(m) * a.ldo + a.coff + n_base;
+      uint16_t* orow2 =
+          reinterpret_cast<uint16_t*>(a.out2) + static_cast<size_t>(m) * a.ldo2 + a.coff2 + n_base - a.n_split;
+      for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
+        uint32_t v[32];
+        const bool two = c0 + 16 < a.n_tile;
+        ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if (two) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !two) break;
+          const int cc = c0 + 16 * h;
+          uint32_t p[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float x0 = fmaf(__uint_as_float(v[16 * h + 2 * j]), s_scale[cc + 2 * j], s_shift[cc + 2 * j]);
+            float x1 = fmaf(__uint_as_float(v[16 * h + 2 * j + 1]), s_scale[cc + 2 * j + 1], s_shift[cc + 2 * j + 1]);
+            x0 = fmaxf(x0, s_floor[cc + 2 * j]);
+            x1 = fmaxf(x1, s_floor[cc + 2 * j + 1]);
+            p[j] = pack2(x0, x1, a.fmt);
+          }
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>((n_base + cc < a.n_split ? orow : orow2) + cc);
+            dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
+            dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tmem_empty(as));          // 128 arrivals release the accumulator to the MMA issuer
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, 2 * a.tmem_cols);
+  }
+}
+
 inline size_t conv_smem_bytes(int stages, int n_tile) {
   return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + 256 + 3072;
 }

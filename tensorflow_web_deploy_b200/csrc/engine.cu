@@ -251,6 +251,7 @@ struct ConvLayer {
   size_t smem = 0;
   long long macs_per_image = 0;
   long long in_elems_per_image = 0;
+  bool persistent = true;  // conv_igemm_persistent_kernel (one CTA per SM walks the tiles)
   bool halo = false;       // conv_halo_kernel instead of conv_igemm_kernel
   HaloArgs hargs{};
 };
@@ -267,6 +268,7 @@ static int pow2_cols(int n) {
   return c;
 }
 static bool g_conv_attr_set = false;
+static int g_num_sms = 148;
 
 // Packs HWIO fp32 weights into the K-major [cout][taps][cblocks*64] 16-bit matrix the B-operand TMA
 // reads, zero-filling the channel tail of every tap.
@@ -337,15 +339,17 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.n_tiles = cout / n_tile;
   const int num_kb = kh * kw * cb;
   const size_t stage_bytes = kABytes + static_cast<size_t>(n_tile) * 128;
-  const size_t budget = (n_tile <= 128) ? 100 * 1024 : 200 * 1024;
+  static const bool conv_v1 = getenv("ICP_CONV_V1") != nullptr;     // one tile per CTA (bring-up version)
+  const size_t budget = conv_v1 ? ((n_tile <= 128) ? 100 * 1024 : 200 * 1024) : 196 * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > num_kb) stages = num_kb;
+  if (conv_v1 && stages > num_kb) stages = num_kb;
   if (stages < 1) stages = 1;
+  L.persistent = !conv_v1;
   static const bool force_im2col = getenv("ICP_FORCE_IM2COL") != nullptr;
   const bool im2col = force_im2col || !(kh == 1 && kw == 1 && stride == 1);
   // Large stride-1 maps with a real filter footprint: read the input once per tile (conv_halo.cuh).
-  static const bool no_halo = getenv("ICP_NO_HALO") != nullptr;
+  static const bool no_halo = getenv("ICP_HALO") == nullptr;      // opt-in: slower than the persistent im2col kernel today
   static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 30;
   if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256) {
     const int rb = pick_row_bytes(cin), ck = rb / 2;
@@ -436,6 +440,10 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.smem = conv_smem_bytes(stages, n_tile);
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     g_conv_attr_set = true;
   }
   return L;
@@ -450,8 +458,15 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
   }
   ConvArgs a = L.args;
   a.m_total = n * L.pix_per_image;
-  dim3 grid((a.m_total + kBM - 1) / kBM, L.n_tiles);
-  conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
+  const int m_tiles = (a.m_total + kBM - 1) / kBM;
+  if (L.persistent) {
+    const int total = m_tiles * L.n_tiles;
+    conv_igemm_persistent_kernel<<<total < g_num_sms ? total : g_num_sms, kConvThreads, L.smem, st>>>(
+        L.tm_a, L.tm_b, a, m_tiles, L.n_tiles);
+  } else {
+    dim3 grid(m_tiles, L.n_tiles);
+    conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
+  }
   CK(cudaGetLastError());
 }
 
@@ -904,8 +919,7 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
   if (tm) tm->mark();
   {
     const Act& o = e.conv0_out;
-    const long long pix = static_cast<long long>(n) * o.h * o.w;
-    const unsigned grid = static_cast<unsigned>((pix + 127) / 128);
+    const dim3 grid((o.w + kC0TileW - 1) / kC0TileW, (o.h + kC0TileH - 1) / kC0TileH, n);
     if (x_is_u8)
       conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev), n, e.S, e.S, e.d_conv0_w,
                                                   e.d_conv0_scale, e.d_conv0_shift, o.p, o.h, o.w, fmt);

@@ -83,39 +83,58 @@ __device__ __forceinline__ float conv0_load<uint8_t>(const uint8_t* p) {
   return (static_cast<float>(__ldg(p)) * 0.003921568859368563f - 0.5f) * 2.0f;
 }
 
+// Tile = 32 x 4 output pixels per 128-thread CTA; the (9 rows x 65 px x 3 ch) input patch is staged in
+// shared memory with coalesced row-segment loads, converted to fp32 once.
+constexpr int kC0TileW = 32, kC0TileH = 4;
+constexpr int kC0PatchW = (kC0TileW * 2 + 1) * 3;   // 195 values per input row
+constexpr int kC0PatchH = kC0TileH * 2 + 1;         // 9 input rows
+
 template <typename TIn>
 __global__ void __launch_bounds__(128)
 conv0_kernel(const TIn* __restrict__ in, int N, int H, int W, const float* __restrict__ wgt /*[27][32]*/,
              const float* __restrict__ scale, const float* __restrict__ shift, uint16_t* __restrict__ out, int OH,
              int OW, int fmt) {
-  __shared__ float sw[27 * 32];
+  __shared__ __align__(16) float sw[27 * 32];
   __shared__ float ssc[32], ssh[32];
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = wgt[i];
-  if (threadIdx.x < 32) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
+  __shared__ float patch[kC0PatchH][kC0PatchW + 1];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * 32; i += 128) sw[i] = wgt[i];
+  if (tid < 32) { ssc[tid] = scale[tid]; ssh[tid] = shift[tid]; }
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * kC0TileH, ox0 = blockIdx.x * kC0TileW;
+  const int iy0 = oy0 * 2, ix0 = ox0 * 2;
+  const int vals_w = min(kC0PatchW, (W - ix0) * 3);            // valid values in a patch row
+  for (int r = 0; r < kC0PatchH; ++r) {
+    const int iy = iy0 + r;
+    if (iy >= H) break;
+    const TIn* src = in + ((static_cast<size_t>(n) * H + iy) * W + ix0) * 3;
+    for (int j = tid; j < vals_w; j += 128) patch[r][j] = conv0_load<TIn>(src + j);
+  }
   __syncthreads();
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * OH * OW;
-  if (pix >= total) return;
-  const int ox = static_cast<int>(pix % OW);
-  const int oy = static_cast<int>((pix / OW) % OH);
-  const int n = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
+  const int tx = tid & (kC0TileW - 1), ty = tid / kC0TileW;
+  const int ox = ox0 + tx, oy = oy0 + ty;
+  if (ox >= OW || oy >= OH) return;
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-  const TIn* ip = in + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    float x[9];
+    const float* prow = &patch[ty * 2 + r][tx * 6];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) x[j] = conv0_load<TIn>(ip + static_cast<size_t>(r) * W * 3 + j);
+    for (int j = 0; j < 9; ++j) {                                  // j = s*3 + ci
+      const float x = prow[j];
+      const float4* wr = reinterpret_cast<const float4*>(sw + (r * 9 + j) * 32);   // HWIO: ((r*3+s)*3+ci)*32 + co
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const float* wr = sw + (r * 9 + j) * 32;   // HWIO flattened: ((r*3+s)*3+ci)*32 + co, j = s*3+ci
-#pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = fmaf(x[j], wr[c], acc[c]);
+      for (int q = 0; q < 8; ++q) {
+        const float4 w4 = wr[q];
+        acc[4 * q + 0] = fmaf(x, w4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(x, w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(x, w4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(x, w4.w, acc[4 * q + 3]);
+      }
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * 32);
+  uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oy) * OW + ox) * 32);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float f[8];

@@ -245,7 +245,7 @@ def cmd_profile(args):
     for (name, kind, fl, by), t in zip(table, ms):
         tf = fl * n / (t * 1e-3) / 1e12 if t > 0 else 0.0
         gb = by * n / (t * 1e-3) / 1e9 if t > 0 else 0.0
-        rows.append({"name": name, "kind": kind, "ms": float(t), "tflops": tf, "gbs": gb, "share": float(t) / tot})
+        rows.append({"name": name, "kind": int(kind), "ms": float(t), "tflops": float(tf), "gbs": float(gb), "share": float(t) / tot})
         if kind == 1:
             conv_ms += float(t); conv_fl += fl * n
         print("OP %-44s kind=%d ms=%8.4f share=%5.1f%% %8.1f TF/s %8.1f GB/s" % (name, kind, t, 100 * t / tot, tf, gb),
@@ -253,7 +253,7 @@ def cmd_profile(args):
     print("PROFILE n=%d %s: sum=%.3f ms ; conv_igemm %.3f ms (%.1f%%) -> %.1f TFLOP/s" % (
         n, args.precision, tot, conv_ms, 100 * conv_ms / tot, conv_fl / (conv_ms * 1e-3) / 1e12), flush=True)
     with open(os.path.join(OUT, "profile_ops_n%d_%s.json" % (n, args.precision)), "w") as f:
-        json.dump({"n": n, "precision": args.precision, "sum_ms": tot, "conv_igemm_ms": conv_ms, "ops": rows}, f, indent=1)
+        json.dump({"n": n, "precision": args.precision, "sum_ms": float(tot), "conv_igemm_ms": float(conv_ms), "ops": rows}, f, indent=1)
     return 0
 
 
