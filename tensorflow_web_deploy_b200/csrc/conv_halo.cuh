@@ -1,42 +1,44 @@
-// Halo-resident implicit-GEMM convolution (stride 1, kh x kw > 1x1) for sm_100a.
+// Halo-resident, weight-resident, persistent implicit-GEMM convolution (stride 1, kh x kw > 1x1).
 //
-// conv_igemm_kernel fetches every filter tap's A tile from L2 again, so a k_h x k_w conv moves each input
-// pixel k_h*k_w times across the L2->SM fabric; ncu shows the stem and the 35x35 convs pinned at that
-// fabric's ~9 TB/s (profiles/r01_ncu_conv_igemm_v1_*.csv).  Here the input is read ONCE per tile:
+// conv_igemm_* fetches every filter tap's A tile and every tile's weights from L2 again, so the stem and
+// the 35x35 convs are pinned at the L2->SM fabric (ncu: conv1 moves 3.98 GB across it for 182 MB of input,
+// profiles/r01_ncu_conv_igemm_v1_*.csv).  Here both operands are fetched once:
 //
-//  * Outputs are indexed on the *padded grid*: position p = oh * wp + wc with wp = iw + 2*pad_w columns, so
-//    the input pixel feeding output p through tap (r,s) is padded-grid position p + r*wp + s — a constant
-//    shift.  Columns wc >= ow are computed and discarded (2..11 % extra MMA work on the maps this kernel is
-//    used for).
-//  * For each block of ck = row_bytes/2 input channels, ONE 4-D tiled TMA box {ck, wp, rows, 1} starting at
-//    (w = -pad_w, h = first_row - pad_h) lands the whole halo strip in shared memory in padded-grid order;
-//    the unit's out-of-bounds zero fill IS the SAME padding.  row_bytes in {32, 64, 128} is chosen per layer
-//    so that Cin = 32/48/80/96 waste no MMA work (SWIZZLE_32B/64B/128B).
-//  * The MMA issuer walks the taps by moving the A descriptor's start address by (r*wp + s) * row_bytes: the
-//    UMMA swizzle is a function of the absolute smem address, exactly like the TMA write that produced the
-//    strip, so a shifted start reads the shifted pixels.  B tiles ([n_tile x ck] per (channel block, tap))
-//    stream through their own small ring.
-//
-// Epilogue as in conv_igemm_kernel (TMEM -> regs -> scale/shift/ReLU -> 16-bit -> concat slice), with the
-// padded-grid position mapped back to (oh, ow) and the discard columns masked.
+//  * Outputs are indexed on the *padded grid*: position p = oh * wp + wc with wp = iw + 2*pad_w columns, so the
+//    input pixel feeding output p through tap (r,s) is padded-grid position p + r*wp + s — a constant shift.
+//    Columns wc >= ow are computed and discarded (1..11 % extra MMA work on the maps this kernel serves).
+//  * A "band" = T consecutive 128-position sub-tiles of one image.  For each block of ck = row_bytes/2 input
+//    channels ONE 4-D tiled TMA box {ck, wp, rows, 1} at (w = -pad_w, h = first_row - pad_h) lands the band's
+//    whole halo strip in shared memory in padded-grid order; out-of-bounds zero fill IS the SAME padding.
+//    row_bytes in {32, 64, 128} (SWIZZLE_32B/64B/128B) is chosen per layer so Cin = 32/48/96 waste no MMA work.
+//  * The whole packed weight matrix ([chunk][tap][n_tile x ck]) is loaded into shared memory once per SM and
+//    stays there while the persistent CTA walks its bands.
+//  * The MMA issuer selects tap (r,s) of sub-tile j by moving the A descriptor's start address to
+//    (j*128 + r*wp + s) * row_bytes inside the strip: the UMMA swizzle is a function of the absolute smem
+//    address, exactly like the TMA write that produced the strip, so a shifted start reads the shifted pixels.
+//  * T accumulators per band, double-buffered in TMEM (2*T*n_tile <= 512 columns): the epilogue of band i
+//    overlaps the strip load and MMAs of band i+1.
 #pragma once
 #include "conv_igemm.cuh"
 
 namespace icp {
 
 struct HaloArgs {
+  int n_images;
   int oh, ow;           // valid output size (per image)
   int wp;               // padded grid width = iw + 2 * pad_w
   int pad_h, pad_w;
   int kh, kw;
   int chunks;           // ceil(cin / ck)
   int row_bytes;        // 32 / 64 / 128  (ck = row_bytes / 2 channels per block)
+  int T;                // 128-position sub-tiles per band
   int strip_rows;       // padded-grid rows per strip
   int strip_bytes;      // strip_rows * wp * row_bytes rounded up to 1024
-  int tiles_per_image;  // ceil(oh * wp / 128)
-  int n_tile;
-  int tmem_cols;
-  int b_stages;
+  int bands_per_image;  // ceil(oh * wp / (128 * T))
+  int n_tile;           // = cout (<= 256)
+  int acc_cols;         // TMEM columns of one accumulator set: T * n_tile
+  int tmem_cols;        // power of two >= 2 * acc_cols
+  int w_bytes;          // chunks * taps * n_tile * row_bytes (resident weights)
   int fmt;
   int relu;
   void* out;
@@ -45,7 +47,7 @@ struct HaloArgs {
   const float* shift;
 };
 
-__global__ void __launch_bounds__(kConvThreads)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -56,40 +58,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
-  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;           // multiple of 512
-  const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
   const uint32_t strip0 = base;
-  const uint32_t bring = base + 2u * a.strip_bytes;
-  const uint32_t bar_base = bring + a.b_stages * b_stride;
-  // barriers: a_full[2], a_empty[2], b_full[S], b_empty[S], tmem_full, then the TMEM slot
-  auto a_full = [&](int i) { return bar_base + 8u * i; };
-  auto a_empty = [&](int i) { return bar_base + 16u + 8u * i; };
-  auto b_full = [&](int i) { return bar_base + 32u + 8u * i; };
-  auto b_empty = [&](int i) { return bar_base + 32u + 8u * (a.b_stages + i); };
-  const uint32_t tmem_full_bar = bar_base + 32u + 16u * a.b_stages;
-  const uint32_t tmem_slot = tmem_full_bar + 8u;
-  float* s_scale = reinterpret_cast<float*>(gbase + (bar_base - base) + 256);
+  const uint32_t wbase = base + 2u * a.strip_bytes;                       // resident weights
+  const uint32_t bar_base = wbase + ((static_cast<uint32_t>(a.w_bytes) + 1023u) & ~1023u);
+  // barriers: strip_full[2], strip_empty[2], tmem_full[2], tmem_empty[2], w_full, then the TMEM slot
+  auto strip_full = [&](int i) { return bar_base + 8u * i; };
+  auto strip_empty = [&](int i) { return bar_base + 16u + 8u * i; };
+  auto tmem_full = [&](int i) { return bar_base + 32u + 8u * i; };
+  auto tmem_empty = [&](int i) { return bar_base + 48u + 8u * i; };
+  const uint32_t w_full = bar_base + 64u;
+  const uint32_t tmem_slot = bar_base + 72u;
+  float* s_scale = reinterpret_cast<float*>(gbase + (bar_base - base) + 128);
   float* s_shift = s_scale + 256;
 
-  const int tile = blockIdx.x % a.tiles_per_image;
-  const int img = blockIdx.x / a.tiles_per_image;
-  const int n_base = blockIdx.y * a.n_tile;
-  const int p0 = tile * kBM;                       // first padded-grid position of this tile
-  const int h_first = p0 / a.wp;                   // first padded-grid row held by the strip
   const int taps = a.kh * a.kw;
   const int ck = a.row_bytes / 2;
+  const int total_bands = a.bands_per_image * a.n_images;
+  const int positions = a.oh * a.wp;                 // padded-grid positions holding outputs, per image
+  const uint32_t tap_bytes = static_cast<uint32_t>(a.n_tile) * rb;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(a_full(i), 1); ptx::mbar_init(a_empty(i), 1); }
-    for (int i = 0; i < a.b_stages; ++i) { ptx::mbar_init(b_full(i), 1); ptx::mbar_init(b_empty(i), 1); }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(strip_full(i), 1);
+      ptx::mbar_init(strip_empty(i), 1);
+      ptx::mbar_init(tmem_full(i), 1);
+      ptx::mbar_init(tmem_empty(i), 128);
+    }
+    ptx::mbar_init(w_full, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, a.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < a.n_tile; i += 128) {
+      s_scale[i] = __ldg(a.scale + i);
+      s_shift[i] = __ldg(a.shift + i);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -98,23 +107,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA producer: strip(c+1) is requested before chunk c's weights ----------------
+      // ---------------- TMA producer ----------------
+      ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.w_bytes));
+      for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
       const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
-      auto load_strip = [&](int c) {
-        const int sa = c & 1;
-        ptx::mbar_wait(a_empty(sa), ((c >> 1) & 1) ^ 1u);
-        ptx::mbar_expect_tx(a_full(sa), strip_tx);
-        ptx::tma_load_4d(strip0 + sa * a.strip_bytes, &tm_a, a_full(sa), c * ck, -a.pad_w, h_first - a.pad_h, img);
-      };
-      load_strip(0);
-      int bi = 0;
-      for (int c = 0; c < a.chunks; ++c) {
-        if (c + 1 < a.chunks) load_strip(c + 1);
-        for (int tap = 0; tap < taps; ++tap, ++bi) {
-          const int sb = bi % a.b_stages;
-          ptx::mbar_wait(b_empty(sb), ((bi / a.b_stages) & 1) ^ 1u);
-          ptx::mbar_expect_tx(b_full(sb), b_bytes);
-          ptx::tma_load_2d(bring + sb * b_stride, &tm_b, b_full(sb), (c * taps + tap) * ck, n_base);
+      uint32_t it = 0;
+      for (int band = blockIdx.x; band < total_bands; band += gridDim.x) {
+        const int img = band / a.bands_per_image;
+        const int p0 = (band - img * a.bands_per_image) * kBM * a.T;
+        const int h_first = p0 / a.wp;
+        for (int c = 0; c < a.chunks; ++c, ++it) {
+          const uint32_t s = it & 1u;
+          ptx::mbar_wait(strip_empty(s), ((it >> 1) & 1u) ^ 1u);
+          ptx::mbar_expect_tx(strip_full(s), strip_tx);
+          ptx::tma_load_4d(strip0 + s * a.strip_bytes, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h, img);
         }
       }
     }
@@ -123,67 +129,87 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
       const int ksteps = a.row_bytes / 32;
-      const uint32_t local0 = static_cast<uint32_t>(p0 - h_first * a.wp);   // tile's first position inside the strip
-      int bi = 0;
-      uint32_t acc = 0;
-      for (int c = 0; c < a.chunks; ++c) {
-        const int sa = c & 1;
-        ptx::mbar_wait(a_full(sa), (c >> 1) & 1);
-        const uint32_t strip = strip0 + sa * a.strip_bytes;
-        for (int tap = 0; tap < taps; ++tap, ++bi) {
-          const int sb = bi % a.b_stages;
-          ptx::mbar_wait(b_full(sb), (bi / a.b_stages) & 1);
+      ptx::mbar_wait(w_full, 0);
+      uint32_t it = 0, lb = 0;
+      for (int band = blockIdx.x; band < total_bands; band += gridDim.x, ++lb) {
+        const int img = band / a.bands_per_image;
+        const int p0 = (band - img * a.bands_per_image) * kBM * a.T;
+        const int h_first = p0 / a.wp;
+        const uint32_t local0 = static_cast<uint32_t>(p0 - h_first * a.wp);
+        const uint32_t as = lb & 1u;
+        ptx::mbar_wait(tmem_empty(as), ((lb >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        for (int c = 0; c < a.chunks; ++c, ++it) {
+          const uint32_t s = it & 1u;
+          ptx::mbar_wait(strip_full(s), (it >> 1) & 1u);
           ptx::tc_fence_after();
-          const int r = tap / a.kw;
-          const uint32_t shift = static_cast<uint32_t>(r * a.wp + (tap - r * a.kw));
-          const uint32_t a_addr = strip + (local0 + shift) * rb;
-          const uint32_t b_addr = bring + sb * b_stride;
-          for (int k = 0; k < ksteps; ++k) {
-            ptx::umma_f16(tmem_base, ptx::make_smem_desc_rows(a_addr + 32u * k, rb),
-                          ptx::make_smem_desc_rows(b_addr + 32u * k, rb), idesc, acc);
-            acc = 1;
+          const uint32_t strip = strip0 + s * a.strip_bytes;
+          for (int j = 0; j < a.T; ++j) {
+            if (p0 + j * kBM >= positions) break;              // sub-tile past the image's last output row
+            const uint32_t tacc = tmem_base + as * a.acc_cols + j * a.n_tile;
+            for (int tap = 0; tap < taps; ++tap) {
+              const int r = tap / a.kw;
+              const uint32_t shift = static_cast<uint32_t>(r * a.wp + (tap - r * a.kw));
+              const uint32_t a_addr = strip + (local0 + j * kBM + shift) * rb;
+              const uint32_t b_addr = wbase + (c * taps + tap) * tap_bytes;
+              for (int k = 0; k < ksteps; ++k)
+                ptx::umma_f16(tacc, ptx::make_smem_desc_rows(a_addr + 32u * k, rb),
+                              ptx::make_smem_desc_rows(b_addr + 32u * k, rb), idesc, (c | tap | k) != 0);
+            }
           }
-          ptx::umma_commit(b_empty(sb));
+          ptx::umma_commit(strip_empty(s));
         }
-        ptx::umma_commit(a_empty(sa));
+        ptx::umma_commit(tmem_full(as));
       }
-      ptx::umma_commit(tmem_full_bar);
     }
   } else {
     // ---------------- epilogue (warps 2..5) ----------------
-    const int et = threadIdx.x - 64;
-    for (int i = et; i < a.n_tile; i += 128) {
-      s_scale[i] = __ldg(a.scale + n_base + i);
-      s_shift[i] = __ldg(a.shift + n_base + i);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int quarter = warp & 3;
-    const int p = p0 + quarter * 32 + lane;        // padded-grid position of this thread's row
-    const int oy = p / a.wp;
-    const int ox = p - oy * a.wp;
-    const bool valid = (oy < a.oh) && (ox < a.ow);
-    uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) +
-                     ((static_cast<size_t>(img) * a.oh + oy) * a.ow + ox) * a.ldo + a.coff + n_base;
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-      uint32_t v[16];
-      ptx::tmem_ld_32x32b_x16(taddr + c0, v);
-      ptx::tmem_ld_wait();
-      uint32_t q[8];
+    const int row = quarter * 32 + lane;
+    uint32_t lb = 0;
+    for (int band = blockIdx.x; band < total_bands; band += gridDim.x, ++lb) {
+      const int img = band / a.bands_per_image;
+      const int p0 = (band - img * a.bands_per_image) * kBM * a.T;
+      const uint32_t as = lb & 1u;
+      ptx::mbar_wait(tmem_full(as), (lb >> 1) & 1u);
+      ptx::tc_fence_after();
+      for (int j = 0; j < a.T; ++j) {
+        if (p0 + j * kBM >= positions) break;
+        const int p = p0 + j * kBM + row;
+        const int oy = p / a.wp;
+        const int ox = p - oy * a.wp;
+        const bool valid = (oy < a.oh) && (ox < a.ow);
+        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) +
+                         ((static_cast<size_t>(img) * a.oh + oy) * a.ow + ox) * a.ldo + a.coff;
+        const uint32_t taddr = tmem_base + as * a.acc_cols + j * a.n_tile + (static_cast<uint32_t>(quarter * 32) << 16);
+        for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
+          uint32_t v[32];
+          const bool two = c0 + 16 < a.n_tile;
+          ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          if (two) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float x0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0 + 2 * j], s_shift[c0 + 2 * j]);
-        float x1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 2 * j + 1], s_shift[c0 + 2 * j + 1]);
-        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-        q[j] = pack2(x0, x1, a.fmt);
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const int cc = c0 + 16 * h;
+            uint32_t q[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float x0 = fmaf(__uint_as_float(v[16 * h + 2 * i]), s_scale[cc + 2 * i], s_shift[cc + 2 * i]);
+              float x1 = fmaf(__uint_as_float(v[16 * h + 2 * i + 1]), s_scale[cc + 2 * i + 1], s_shift[cc + 2 * i + 1]);
+              if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+              q[i] = pack2(x0, x1, a.fmt);
+            }
+            if (valid) {
+              uint4* dst = reinterpret_cast<uint4*>(orow + cc);
+              dst[0] = make_uint4(q[0], q[1], q[2], q[3]);
+              dst[1] = make_uint4(q[4], q[5], q[6], q[7]);
+            }
+          }
+        }
       }
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-        dst[0] = make_uint4(q[0], q[1], q[2], q[3]);
-        dst[1] = make_uint4(q[4], q[5], q[6], q[7]);
-      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tmem_empty(as));
     }
   }
 
@@ -196,9 +222,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
-inline size_t halo_smem_bytes(int strip_bytes, int b_stages, int n_tile, int row_bytes) {
-  const size_t b_stride = (static_cast<size_t>(n_tile) * row_bytes + 1023) & ~size_t(1023);
-  return 1024 + 2 * static_cast<size_t>(strip_bytes) + b_stages * b_stride + 256 + 2048;
+inline size_t halo_smem_bytes(int strip_bytes, int w_bytes) {
+  return 1024 + 2 * static_cast<size_t>(strip_bytes) + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 128 + 2048;
 }
 
 }  // namespace icp

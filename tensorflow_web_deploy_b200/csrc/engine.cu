@@ -256,6 +256,7 @@ struct ConvLayer {
   HaloArgs hargs{};
 };
 
+static int g_num_sms = 148;
 static int pick_n_tile(int cout) {
   if (cout <= 256) return cout;
   for (int parts = 2; parts <= 16; ++parts)
@@ -268,7 +269,6 @@ static int pow2_cols(int n) {
   return c;
 }
 static bool g_conv_attr_set = false;
-static int g_num_sms = 148;
 
 // Packs HWIO fp32 weights into the K-major [cout][taps][cblocks*64] 16-bit matrix the B-operand TMA
 // reads, zero-filling the channel tail of every tap.
@@ -345,24 +345,40 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   if (stages > kMaxStages) stages = kMaxStages;
   if (conv_v1 && stages > num_kb) stages = num_kb;
   if (stages < 1) stages = 1;
-  L.persistent = !conv_v1;
+  static const bool conv_v2_all = getenv("ICP_CONV_V2_ALL") != nullptr;
+  // narrow layers (n_tile < 128) keep several short-lived CTAs per SM: measured faster than one persistent CTA
+  const bool persistent = !conv_v1 && (conv_v2_all || n_tile >= 128);
+  if (!persistent) {
+    const size_t b1 = (n_tile <= 128) ? 100 * 1024 : 200 * 1024;
+    stages = static_cast<int>(b1 / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > num_kb) stages = num_kb;
+    if (stages < 1) stages = 1;
+  }
+  L.persistent = persistent;
   static const bool force_im2col = getenv("ICP_FORCE_IM2COL") != nullptr;
   const bool im2col = force_im2col || !(kh == 1 && kw == 1 && stride == 1);
-  // Large stride-1 maps with a real filter footprint: read the input once per tile (conv_halo.cuh).
-  static const bool no_halo = getenv("ICP_HALO") == nullptr;      // opt-in: slower than the persistent im2col kernel today
+  // Large stride-1 maps with a real filter footprint whose packed weights fit in shared memory: read input and
+  // weights once (conv_halo.cuh).  ICP_NO_HALO=1 falls back to the im2col kernel for A/B comparison.
+  static const bool no_halo = getenv("ICP_NO_HALO") != nullptr;
   static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 30;
-  if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256) {
+  if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256 &&
+      cout <= 256) {
     const int rb = pick_row_bytes(cin), ck = rb / 2;
     const int wp = in.w + 2 * pad_w;
     const int chunks = (cin + ck - 1) / ck;
-    const int strip_rows = (kh - 1) + 1 + (wp - 1 + (kBM - 1) + (kw - 1)) / wp;
-    const int strip_bytes = ((strip_rows * wp * rb) + 1023) & ~1023;
-    const size_t b_stride = (static_cast<size_t>(n_tile) * rb + 1023) & ~size_t(1023);
-    int b_stages = 4;
-    while (b_stages > 2 && halo_smem_bytes(strip_bytes, b_stages, n_tile, rb) > 110 * 1024) --b_stages;
-    const size_t smem = halo_smem_bytes(strip_bytes, b_stages, n_tile, rb);
-    if (smem <= 220 * 1024) {
-      (void)b_stride;
+    int T = 4;
+    while (T > 1 && 2 * T * cout > 512) T >>= 1;
+    const int w_bytes = chunks * kh * kw * cout * rb;
+    int strip_rows = 0, strip_bytes = 0;
+    size_t smem = 0;
+    for (; T >= 1; T >>= 1) {
+      strip_rows = (kh - 1) + 1 + (wp - 1 + (T * kBM - 1) + (kw - 1)) / wp;
+      strip_bytes = ((strip_rows * wp * rb) + 1023) & ~1023;
+      smem = halo_smem_bytes(strip_bytes, w_bytes);
+      if (smem <= 225 * 1024 && strip_rows <= 256) break;
+    }
+    if (T >= 1 && 2 * T * cout <= 512) {
       std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt);
       void* d_w = pool.alloc(wp_host.size() * 2);
       CK(cudaMemcpy(d_w, wp_host.data(), wp_host.size() * 2, cudaMemcpyHostToDevice));
@@ -372,17 +388,23 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
       const uint64_t kp = static_cast<uint64_t>(chunks) * kh * kw * ck;
       L.halo = true;
-      L.tm_b = make_tm_2d_rows(d_w, cout, kp, n_tile, rb, fmt);
+      L.n_tiles = 1;
+      L.tm_b = make_tm_2d_rows(d_w, cout, kp, cout, rb, fmt);
       L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
       HaloArgs& h = L.hargs;
+      h.n_images = 0;
       h.oh = oh; h.ow = ow; h.wp = wp; h.pad_h = pad_h; h.pad_w = pad_w; h.kh = kh; h.kw = kw;
-      h.chunks = chunks; h.row_bytes = rb; h.strip_rows = strip_rows; h.strip_bytes = strip_bytes;
-      h.tiles_per_image = (oh * wp + kBM - 1) / kBM;
-      h.n_tile = n_tile; h.tmem_cols = pow2_cols(n_tile); h.b_stages = b_stages; h.fmt = fmt; h.relu = relu ? 1 : 0;
+      h.chunks = chunks; h.row_bytes = rb; h.T = T; h.strip_rows = strip_rows; h.strip_bytes = strip_bytes;
+      h.bands_per_image = (oh * wp + kBM * T - 1) / (kBM * T);
+      h.n_tile = cout; h.acc_cols = T * cout; h.tmem_cols = pow2_cols(2 * T * cout); h.w_bytes = w_bytes;
+      h.fmt = fmt; h.relu = relu ? 1 : 0;
       h.out = out.p; h.ldo = out.c; h.coff = out_coff; h.scale = d_scale; h.shift = d_shift;
       L.smem = smem;
       if (!g_halo_attr_set) {
         CK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
         g_halo_attr_set = true;
       }
       return L;
@@ -451,8 +473,10 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
 
 static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
   if (L.halo) {
-    dim3 grid(L.hargs.tiles_per_image * n, L.n_tiles);
-    conv_halo_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.hargs);
+    HaloArgs h = L.hargs;
+    h.n_images = n;
+    const int bands = h.bands_per_image * n;
+    conv_halo_kernel<<<bands < g_num_sms ? bands : g_num_sms, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, h);
     CK(cudaGetLastError());
     return;
   }

@@ -83,11 +83,12 @@ __device__ __forceinline__ float conv0_load<uint8_t>(const uint8_t* p) {
   return (static_cast<float>(__ldg(p)) * 0.003921568859368563f - 0.5f) * 2.0f;
 }
 
-// Tile = 32 x 4 output pixels per 128-thread CTA; the (9 rows x 65 px x 3 ch) input patch is staged in
-// shared memory with coalesced row-segment loads, converted to fp32 once.
-constexpr int kC0TileW = 32, kC0TileH = 4;
+// Tile = 32 x 8 output pixels per 128-thread CTA, two output rows (ty, ty+4) per thread so every weight
+// fetched from shared memory feeds two FMAs; the (17 rows x 65 px x 3 ch) input patch is staged in shared
+// memory with coalesced row-segment loads and converted to fp32 once.
+constexpr int kC0TileW = 32, kC0TileH = 8;
 constexpr int kC0PatchW = (kC0TileW * 2 + 1) * 3;   // 195 values per input row
-constexpr int kC0PatchH = kC0TileH * 2 + 1;         // 9 input rows
+constexpr int kC0PatchH = kC0TileH * 2 + 1;         // 17 input rows
 
 template <typename TIn>
 __global__ void __launch_bounds__(128)
@@ -111,36 +112,50 @@ conv0_kernel(const TIn* __restrict__ in, int N, int H, int W, const float* __res
     for (int j = tid; j < vals_w; j += 128) patch[r][j] = conv0_load<TIn>(src + j);
   }
   __syncthreads();
-  const int tx = tid & (kC0TileW - 1), ty = tid / kC0TileW;
-  const int ox = ox0 + tx, oy = oy0 + ty;
-  if (ox >= OW || oy >= OH) return;
-  float acc[32];
+  const int tx = tid & (kC0TileW - 1), ty = tid / kC0TileW;      // ty in 0..3; rows ty and ty + 4
+  const int ox = ox0 + tx;
+  const int oyA = oy0 + ty, oyB = oy0 + ty + 4;
+  if (ox >= OW || oyA >= OH) return;
+  const bool hasB = oyB < OH;
+  float accA[32], accB[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int c = 0; c < 32; ++c) { accA[c] = 0.f; accB[c] = 0.f; }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const float* prow = &patch[ty * 2 + r][tx * 6];
+    const float* pa = &patch[ty * 2 + r][tx * 6];
+    const float* pb = &patch[(ty + 4) * 2 + r][tx * 6];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {                                  // j = s*3 + ci
-      const float x = prow[j];
+      const float xa = pa[j];
+      const float xb = pb[j];
       const float4* wr = reinterpret_cast<const float4*>(sw + (r * 9 + j) * 32);   // HWIO: ((r*3+s)*3+ci)*32 + co
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 w4 = wr[q];
-        acc[4 * q + 0] = fmaf(x, w4.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(x, w4.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(x, w4.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(x, w4.w, acc[4 * q + 3]);
+        accA[4 * q + 0] = fmaf(xa, w4.x, accA[4 * q + 0]);
+        accA[4 * q + 1] = fmaf(xa, w4.y, accA[4 * q + 1]);
+        accA[4 * q + 2] = fmaf(xa, w4.z, accA[4 * q + 2]);
+        accA[4 * q + 3] = fmaf(xa, w4.w, accA[4 * q + 3]);
+        accB[4 * q + 0] = fmaf(xb, w4.x, accB[4 * q + 0]);
+        accB[4 * q + 1] = fmaf(xb, w4.y, accB[4 * q + 1]);
+        accB[4 * q + 2] = fmaf(xb, w4.z, accB[4 * q + 2]);
+        accB[4 * q + 3] = fmaf(xb, w4.w, accB[4 * q + 3]);
       }
     }
   }
-  uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oy) * OW + ox) * 32);
+  uint4* opA = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oyA) * OW + ox) * 32);
+  uint4* opB = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oyB) * OW + ox) * 32);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(acc[g * 8 + j], ssc[g * 8 + j], ssh[g * 8 + j]), 0.f);
-    op[g] = pack8(f, fmt);
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(accA[g * 8 + j], ssc[g * 8 + j], ssh[g * 8 + j]), 0.f);
+    opA[g] = pack8(f, fmt);
+    if (hasB) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(accB[g * 8 + j], ssc[g * 8 + j], ssh[g * 8 + j]), 0.f);
+      opB[g] = pack8(f, fmt);
+    }
   }
 }
 
