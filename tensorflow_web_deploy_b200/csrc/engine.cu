@@ -361,7 +361,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   // Large stride-1 maps with a real filter footprint whose packed weights fit in shared memory: read input and
   // weights once (conv_halo.cuh).  ICP_NO_HALO=1 falls back to the im2col kernel for A/B comparison.
   static const bool no_halo = getenv("ICP_NO_HALO") != nullptr;
-  static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 30;
+  static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 100;   // stem only: measured slower on 35x35
   if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256 &&
       cout <= 256) {
     const int rb = pick_row_bytes(cin), ck = rb / 2;
@@ -547,8 +547,7 @@ struct icp_engine {
   int graph_k = 5;
   uint8_t* d_rgb = nullptr;         // staging for icp_classify_rgb8
   size_t d_rgb_cap = 0;
-  float* d_conv0_w = nullptr;       // [27][32]
-  float *d_conv0_scale = nullptr, *d_conv0_shift = nullptr;
+  Conv0Params conv0{};              // weights + folded BN of the Cin=3 stem conv, passed by value
   Act conv0_out;
   std::vector<Op> ops;              // everything after conv0 up to the last block
   Act final_act;                    // 8x8x2048
@@ -818,12 +817,9 @@ struct Builder {
       const HostTensor& w = blob_get(blob, "conv0/weights", {3, 3, 3, 32});
       std::vector<float> scale, shift;
       bn_fold("conv0", 32, scale, shift);
-      e.d_conv0_w = static_cast<float*>(e.pool.alloc(27 * 32 * 4));
-      e.d_conv0_scale = static_cast<float*>(e.pool.alloc(32 * 4));
-      e.d_conv0_shift = static_cast<float*>(e.pool.alloc(32 * 4));
-      CK(cudaMemcpy(e.d_conv0_w, w.data.data(), 27 * 32 * 4, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(e.d_conv0_scale, scale.data(), 32 * 4, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(e.d_conv0_shift, shift.data(), 32 * 4, cudaMemcpyHostToDevice));
+      memcpy(e.conv0.w, w.data.data(), sizeof e.conv0.w);
+      memcpy(e.conv0.scale, scale.data(), sizeof e.conv0.scale);
+      memcpy(e.conv0.shift, shift.data(), sizeof e.conv0.shift);
       const int o = (S - 3) / 2 + 1;
       e.conv0_out = alloc_act(o, o, 32);
       e.conv_macs_per_image += static_cast<long long>(o) * o * 32 * 27;
@@ -943,13 +939,14 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
   if (tm) tm->mark();
   {
     const Act& o = e.conv0_out;
-    const dim3 grid((o.w + kC0TileW - 1) / kC0TileW, (o.h + kC0TileH - 1) / kC0TileH, n);
+    const long long pix = static_cast<long long>(n) * o.h * o.w;
+    const unsigned grid = static_cast<unsigned>((pix + 127) / 128);
     if (x_is_u8)
-      conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev), n, e.S, e.S, e.d_conv0_w,
-                                                  e.d_conv0_scale, e.d_conv0_shift, o.p, o.h, o.w, fmt);
+      conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev), n, e.S, e.S, e.conv0, o.p, o.h,
+                                                  o.w, fmt);
     else
-      conv0_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x_dev), n, e.S, e.S, e.d_conv0_w,
-                                                e.d_conv0_scale, e.d_conv0_shift, o.p, o.h, o.w, fmt);
+      conv0_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x_dev), n, e.S, e.S, e.conv0, o.p, o.h, o.w,
+                                                fmt);
     CK(cudaGetLastError());
     ++launches;
     if (tm) tm->mark();

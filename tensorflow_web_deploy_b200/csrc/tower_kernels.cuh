@@ -83,79 +83,48 @@ __device__ __forceinline__ float conv0_load<uint8_t>(const uint8_t* p) {
   return (static_cast<float>(__ldg(p)) * 0.003921568859368563f - 0.5f) * 2.0f;
 }
 
-// Tile = 32 x 8 output pixels per 128-thread CTA, two output rows (ty, ty+4) per thread so every weight
-// fetched from shared memory feeds two FMAs; the (17 rows x 65 px x 3 ch) input patch is staged in shared
-// memory with coalesced row-segment loads and converted to fp32 once.
-constexpr int kC0TileW = 32, kC0TileH = 8;
-constexpr int kC0PatchW = (kC0TileW * 2 + 1) * 3;   // 195 values per input row
-constexpr int kC0PatchH = kC0TileH * 2 + 1;         // 17 input rows
+// The 27x32 weights and the folded BN vectors travel as a __grid_constant__ kernel parameter (3.7 KB): with
+// the tap/channel loops fully unrolled every weight is an FFMA constant-bank operand, so the inner loop is
+// pure FP32 FMA issue — no shared-memory broadcast traffic (which bounded the earlier smem-weight versions
+// at ~3x the FMA floor).  One thread = one output pixel x 32 channels; the 27 inputs come through L1.
+struct Conv0Params {
+  float w[27 * 32];     // HWIO flattened: ((r*3+s)*3+ci)*32 + co
+  float scale[32];
+  float shift[32];
+};
 
 template <typename TIn>
 __global__ void __launch_bounds__(128)
-conv0_kernel(const TIn* __restrict__ in, int N, int H, int W, const float* __restrict__ wgt /*[27][32]*/,
-             const float* __restrict__ scale, const float* __restrict__ shift, uint16_t* __restrict__ out, int OH,
-             int OW, int fmt) {
-  __shared__ __align__(16) float sw[27 * 32];
-  __shared__ float ssc[32], ssh[32];
-  __shared__ float patch[kC0PatchH][kC0PatchW + 1];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 27 * 32; i += 128) sw[i] = wgt[i];
-  if (tid < 32) { ssc[tid] = scale[tid]; ssh[tid] = shift[tid]; }
-  const int n = blockIdx.z;
-  const int oy0 = blockIdx.y * kC0TileH, ox0 = blockIdx.x * kC0TileW;
-  const int iy0 = oy0 * 2, ix0 = ox0 * 2;
-  const int vals_w = min(kC0PatchW, (W - ix0) * 3);            // valid values in a patch row
-  for (int r = 0; r < kC0PatchH; ++r) {
-    const int iy = iy0 + r;
-    if (iy >= H) break;
-    const TIn* src = in + ((static_cast<size_t>(n) * H + iy) * W + ix0) * 3;
-    for (int j = tid; j < vals_w; j += 128) patch[r][j] = conv0_load<TIn>(src + j);
-  }
-  __syncthreads();
-  const int tx = tid & (kC0TileW - 1), ty = tid / kC0TileW;      // ty in 0..3; rows ty and ty + 4
-  const int ox = ox0 + tx;
-  const int oyA = oy0 + ty, oyB = oy0 + ty + 4;
-  if (ox >= OW || oyA >= OH) return;
-  const bool hasB = oyB < OH;
-  float accA[32], accB[32];
+conv0_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_constant__ Conv0Params p,
+             uint16_t* __restrict__ out, int OH, int OW, int fmt) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * OH * OW;
+  if (pix >= total) return;
+  const int ox = static_cast<int>(pix % OW);
+  const int oy = static_cast<int>((pix / OW) % OH);
+  const int n = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
+  float acc[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) { accA[c] = 0.f; accB[c] = 0.f; }
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  const TIn* ip = in + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const float* pa = &patch[ty * 2 + r][tx * 6];
-    const float* pb = &patch[(ty + 4) * 2 + r][tx * 6];
+    float x[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {                                  // j = s*3 + ci
-      const float xa = pa[j];
-      const float xb = pb[j];
-      const float4* wr = reinterpret_cast<const float4*>(sw + (r * 9 + j) * 32);   // HWIO: ((r*3+s)*3+ci)*32 + co
+    for (int j = 0; j < 9; ++j) x[j] = conv0_load<TIn>(ip + static_cast<size_t>(r) * W * 3 + j);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 w4 = wr[q];
-        accA[4 * q + 0] = fmaf(xa, w4.x, accA[4 * q + 0]);
-        accA[4 * q + 1] = fmaf(xa, w4.y, accA[4 * q + 1]);
-        accA[4 * q + 2] = fmaf(xa, w4.z, accA[4 * q + 2]);
-        accA[4 * q + 3] = fmaf(xa, w4.w, accA[4 * q + 3]);
-        accB[4 * q + 0] = fmaf(xb, w4.x, accB[4 * q + 0]);
-        accB[4 * q + 1] = fmaf(xb, w4.y, accB[4 * q + 1]);
-        accB[4 * q + 2] = fmaf(xb, w4.z, accB[4 * q + 2]);
-        accB[4 * q + 3] = fmaf(xb, w4.w, accB[4 * q + 3]);
-      }
+    for (int j = 0; j < 9; ++j) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = fmaf(x[j], p.w[(r * 9 + j) * 32 + c], acc[c]);
     }
   }
-  uint4* opA = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oyA) * OW + ox) * 32);
-  uint4* opB = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oyB) * OW + ox) * 32);
+  uint4* op = reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * 32);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(accA[g * 8 + j], ssc[g * 8 + j], ssh[g * 8 + j]), 0.f);
-    opA[g] = pack8(f, fmt);
-    if (hasB) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(accB[g * 8 + j], ssc[g * 8 + j], ssh[g * 8 + j]), 0.f);
-      opB[g] = pack8(f, fmt);
-    }
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(acc[g * 8 + j], p.scale[g * 8 + j], p.shift[g * 8 + j]), 0.f);
+    op[g] = pack8(f, fmt);
   }
 }
 
