@@ -224,7 +224,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                             const ConvArgs a, const int m_tiles, const int n_tiles) {
+                             const ConvArgs a, const int m_tiles, const int n_tiles, const int csize) {
+  // csize > 1: launched as thread-block clusters of `csize` CTAs that walk `csize` consecutive M tiles of the
+  // same N tile in lock-step.  Each CTA fetches 1/csize of the weight tile (tm_b's box is n_tile/csize rows)
+  // and multicasts it into every CTA of the cluster, so the weight traffic across the L2->SM fabric — more
+  // than half of the total for n_tile >= 128 — drops by csize.  Stage release becomes cluster-wide: every
+  // MMA issuer's tcgen05.commit arrives on the empty barrier of all csize CTAs.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -245,15 +250,22 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   float* s_shift = s_scale + 256;
   float* s_floor = s_shift + 256;
 
-  const int total_tiles = m_tiles * n_tiles;
+  // work items: (M-tile group of csize tiles, N tile); this CTA owns M tile group*csize + rank
+  const int m_groups = (m_tiles + csize - 1) / csize;
+  const int total_tiles = m_groups * n_tiles;
   const int num_kb = a.taps * a.cblocks;
+  const uint32_t crank = csize > 1 ? ptx::cluster_ctarank() : 0u;
+  const int first = static_cast<int>(blockIdx.x) / csize;
+  const int step = static_cast<int>(gridDim.x) / csize;
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+  const uint32_t slice_bytes = b_bytes / static_cast<uint32_t>(csize);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
     for (int s = 0; s < a.stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), csize);     // one tcgen05.commit from every CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
@@ -267,6 +279,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (csize > 1) ptx::cluster_sync();          // peers' barriers exist before anything is multicast at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
@@ -274,8 +287,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * kBM;
+      for (int t = first; t < total_tiles; t += step) {
+        const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
         const int n_base = (t % n_tiles) * a.n_tile;
         int bw = 0, bh = 0, bn = 0;
         if (a.im2col) {
@@ -299,7 +312,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           } else {
             ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * kBK, m0);
           }
-          ptx::tma_load_2d(sa + kABytes, &tm_b, full_bar(s), kb * kBK, n_base);
+          if (csize > 1)
+            ptx::tma_load_2d_mcast(sa + kABytes + crank * slice_bytes, &tm_b, full_bar(s), kb * kBK,
+                                   n_base + static_cast<int>(crank) * (a.n_tile / csize), cmask);
+          else
+            ptx::tma_load_2d(sa + kABytes, &tm_b, full_bar(s), kb * kBK, n_base);
           if (++cb == a.cblocks) { cb = 0; ++tap; }
         }
       }
@@ -309,7 +326,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (int t = first; t < total_tiles; t += step, ++lt) {
         const uint32_t as = lt & 1u;
         ptx::mbar_wait(tmem_empty(as), ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
@@ -324,7 +341,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint64_t db = ptx::make_smem_desc_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-          ptx::umma_commit(empty_bar(s));
+          if (csize > 1) ptx::umma_commit_mcast(empty_bar(s), cmask);
+          else ptx::umma_commit(empty_bar(s));
         }
         ptx::umma_commit(tmem_full(as));
       }
@@ -336,8 +354,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     const int row = quarter * 32 + lane;
     uint32_t lt = 0;
     int loaded_n_base = -1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      const int m0 = (t / n_tiles) * kBM;
+    for (int t = first; t < total_tiles; t += step, ++lt) {
+      const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
       const int n_base = (t % n_tiles) * a.n_tile;
       if (n_base != loaded_n_base) {             // uniform across the 128 epilogue threads
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -391,6 +409,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (csize > 1) ptx::cluster_sync();          // no CTA leaves while a peer can still write its smem / barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     __syncwarp();

@@ -252,6 +252,7 @@ struct ConvLayer {
   long long macs_per_image = 0;
   long long in_elems_per_image = 0;
   bool persistent = true;  // conv_igemm_persistent_kernel (one CTA per SM walks the tiles)
+  int csize = 1;           // thread-block cluster size sharing (multicasting) each weight tile
   bool halo = false;       // conv_halo_kernel instead of conv_igemm_kernel
   HaloArgs hargs{};
 };
@@ -421,7 +422,14 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
 
   const uint64_t kp = static_cast<uint64_t>(num_kb) * kBK;
-  L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile, fmt);
+  static const int max_cluster = getenv("ICP_CLUSTER") ? atoi(getenv("ICP_CLUSTER")) : 4;
+  int csize = 1;
+  if (persistent) {
+    if (max_cluster >= 4 && n_tile % 32 == 0) csize = 4;            // slices stay whole 8-row swizzle atoms
+    else if (max_cluster >= 2 && n_tile % 16 == 0) csize = 2;
+  }
+  L.csize = csize;
+  L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile / csize, fmt);
   const uint16_t* a_ptr = in.p + in_coff;
   if (im2col)
     L.tm_a = make_tm_im2col(a_ptr, max_n, in.h, in.w, cin, in.c, kh, kw, stride, pad_h, pad_w, fmt);
@@ -484,9 +492,23 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
   a.m_total = n * L.pix_per_image;
   const int m_tiles = (a.m_total + kBM - 1) / kBM;
   if (L.persistent) {
-    const int total = m_tiles * L.n_tiles;
-    conv_igemm_persistent_kernel<<<total < g_num_sms ? total : g_num_sms, kConvThreads, L.smem, st>>>(
-        L.tm_a, L.tm_b, a, m_tiles, L.n_tiles);
+    const int cs = L.csize;
+    const int total = ((m_tiles + cs - 1) / cs) * L.n_tiles;          // (M-tile group, N tile) work items
+    const int max_clusters = g_num_sms / cs;
+    const int clusters = total < max_clusters ? total : max_clusters;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * cs);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel, L.tm_a, L.tm_b, a, m_tiles, L.n_tiles, cs));
   } else {
     dim3 grid(m_tiles, L.n_tiles);
     conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
