@@ -33,7 +33,8 @@ struct HaloArgs {
   int row_bytes;        // 32 / 64 / 128  (ck = row_bytes / 2 channels per block)
   int T;                // 128-position sub-tiles per band
   int strip_rows;       // padded-grid rows per strip
-  int strip_bytes;      // strip_rows * wp * row_bytes rounded up to 1024
+  int strip_bytes;      // strip_rows * wp * row_bytes (wp * row_bytes is a multiple of 1024)
+  int nstrips;          // strips in the shared-memory ring (2..4)
   int bands_per_image;  // ceil(oh * wp / (128 * T))
   int n_tile;           // = cout (<= 256)
   int acc_cols;         // TMEM columns of one accumulator set: T * n_tile
@@ -59,15 +60,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
   const uint32_t strip0 = base;
-  const uint32_t wbase = base + 2u * a.strip_bytes;                       // resident weights
+  const uint32_t wbase = base + static_cast<uint32_t>(a.nstrips) * a.strip_bytes;   // resident weights
   const uint32_t bar_base = wbase + ((static_cast<uint32_t>(a.w_bytes) + 1023u) & ~1023u);
-  // barriers: strip_full[2], strip_empty[2], tmem_full[2], tmem_empty[2], w_full, then the TMEM slot
+  // barriers: strip_full[4], strip_empty[4], tmem_full[2], tmem_empty[2], w_full, then the TMEM slot
   auto strip_full = [&](int i) { return bar_base + 8u * i; };
-  auto strip_empty = [&](int i) { return bar_base + 16u + 8u * i; };
-  auto tmem_full = [&](int i) { return bar_base + 32u + 8u * i; };
-  auto tmem_empty = [&](int i) { return bar_base + 48u + 8u * i; };
-  const uint32_t w_full = bar_base + 64u;
-  const uint32_t tmem_slot = bar_base + 72u;
+  auto strip_empty = [&](int i) { return bar_base + 32u + 8u * i; };
+  auto tmem_full = [&](int i) { return bar_base + 64u + 8u * i; };
+  auto tmem_empty = [&](int i) { return bar_base + 80u + 8u * i; };
+  const uint32_t w_full = bar_base + 96u;
+  const uint32_t tmem_slot = bar_base + 104u;
   float* s_scale = reinterpret_cast<float*>(gbase + (bar_base - base) + 128);
   float* s_shift = s_scale + 256;
 
@@ -80,9 +81,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < a.nstrips; ++i) {
       ptx::mbar_init(strip_full(i), 1);
       ptx::mbar_init(strip_empty(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
       ptx::mbar_init(tmem_empty(i), 128);
     }
@@ -110,17 +113,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // ---------------- TMA producer ----------------
       ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.w_bytes));
       for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
-      const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
+      // One TMA box per padded-grid row ({ck, wp, 1, 1}): a single large box is serviced serially by the
+      // unit (ncu: 66.8 KB strip = 8.8 us), many row boxes in flight overlap their L2/HBM latency.
+      const uint32_t row_bytes_s = static_cast<uint32_t>(a.wp) * rb;
+      const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * row_bytes_s;
       uint32_t it = 0;
       for (int band = blockIdx.x; band < total_bands; band += gridDim.x) {
         const int img = band / a.bands_per_image;
         const int p0 = (band - img * a.bands_per_image) * kBM * a.T;
         const int h_first = p0 / a.wp;
         for (int c = 0; c < a.chunks; ++c, ++it) {
-          const uint32_t s = it & 1u;
-          ptx::mbar_wait(strip_empty(s), ((it >> 1) & 1u) ^ 1u);
+          const uint32_t s = it % a.nstrips;
+          ptx::mbar_wait(strip_empty(s), ((it / a.nstrips) & 1u) ^ 1u);
           ptx::mbar_expect_tx(strip_full(s), strip_tx);
-          ptx::tma_load_4d(strip0 + s * a.strip_bytes, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h, img);
+          const uint32_t dst = strip0 + s * a.strip_bytes;
+          for (int r = 0; r < a.strip_rows; ++r)
+            ptx::tma_load_4d(dst + r * row_bytes_s, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h + r, img);
         }
       }
     }
@@ -140,8 +148,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ptx::mbar_wait(tmem_empty(as), ((lb >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
         for (int c = 0; c < a.chunks; ++c, ++it) {
-          const uint32_t s = it & 1u;
-          ptx::mbar_wait(strip_full(s), (it >> 1) & 1u);
+          const uint32_t s = it % a.nstrips;
+          ptx::mbar_wait(strip_full(s), (it / a.nstrips) & 1u);
           ptx::tc_fence_after();
           const uint32_t strip = strip0 + s * a.strip_bytes;
           for (int j = 0; j < a.T; ++j) {
@@ -222,8 +230,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
-inline size_t halo_smem_bytes(int strip_bytes, int w_bytes) {
-  return 1024 + 2 * static_cast<size_t>(strip_bytes) + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 128 + 2048;
+inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes) {
+  return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 128 +
+         2048;
 }
 
 }  // namespace icp

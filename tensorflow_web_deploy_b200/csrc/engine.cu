@@ -366,20 +366,25 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256 &&
       cout <= 256) {
     const int rb = pick_row_bytes(cin), ck = rb / 2;
-    const int wp = in.w + 2 * pad_w;
+    // padded-grid width: real padding plus zero columns up to a whole number of 1024-B swizzle periods per
+    // row, so every row box starts on the pattern boundary TMA and UMMA both assume
+    const int wq = 1024 / rb;
+    const int wp = (in.w + 2 * pad_w + wq - 1) / wq * wq;
     const int chunks = (cin + ck - 1) / ck;
     int T = 4;
     while (T > 1 && 2 * T * cout > 512) T >>= 1;
     const int w_bytes = chunks * kh * kw * cout * rb;
-    int strip_rows = 0, strip_bytes = 0;
+    int strip_rows = 0, strip_bytes = 0, nstrips = 2;
     size_t smem = 0;
     for (; T >= 1; T >>= 1) {
       strip_rows = (kh - 1) + 1 + (wp - 1 + (T * kBM - 1) + (kw - 1)) / wp;
-      strip_bytes = ((strip_rows * wp * rb) + 1023) & ~1023;
-      smem = halo_smem_bytes(strip_bytes, w_bytes);
-      if (smem <= 225 * 1024 && strip_rows <= 256) break;
+      strip_bytes = strip_rows * wp * rb;
+      smem = halo_smem_bytes(strip_bytes, 2, w_bytes);
+      if (smem <= 225 * 1024 && wp <= 256) break;
     }
-    if (T >= 1 && 2 * T * cout <= 512) {
+    while (nstrips < 4 && halo_smem_bytes(strip_bytes, nstrips + 1, w_bytes) <= 225 * 1024) ++nstrips;
+    smem = halo_smem_bytes(strip_bytes, nstrips, w_bytes);
+    if (T >= 1 && 2 * T * cout <= 512 && wp <= 256) {
       std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt);
       void* d_w = pool.alloc(wp_host.size() * 2);
       CK(cudaMemcpy(d_w, wp_host.data(), wp_host.size() * 2, cudaMemcpyHostToDevice));
@@ -391,11 +396,12 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       L.halo = true;
       L.n_tiles = 1;
       L.tm_b = make_tm_2d_rows(d_w, cout, kp, cout, rb, fmt);
-      L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
+      L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, 1, rb, fmt);
       HaloArgs& h = L.hargs;
       h.n_images = 0;
       h.oh = oh; h.ow = ow; h.wp = wp; h.pad_h = pad_h; h.pad_w = pad_w; h.kh = kh; h.kw = kw;
       h.chunks = chunks; h.row_bytes = rb; h.T = T; h.strip_rows = strip_rows; h.strip_bytes = strip_bytes;
+      h.nstrips = nstrips;
       h.bands_per_image = (oh * wp + kBM * T - 1) / (kBM * T);
       h.n_tile = cout; h.acc_cols = T * cout; h.tmem_cols = pow2_cols(2 * T * cout); h.w_bytes = w_bytes;
       h.fmt = fmt; h.relu = relu ? 1 : 0;
