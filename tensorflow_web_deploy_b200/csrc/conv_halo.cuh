@@ -113,10 +113,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       // ---------------- TMA producer ----------------
       ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.w_bytes));
       for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
-      // One TMA box per padded-grid row ({ck, wp, 1, 1}): a single large box is serviced serially by the
-      // unit (ncu: 66.8 KB strip = 8.8 us), many row boxes in flight overlap their L2/HBM latency.
-      const uint32_t row_bytes_s = static_cast<uint32_t>(a.wp) * rb;
-      const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * row_bytes_s;
+      const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
       uint32_t it = 0;
       for (int band = blockIdx.x; band < total_bands; band += gridDim.x) {
         const int img = band / a.bands_per_image;
@@ -126,24 +123,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t s = it % a.nstrips;
           ptx::mbar_wait(strip_empty(s), ((it / a.nstrips) & 1u) ^ 1u);
           ptx::mbar_expect_tx(strip_full(s), strip_tx);
-          const uint32_t dst = strip0 + s * a.strip_bytes;
-          for (int r = 0; r < a.strip_rows; ++r)
-            ptx::tma_load_4d(dst + r * row_bytes_s, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h + r, img);
+          ptx::tma_load_4d(strip0 + s * a.strip_bytes, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h, img);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
+      // The issuing thread is the bottleneck for narrow layers (an M128 x N32 x K16 MMA occupies the tensor
+      // pipe for 16 cycles), so the inner loop carries no division and no 64-bit descriptor construction:
+      // descriptors differ only in their 14-bit address field (16-byte units), advanced by table lookups.
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
       const int ksteps = a.row_bytes / 32;
+      const uint64_t desc_hi = ptx::make_smem_desc_rows(0, rb);          // everything but the address
+      uint32_t* tap_off = reinterpret_cast<uint32_t*>(s_shift + 256);     // [taps] A shift of tap (r,s), 16-B units
+      for (int tap = 0; tap < taps; ++tap) {
+        const int r = tap / a.kw;
+        tap_off[tap] = (static_cast<uint32_t>(r * a.wp + (tap - r * a.kw)) * rb) >> 4;
+      }
+      const uint32_t tap_units = tap_bytes >> 4;
+      const uint32_t sub_units = (static_cast<uint32_t>(kBM) * rb) >> 4;
       ptx::mbar_wait(w_full, 0);
       uint32_t it = 0, lb = 0;
+      int img = static_cast<int>(blockIdx.x) / a.bands_per_image;
+      int bi = static_cast<int>(blockIdx.x) - img * a.bands_per_image;      // band index inside the image
+      const int img_step = static_cast<int>(gridDim.x) / a.bands_per_image;
+      const int bi_step = static_cast<int>(gridDim.x) - img_step * a.bands_per_image;
       for (int band = blockIdx.x; band < total_bands; band += gridDim.x, ++lb) {
-        const int img = band / a.bands_per_image;
-        const int p0 = (band - img * a.bands_per_image) * kBM * a.T;
+        const int p0 = bi * kBM * a.T;
         const int h_first = p0 / a.wp;
-        const uint32_t local0 = static_cast<uint32_t>(p0 - h_first * a.wp);
+        const uint32_t local_units = (static_cast<uint32_t>(p0 - h_first * a.wp) * rb) >> 4;
+        int nsub = (positions - p0 + kBM - 1) / kBM;                       // sub-tiles that hold outputs
+        if (nsub > a.T) nsub = a.T;
         const uint32_t as = lb & 1u;
         ptx::mbar_wait(tmem_empty(as), ((lb >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
@@ -151,23 +162,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t s = it % a.nstrips;
           ptx::mbar_wait(strip_full(s), (it / a.nstrips) & 1u);
           ptx::tc_fence_after();
-          const uint32_t strip = strip0 + s * a.strip_bytes;
-          for (int j = 0; j < a.T; ++j) {
-            if (p0 + j * kBM >= positions) break;              // sub-tile past the image's last output row
+          const uint32_t a_units0 = ((strip0 + s * a.strip_bytes) >> 4) + local_units;
+          const uint32_t b_units0 = (wbase >> 4) + static_cast<uint32_t>(c * taps) * tap_units;
+          for (int j = 0; j < nsub; ++j) {
             const uint32_t tacc = tmem_base + as * a.acc_cols + j * a.n_tile;
-            for (int tap = 0; tap < taps; ++tap) {
-              const int r = tap / a.kw;
-              const uint32_t shift = static_cast<uint32_t>(r * a.wp + (tap - r * a.kw));
-              const uint32_t a_addr = strip + (local0 + j * kBM + shift) * rb;
-              const uint32_t b_addr = wbase + (c * taps + tap) * tap_bytes;
+            const uint32_t a_units = a_units0 + j * sub_units;
+            uint32_t b_units = b_units0;
+            for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
+              const uint32_t au = a_units + tap_off[tap];
               for (int k = 0; k < ksteps; ++k)
-                ptx::umma_f16(tacc, ptx::make_smem_desc_rows(a_addr + 32u * k, rb),
-                              ptx::make_smem_desc_rows(b_addr + 32u * k, rb), idesc, (c | tap | k) != 0);
+                ptx::umma_f16(tacc, desc_hi | (au + 2u * k), desc_hi | (b_units + 2u * k), idesc,
+                              static_cast<uint32_t>(c | tap | k));
             }
           }
           ptx::umma_commit(strip_empty(s));
         }
         ptx::umma_commit(tmem_full(as));
+        bi += bi_step;
+        img += img_step;
+        if (bi >= a.bands_per_image) { bi -= a.bands_per_image; ++img; }
       }
     }
   } else {
@@ -232,7 +245,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
 inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes) {
   return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 128 +
-         2048;
+         2048 + 256;   // + per-tap offset table
 }
 
 }  // namespace icp

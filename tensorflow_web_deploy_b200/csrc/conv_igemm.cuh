@@ -28,7 +28,7 @@ constexpr int kBM = 128;                    // output pixels per CTA tile (UMMA 
 constexpr int kBK = 64;                     // K elements per pipeline stage (one 128-B swizzle row)
 constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kConvThreads = 192;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 
 struct ConvArgs {
   int m_total;     // valid output pixels (n * oh * ow)
@@ -37,7 +37,9 @@ struct ConvArgs {
   int pad_h, pad_w;
   int kw;          // filter width (S)
   int taps;        // R * S
-  int cblocks;     // ceil(cin / 64)
+  int cblocks;     // ceil(cin / ck), ck = row_bytes / 2 channels per K block
+  int row_bytes;   // bytes per operand row in smem: 32 / 64 / 128 (SWIZZLE_32B/64B/128B), chosen per layer so that
+                   // Cin = 48 / 80 / 96 / 160 pad to (almost) nothing instead of to a multiple of 64
   int n_tile;      // output channels per CTA, multiple of 16, <= 256
   int tmem_cols;   // power of two >= max(32, n_tile)
   int stages;
@@ -78,8 +80,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
+  const int ck = a.row_bytes / 2;
+  const uint32_t a_bytes = static_cast<uint32_t>(kBM) * rb;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;
+  const uint32_t stage_tx = a_bytes + b_bytes;                       // bytes TMA delivers per stage
+  const uint32_t stage_bytes = (stage_tx + 1023u) & ~1023u;          // stage pitch keeps every tile on a swizzle period
   const uint32_t bar_base = base + a.stages * stage_bytes;
   const uint32_t tmem_full_bar = bar_base + 16u * a.stages;
   const uint32_t tmem_slot = tmem_full_bar + 8u;
@@ -128,16 +134,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int s = kb % a.stages;
         const uint32_t ph = (kb / a.stages) & 1;
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        ptx::mbar_expect_tx(full_bar(s), stage_bytes);
+        ptx::mbar_expect_tx(full_bar(s), stage_tx);
         const uint32_t sa = base + s * stage_bytes;
         if (a.im2col) {
           const int r = tap / a.kw;
-          ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * kBK, bw, bh, bn, static_cast<uint16_t>(tap - r * a.kw),
+          ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(tap - r * a.kw),
                                   static_cast<uint16_t>(r));
         } else {
-          ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * kBK, m0);
+          ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
         }
-        ptx::tma_load_2d(sa + kABytes, &tm_b, full_bar(s), kb * kBK, n_base);
+        ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
         if (++cb == a.cblocks) { cb = 0; ++tap; }
       }
     }
@@ -145,17 +151,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+      const int ksteps = a.row_bytes / 32;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % a.stages;
         const uint32_t ph = (kb / a.stages) & 1;
         ptx::mbar_wait(full_bar(s), ph);
         ptx::tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
-        const uint64_t da = ptx::make_smem_desc_sw128(sa);
-        const uint64_t db = ptx::make_smem_desc_sw128(sa + kABytes);
-#pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // +32 B per K=16 slice inside the 128-B swizzle row: +2 in the (addr>>4) field
+        const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
+        const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
+        for (int k = 0; k < ksteps; ++k) {
+          // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
           ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
         }
         ptx::umma_commit(empty_bar(s));      // smem slot free once these MMAs retire
@@ -237,8 +243,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
+  const int ck = a.row_bytes / 2;
+  const uint32_t a_bytes = static_cast<uint32_t>(kBM) * rb;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;
+  const uint32_t stage_tx = a_bytes + b_bytes;                       // bytes TMA delivers per stage
+  const uint32_t stage_bytes = (stage_tx + 1023u) & ~1023u;          // stage pitch keeps every tile on a swizzle period
   const uint32_t bar_base = base + a.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
@@ -303,20 +313,20 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const int s = it % a.stages;
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-          ptx::mbar_expect_tx(full_bar(s), stage_bytes);
+          ptx::mbar_expect_tx(full_bar(s), stage_tx);
           const uint32_t sa = base + s * stage_bytes;
           if (a.im2col) {
             const int r = tap / a.kw;
-            ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * kBK, bw, bh, bn,
+            ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
                                     static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
           } else {
-            ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * kBK, m0);
+            ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
           }
           if (csize > 1)
-            ptx::tma_load_2d_mcast(sa + kABytes + crank * slice_bytes, &tm_b, full_bar(s), kb * kBK,
+            ptx::tma_load_2d_mcast(sa + a_bytes + crank * slice_bytes, &tm_b, full_bar(s), kb * ck,
                                    n_base + static_cast<int>(crank) * (a.n_tile / csize), cmask);
           else
-            ptx::tma_load_2d(sa + kABytes, &tm_b, full_bar(s), kb * kBK, n_base);
+            ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
           if (++cb == a.cblocks) { cb = 0; ++tap; }
         }
       }
@@ -325,6 +335,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+      const int ksteps = a.row_bytes / 32;
       uint32_t it = 0, lt = 0;
       for (int t = first; t < total_tiles; t += step, ++lt) {
         const uint32_t as = lt & 1u;
@@ -337,10 +348,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           ptx::mbar_wait(full_bar(s), ph);
           ptx::tc_fence_after();
           const uint32_t sa = base + s * stage_bytes;
-          const uint64_t da = ptx::make_smem_desc_sw128(sa);
-          const uint64_t db = ptx::make_smem_desc_sw128(sa + kABytes);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
+          const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
+          for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
           if (csize > 1) ptx::umma_commit_mcast(empty_bar(s), cmask);
           else ptx::umma_commit(empty_bar(s));
         }
@@ -417,8 +427,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   }
 }
 
-inline size_t conv_smem_bytes(int stages, int n_tile) {
-  return 1024 + static_cast<size_t>(stages) * (kABytes + n_tile * 128) + 256 + 3072;
+inline size_t conv_stage_bytes(int n_tile, int row_bytes) {
+  return (static_cast<size_t>(kBM + n_tile) * row_bytes + 1023) & ~size_t(1023);
+}
+inline size_t conv_smem_bytes(int stages, int n_tile, int row_bytes) {
+  return 1024 + static_cast<size_t>(stages) * conv_stage_bytes(n_tile, row_bytes) + 256 + 3072;
 }
 
 }  // namespace icp

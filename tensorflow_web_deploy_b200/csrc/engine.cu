@@ -77,25 +77,25 @@ static CUtensorMapDataType tm_dtype(int fmt) {
 }
 
 // 2-D row-major [rows, cols] 16-bit matrix, box [box_rows x 64 cols], 128-B swizzle.
+static CUtensorMapSwizzle tm_swizzle(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 static CUtensorMap make_tm_2d(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
-                              int fmt) {
+                              int fmt, int row_bytes = 128) {
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(row_bytes / 2), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(&m, tm_dtype(fmt), 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, tm_swizzle(row_bytes),
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     fail(ICP_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r,
          (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, box_rows);
   return m;
-}
-
-static CUtensorMapSwizzle tm_swizzle(int row_bytes) {
-  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 // 2-D K-major weight matrix with rows of `row_bytes` per box (halo kernel's B operand).
@@ -132,7 +132,7 @@ static CUtensorMap make_tm_strip(const void* ptr, int n, int h, int w, int c, in
 
 // NHWC activation [n,h,w,c] (channel stride ld) in im2col mode: 128 base pixels x 64 channels per load.
 static CUtensorMap make_tm_im2col(const void* ptr, int n, int h, int w, int c, int ld, int kh, int kw, int stride,
-                                  int pad_h, int pad_w, int fmt) {
+                                  int pad_h, int pad_w, int fmt, int row_bytes = 128) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
@@ -140,8 +140,8 @@ static CUtensorMap make_tm_im2col(const void* ptr, int n, int h, int w, int c, i
   int upper[2] = {pad_w - (kw - 1), pad_h - (kh - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encode_im2col(&m, tm_dtype(fmt), 4, const_cast<void*>(ptr), dims, strides, lower, upper,
-                               /*channelsPerPixel=*/kBK, /*pixelsPerColumn=*/kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               /*channelsPerPixel=*/row_bytes / 2, /*pixelsPerColumn=*/kBM, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, tm_swizzle(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     fail(ICP_E_CUDA, "cuTensorMapEncodeIm2col failed (%d) n=%d h=%d w=%d c=%d ld=%d k=%dx%d s=%d pad=%d,%d", (int)r,
@@ -273,15 +273,15 @@ static bool g_conv_attr_set = false;
 
 // Packs HWIO fp32 weights into the K-major [cout][taps][cblocks*64] 16-bit matrix the B-operand TMA
 // reads, zero-filling the channel tail of every tap.
-static std::vector<uint16_t> pack_weights(const float* w, int kh, int kw, int cin, int cout, int fmt) {
-  const int cb = (cin + kBK - 1) / kBK;
-  const size_t kp = static_cast<size_t>(kh) * kw * cb * kBK;
+static std::vector<uint16_t> pack_weights(const float* w, int kh, int kw, int cin, int cout, int ck, int fmt) {
+  const int cb = (cin + ck - 1) / ck;
+  const size_t kp = static_cast<size_t>(kh) * kw * cb * ck;
   std::vector<uint16_t> out(static_cast<size_t>(cout) * kp, 0);
   for (int r = 0; r < kh; ++r)
     for (int s = 0; s < kw; ++s)
       for (int ci = 0; ci < cin; ++ci) {
         const float* src = w + ((static_cast<size_t>(r) * kw + s) * cin + ci) * cout;
-        const size_t kidx = (static_cast<size_t>(r) * kw + s) * cb * kBK + ci;
+        const size_t kidx = (static_cast<size_t>(r) * kw + s) * cb * ck + ci;
         for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(src[co], fmt);
       }
   return out;
@@ -335,11 +335,22 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.pix_per_image = oh * ow;
   L.macs_per_image = static_cast<long long>(oh) * ow * cout * kh * kw * cin;
   L.in_elems_per_image = static_cast<long long>(in.h) * in.w * cin;
-  const int cb = (cin + kBK - 1) / kBK;
+  // Operand row width: the widest of 128/64/32 bytes (64/32/16 channels per K block) that pads Cin by at most
+  // 12 % — Cin = 80 -> 5 x 16, 160 -> 5 x 32, 48 -> 3 x 16, 96 -> 3 x 32, 288 -> 5 x 64 (11 %), the rest x 64.
+  static const bool rb128_only = getenv("ICP_RB128") != nullptr;
+  int rb = 128;
+  if (!rb128_only)
+    for (int cand : {128, 64, 32}) {
+      const int k = cand / 2, padded = (cin + k - 1) / k * k;
+      rb = cand;
+      if ((padded - cin) * 100 <= 12 * cin) break;
+    }
+  const int ck = rb / 2;
+  const int cb = (cin + ck - 1) / ck;
   const int n_tile = pick_n_tile(cout);
   L.n_tiles = cout / n_tile;
   const int num_kb = kh * kw * cb;
-  const size_t stage_bytes = kABytes + static_cast<size_t>(n_tile) * 128;
+  const size_t stage_bytes = conv_stage_bytes(n_tile, rb);
   static const bool conv_v1 = getenv("ICP_CONV_V1") != nullptr;     // one tile per CTA (bring-up version)
   const size_t budget = conv_v1 ? ((n_tile <= 128) ? 100 * 1024 : 200 * 1024) : 196 * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
@@ -366,10 +377,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256 &&
       cout <= 256) {
     const int rb = pick_row_bytes(cin), ck = rb / 2;
-    // padded-grid width: real padding plus zero columns up to a whole number of 1024-B swizzle periods per
-    // row, so every row box starts on the pattern boundary TMA and UMMA both assume
-    const int wq = 1024 / rb;
-    const int wp = (in.w + 2 * pad_w + wq - 1) / wq * wq;
+    const int wp = in.w + 2 * pad_w;
     const int chunks = (cin + ck - 1) / ck;
     int T = 4;
     while (T > 1 && 2 * T * cout > 512) T >>= 1;
@@ -378,7 +386,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     size_t smem = 0;
     for (; T >= 1; T >>= 1) {
       strip_rows = (kh - 1) + 1 + (wp - 1 + (T * kBM - 1) + (kw - 1)) / wp;
-      strip_bytes = strip_rows * wp * rb;
+      strip_bytes = ((strip_rows * wp * rb) + 1023) & ~1023;
       smem = halo_smem_bytes(strip_bytes, 2, w_bytes);
       if (smem <= 225 * 1024 && wp <= 256) break;
     }
@@ -396,7 +404,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       L.halo = true;
       L.n_tiles = 1;
       L.tm_b = make_tm_2d_rows(d_w, cout, kp, cout, rb, fmt);
-      L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, 1, rb, fmt);
+      L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
       HaloArgs& h = L.hargs;
       h.n_images = 0;
       h.oh = oh; h.ow = ow; h.wp = wp; h.pad_h = pad_h; h.pad_w = pad_w; h.kh = kh; h.kw = kw;
@@ -419,7 +427,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   }
 
   // weights + BN vectors to the device
-  std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, fmt);
+  std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, ck, fmt);
   void* d_w = pool.alloc(wp.size() * 2);
   CK(cudaMemcpy(d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   float* d_scale = static_cast<float*>(pool.alloc(cout * 4));
@@ -427,20 +435,22 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
 
-  const uint64_t kp = static_cast<uint64_t>(num_kb) * kBK;
-  static const int max_cluster = getenv("ICP_CLUSTER") ? atoi(getenv("ICP_CLUSTER")) : 4;
+  const uint64_t kp = static_cast<uint64_t>(num_kb) * ck;
+  // Weight-tile multicast across a cluster is implemented and correct but measured SLOWER on B200 (lock-step
+  // coupling; L2 already de-duplicates neighbouring CTAs' identical requests): opt-in for experiments only.
+  static const int max_cluster = getenv("ICP_CLUSTER") ? atoi(getenv("ICP_CLUSTER")) : 1;
   int csize = 1;
   if (persistent) {
     if (max_cluster >= 4 && n_tile % 32 == 0) csize = 4;            // slices stay whole 8-row swizzle atoms
     else if (max_cluster >= 2 && n_tile % 16 == 0) csize = 2;
   }
   L.csize = csize;
-  L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile / csize, fmt);
+  L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile / csize, fmt, rb);
   const uint16_t* a_ptr = in.p + in_coff;
   if (im2col)
-    L.tm_a = make_tm_im2col(a_ptr, max_n, in.h, in.w, cin, in.c, kh, kw, stride, pad_h, pad_w, fmt);
+    L.tm_a = make_tm_im2col(a_ptr, max_n, in.h, in.w, cin, in.c, kh, kw, stride, pad_h, pad_w, fmt, rb);
   else
-    L.tm_a = make_tm_2d(a_ptr, static_cast<uint64_t>(max_n) * in.h * in.w, cin, in.c, kBM, fmt);
+    L.tm_a = make_tm_2d(a_ptr, static_cast<uint64_t>(max_n) * in.h * in.w, cin, in.c, kBM, fmt, rb);
 
   ConvArgs& a = L.args;
   a.m_total = 0;
@@ -452,6 +462,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.kw = kw;
   a.taps = kh * kw;
   a.cblocks = cb;
+  a.row_bytes = rb;
   a.n_tile = n_tile;
   a.tmem_cols = pow2_cols(n_tile);
   a.stages = stages;
@@ -473,7 +484,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.ldo2 = out2 ? out2->c : 0;
   a.coff2 = out2_coff;
   a.n_split = out2 ? n_split : (1 << 30);
-  L.smem = conv_smem_bytes(stages, n_tile);
+  L.smem = conv_smem_bytes(stages, n_tile, rb);
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
