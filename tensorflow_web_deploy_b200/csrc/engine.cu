@@ -337,9 +337,11 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.in_elems_per_image = static_cast<long long>(in.h) * in.w * cin;
   // Operand row width: the widest of 128/64/32 bytes (64/32/16 channels per K block) that pads Cin by at most
   // 12 % — Cin = 80 -> 5 x 16, 160 -> 5 x 32, 48 -> 3 x 16, 96 -> 3 x 32, 288 -> 5 x 64 (11 %), the rest x 64.
-  static const bool rb128_only = getenv("ICP_RB128") != nullptr;
+  // MEASURED: the TMA unit retires ~one box row per 2.7 cycles per SM whatever the row's width, so narrower
+  // rows (more rows for the same bytes) made conv4 2.5x SLOWER.  128-byte rows everywhere unless ICP_RB_AUTO.
+  static const bool rb_auto = getenv("ICP_RB_AUTO") != nullptr;
   int rb = 128;
-  if (!rb128_only)
+  if (rb_auto)
     for (int cand : {128, 64, 32}) {
       const int k = cand / 2, padded = (cin + k - 1) / k * k;
       rb = cand;
@@ -435,6 +437,23 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
 
+  // Weight tiles as contiguous pre-swizzled smem images for plain bulk copies (rb == 128 only).
+  static const bool no_w_image = getenv("ICP_NO_W_IMAGE") != nullptr;
+  const void* d_w_image = nullptr;
+  if (!no_w_image && rb == 128) {
+    const size_t kp_e = static_cast<size_t>(num_kb) * ck;
+    std::vector<uint16_t> img(wp.size());
+    for (int nt = 0; nt < L.n_tiles; ++nt)
+      for (int kb = 0; kb < num_kb; ++kb)
+        for (int r = 0; r < n_tile; ++r) {
+          const uint16_t* src = &wp[(static_cast<size_t>(nt) * n_tile + r) * kp_e + static_cast<size_t>(kb) * ck];
+          uint16_t* dst = &img[((static_cast<size_t>(nt) * num_kb + kb) * n_tile + r) * 64];
+          for (int c = 0; c < 8; ++c) memcpy(dst + ((c ^ (r & 7)) * 8), src + c * 8, 16);   // 16-B chunk c -> c ^ (row % 8)
+        }
+    void* d_img = pool.alloc(img.size() * 2);
+    CK(cudaMemcpy(d_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    d_w_image = d_img;
+  }
   const uint64_t kp = static_cast<uint64_t>(num_kb) * ck;
   // Weight-tile multicast across a cluster is implemented and correct but measured SLOWER on B200 (lock-step
   // coupling; L2 already de-duplicates neighbouring CTAs' identical requests): opt-in for experiments only.
@@ -474,6 +493,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.coff = out_coff;
   a.scale = d_scale;
   a.shift = d_shift;
+  a.w_image = d_w_image;
   a.floor = nullptr;
   if (floor) {
     float* d_floor = static_cast<float*>(pool.alloc(cout * 4));
