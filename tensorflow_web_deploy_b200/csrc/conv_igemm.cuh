@@ -59,10 +59,6 @@ struct ConvArgs {
   int coff2;
   int n_split;         // multiple of 16; >= cout when there is no second destination
   const float* floor;
-  // When non-null the weight tiles are fetched with plain bulk copies from this buffer, which holds every
-  // (N tile, K block) tile as a contiguous, already 128-B-swizzled shared-memory image
-  // ([n_tiles][num_kb][n_tile rows x 128 B]) instead of through the tensor map.
-  const void* w_image;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
@@ -147,11 +143,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         } else {
           ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
         }
-        if (a.w_image)
-          ptx::bulk_load(sa + a_bytes, static_cast<const uint8_t*>(a.w_image) +
-                                            (static_cast<size_t>(blockIdx.y) * num_kb + kb) * b_bytes, b_bytes, full_bar(s));
-        else
-          ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
+        ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
         if (++cb == a.cblocks) { cb = 0; ++tap; }
       }
     }
@@ -333,9 +325,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           if (csize > 1)
             ptx::tma_load_2d_mcast(sa + a_bytes + crank * slice_bytes, &tm_b, full_bar(s), kb * ck,
                                    n_base + static_cast<int>(crank) * (a.n_tile / csize), cmask);
-          else if (a.w_image)
-            ptx::bulk_load(sa + a_bytes, static_cast<const uint8_t*>(a.w_image) +
-                                              (static_cast<size_t>(t % n_tiles) * num_kb + kb) * b_bytes, b_bytes, full_bar(s));
           else
             ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
           if (++cb == a.cblocks) { cb = 0; ++tap; }
@@ -361,7 +350,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t sa = base + s * stage_bytes;
           const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
           const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
-          for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          } else {
+            for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          }
           if (csize > 1) ptx::umma_commit_mcast(empty_bar(s), cmask);
           else ptx::umma_commit(empty_bar(s));
         }

@@ -437,23 +437,6 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
 
-  // Weight tiles as contiguous pre-swizzled smem images for plain bulk copies (rb == 128 only).
-  static const bool no_w_image = getenv("ICP_NO_W_IMAGE") != nullptr;
-  const void* d_w_image = nullptr;
-  if (!no_w_image && rb == 128) {
-    const size_t kp_e = static_cast<size_t>(num_kb) * ck;
-    std::vector<uint16_t> img(wp.size());
-    for (int nt = 0; nt < L.n_tiles; ++nt)
-      for (int kb = 0; kb < num_kb; ++kb)
-        for (int r = 0; r < n_tile; ++r) {
-          const uint16_t* src = &wp[(static_cast<size_t>(nt) * n_tile + r) * kp_e + static_cast<size_t>(kb) * ck];
-          uint16_t* dst = &img[((static_cast<size_t>(nt) * num_kb + kb) * n_tile + r) * 64];
-          for (int c = 0; c < 8; ++c) memcpy(dst + ((c ^ (r & 7)) * 8), src + c * 8, 16);   // 16-B chunk c -> c ^ (row % 8)
-        }
-    void* d_img = pool.alloc(img.size() * 2);
-    CK(cudaMemcpy(d_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
-    d_w_image = d_img;
-  }
   const uint64_t kp = static_cast<uint64_t>(num_kb) * ck;
   // Weight-tile multicast across a cluster is implemented and correct but measured SLOWER on B200 (lock-step
   // coupling; L2 already de-duplicates neighbouring CTAs' identical requests): opt-in for experiments only.
@@ -493,7 +476,6 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.coff = out_coff;
   a.scale = d_scale;
   a.shift = d_shift;
-  a.w_image = d_w_image;
   a.floor = nullptr;
   if (floor) {
     float* d_floor = static_cast<float*>(pool.alloc(cout * 4));
@@ -533,6 +515,11 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     const int total = ((m_tiles + cs - 1) / cs) * L.n_tiles;          // (M-tile group, N tile) work items
     const int max_clusters = g_num_sms / cs;
     const int clusters = total < max_clusters ? total : max_clusters;
+    if (cs == 1) {
+      conv_igemm_persistent_kernel<<<clusters, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a, m_tiles, L.n_tiles, 1);
+      CK(cudaGetLastError());
+      return;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cs);
     cfg.blockDim = dim3(kConvThreads);
