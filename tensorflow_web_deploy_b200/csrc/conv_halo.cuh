@@ -1,27 +1,36 @@
-// Halo-resident, weight-resident, persistent implicit-GEMM convolution (stride 1, kh x kw > 1x1).
+// Halo-resident persistent implicit-GEMM convolution (stride 1, kh x kw > 1x1) for sm_100a.
 //
-// conv_igemm_* fetches every filter tap's A tile and every tile's weights from L2 again, so the stem and
-// the 35x35 convs are pinned at the L2->SM fabric (ncu: conv1 moves 3.98 GB across it for 182 MB of input,
-// profiles/r01_ncu_conv_igemm_v1_*.csv).  Here both operands are fetched once:
+// Measured on B200 (profiles/): an SM pulls at most ~47 B/cycle (~13 TB/s chip-wide) through TMA from L2,
+// and the tap-wise im2col kernel moves each input pixel kh*kw times and each weight tile once per 128-pixel
+// tile across that path — it, not the tensor pipe, bounds every k>1 layer.  This kernel moves far fewer bytes:
 //
-//  * Outputs are indexed on the *padded grid*: position p = oh * wp + wc with wp = iw + 2*pad_w columns, so the
+//  * Outputs are indexed on a *padded grid*: position p = row * wp + col with wp = iw + 2*pad_w columns, so the
 //    input pixel feeding output p through tap (r,s) is padded-grid position p + r*wp + s — a constant shift.
-//    Columns wc >= ow are computed and discarded (1..11 % extra MMA work on the maps this kernel serves).
-//  * A "band" = T consecutive 128-position sub-tiles of one image.  For each block of ck = row_bytes/2 input
-//    channels ONE 4-D tiled TMA box {ck, wp, rows, 1} at (w = -pad_w, h = first_row - pad_h) lands the band's
-//    whole halo strip in shared memory in padded-grid order; out-of-bounds zero fill IS the SAME padding.
-//    row_bytes in {32, 64, 128} (SWIZZLE_32B/64B/128B) is chosen per layer so Cin = 32/48/96 waste no MMA work.
-//  * The whole packed weight matrix ([chunk][tap][n_tile x ck]) is loaded into shared memory once per SM and
-//    stays there while the persistent CTA walks its bands.
+//    Columns col >= ow are computed and discarded.
+//  * A "band" = T consecutive 128-position sub-tiles.  For each block of ck = row_bytes/2 input channels ONE
+//    4-D tiled TMA box {ck, wp, rows, 1} at (w = -pad_w, h = first_row - pad_h) lands the band's whole halo
+//    strip in shared memory in padded-grid order; the unit's out-of-bounds zero fill IS the SAME padding.
+//    Every input pixel crosses the fabric ~(1 + halo/T) times instead of kh*kw times.
 //  * The MMA issuer selects tap (r,s) of sub-tile j by moving the A descriptor's start address to
 //    (j*128 + r*wp + s) * row_bytes inside the strip: the UMMA swizzle is a function of the absolute smem
 //    address, exactly like the TMA write that produced the strip, so a shifted start reads the shifted pixels.
-//  * T accumulators per band, double-buffered in TMEM (2*T*n_tile <= 512 columns): the epilogue of band i
-//    overlaps the strip load and MMAs of band i+1.
+//  * Weights: either the whole packed matrix stays resident in shared memory for the life of the persistent CTA
+//    (small layers), or [n_tile x ck] tiles per (channel block, tap) stream through a ring fed by a dedicated
+//    producer warp; either way one weight tile serves all T sub-tiles of the band.
+//  * T accumulators per band in TMEM, double-buffered when 2*T*n_tile <= 512 columns so the epilogue of one band
+//    overlaps the MMAs of the next.
+//  * "tall" mode (kh == 1): rows of ALL images form one padded grid (no vertical taps, so no vertical padding is
+//    needed between images) — bands run across image boundaries and 17x17 / 8x8 maps keep full 128-row tiles.
+//    k x 1 filters run as 1 x k on transposed storage: `transpose_out` makes the epilogue store pixel (y,x) at
+//    (x,y), so a 1x7 -> 7x1 chain alternates layouts for free.
+//
+// Warp roles: 0 = strip producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue, 6 = weight producer.
 #pragma once
 #include "conv_igemm.cuh"
 
 namespace icp {
+
+constexpr int kHaloThreads = 224;
 
 struct HaloArgs {
   int n_images;
@@ -30,16 +39,21 @@ struct HaloArgs {
   int pad_h, pad_w;
   int kh, kw;
   int chunks;           // ceil(cin / ck)
-  int row_bytes;        // 32 / 64 / 128  (ck = row_bytes / 2 channels per block)
+  int row_bytes;        // 64 / 128  (ck = row_bytes / 2 channels per block)
   int T;                // 128-position sub-tiles per band
   int strip_rows;       // padded-grid rows per strip
-  int strip_bytes;      // strip_rows * wp * row_bytes (wp * row_bytes is a multiple of 1024)
+  int strip_bytes;      // strip_rows * wp * row_bytes rounded up to 1024
   int nstrips;          // strips in the shared-memory ring (2..4)
-  int bands_per_image;  // ceil(oh * wp / (128 * T))
-  int n_tile;           // = cout (<= 256)
+  int bands_per_image;  // ceil(oh * wp / (128 * T));  tall mode: unused
+  int tall;             // 1: one grid over all images' rows (kh == 1)
+  int transpose_out;    // 1: store output pixel (y, x) at (x, y)   (square maps)
+  int n_tile, n_tiles;  // output channels per work item, number of N tiles
   int acc_cols;         // TMEM columns of one accumulator set: T * n_tile
-  int tmem_cols;        // power of two >= 2 * acc_cols
-  int w_bytes;          // chunks * taps * n_tile * row_bytes (resident weights)
+  int acc_sets;         // 2 when 2 * acc_cols <= 512, else 1
+  int tmem_cols;        // power of two >= acc_sets * acc_cols
+  int w_resident;       // 1: all weights live in smem (n_tiles == 1)
+  int w_bytes;          // resident: chunks * taps * n_tile * row_bytes; streaming: b_stages * tile pitch
+  int b_stages;         // streaming ring depth (<= 8)
   int fmt;
   int relu;
   void* out;
@@ -48,7 +62,7 @@ struct HaloArgs {
   const float* shift;
 };
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -60,23 +74,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
   const uint32_t strip0 = base;
-  const uint32_t wbase = base + static_cast<uint32_t>(a.nstrips) * a.strip_bytes;   // resident weights
+  const uint32_t wbase = base + static_cast<uint32_t>(a.nstrips) * a.strip_bytes;   // resident weights or ring
   const uint32_t bar_base = wbase + ((static_cast<uint32_t>(a.w_bytes) + 1023u) & ~1023u);
-  // barriers: strip_full[4], strip_empty[4], tmem_full[2], tmem_empty[2], w_full, then the TMEM slot
+  // barriers: strip_full[4] strip_empty[4] tmem_full[2] tmem_empty[2] w_full b_full[8] b_empty[8]; TMEM slot
   auto strip_full = [&](int i) { return bar_base + 8u * i; };
   auto strip_empty = [&](int i) { return bar_base + 32u + 8u * i; };
   auto tmem_full = [&](int i) { return bar_base + 64u + 8u * i; };
   auto tmem_empty = [&](int i) { return bar_base + 80u + 8u * i; };
   const uint32_t w_full = bar_base + 96u;
-  const uint32_t tmem_slot = bar_base + 104u;
-  float* s_scale = reinterpret_cast<float*>(gbase + (bar_base - base) + 128);
+  auto b_full = [&](int i) { return bar_base + 104u + 8u * i; };
+  auto b_empty = [&](int i) { return bar_base + 168u + 8u * i; };
+  const uint32_t tmem_slot = bar_base + 232u;
+  float* s_scale = reinterpret_cast<float*>(gbase + (bar_base - base) + 256);
   float* s_shift = s_scale + 256;
+  uint32_t* tap_off = reinterpret_cast<uint32_t*>(s_shift + 256);    // [taps] A shift of tap (r,s), 16-B units
 
   const int taps = a.kh * a.kw;
   const int ck = a.row_bytes / 2;
-  const int total_bands = a.bands_per_image * a.n_images;
-  const int positions = a.oh * a.wp;                 // padded-grid positions holding outputs, per image
   const uint32_t tap_bytes = static_cast<uint32_t>(a.n_tile) * rb;
+  const uint32_t b_stride = (tap_bytes + 1023u) & ~1023u;
+  // padded-grid positions that hold outputs: per image, or over the whole batch in tall mode
+  const int positions = a.tall ? a.n_images * a.oh * a.wp : a.oh * a.wp;
+  const int bands_per_image = a.tall ? (positions + kBM * a.T - 1) / (kBM * a.T) : a.bands_per_image;
+  const int total_bands = a.tall ? bands_per_image : bands_per_image * a.n_images;
+  const int total_items = total_bands * a.n_tiles;          // work item = (band, N tile), N fastest
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -90,18 +111,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       ptx::mbar_init(tmem_empty(i), 128);
     }
     ptx::mbar_init(w_full, 1);
+    for (int i = 0; i < a.b_stages; ++i) {
+      ptx::mbar_init(b_full(i), 1);
+      ptx::mbar_init(b_empty(i), 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, a.tmem_cols);
     ptx::tmem_relinquish();
-  }
-  if (warp >= 2) {
-    const int et = threadIdx.x - 64;
-    for (int i = et; i < a.n_tile; i += 128) {
-      s_scale[i] = __ldg(a.scale + i);
-      s_shift[i] = __ldg(a.shift + i);
-    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -110,14 +128,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.w_bytes));
-      for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
+      // ---------------- strip producer ----------------
       const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
       uint32_t it = 0;
-      for (int band = blockIdx.x; band < total_bands; band += gridDim.x) {
-        const int img = band / a.bands_per_image;
-        const int p0 = (band - img * a.bands_per_image) * kBM * a.T;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int band = item / a.n_tiles;
+        const int img = a.tall ? 0 : band / bands_per_image;
+        const int p0 = (band - img * bands_per_image) * kBM * a.T;
         const int h_first = p0 / a.wp;
         for (int c = 0; c < a.chunks; ++c, ++it) {
           const uint32_t s = it % a.nstrips;
@@ -127,81 +144,123 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ---------------- weight producer ----------------
+      if (a.w_resident) {
+        ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes);
+        for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
+      } else {
+        uint32_t bi = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+          const int n_base = (item % a.n_tiles) * a.n_tile;
+          for (int i = 0; i < a.chunks * taps; ++i, ++bi) {
+            const uint32_t sb = bi % a.b_stages;
+            ptx::mbar_wait(b_empty(sb), ((bi / a.b_stages) & 1u) ^ 1u);
+            ptx::mbar_expect_tx(b_full(sb), tap_bytes);
+            ptx::tma_load_2d(wbase + sb * b_stride, &tm_b, b_full(sb), i * ck, n_base);
+          }
+        }
+      }
+    }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      // The issuing thread is the bottleneck for narrow layers (an M128 x N32 x K16 MMA occupies the tensor
-      // pipe for 16 cycles), so the inner loop carries no division and no 64-bit descriptor construction:
-      // descriptors differ only in their 14-bit address field (16-byte units), advanced by table lookups.
+      // The issuing thread must stay lean (an M128 x N32 x K16 MMA holds the tensor pipe for 16 cycles): no
+      // division and no 64-bit descriptor construction in the inner loops — descriptors differ only in their
+      // 14-bit address field (16-byte units), advanced with a per-tap table.
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
       const int ksteps = a.row_bytes / 32;
       const uint64_t desc_hi = ptx::make_smem_desc_rows(0, rb);          // everything but the address
-      uint32_t* tap_off = reinterpret_cast<uint32_t*>(s_shift + 256);     // [taps] A shift of tap (r,s), 16-B units
       for (int tap = 0; tap < taps; ++tap) {
         const int r = tap / a.kw;
         tap_off[tap] = (static_cast<uint32_t>(r * a.wp + (tap - r * a.kw)) * rb) >> 4;
       }
       const uint32_t tap_units = tap_bytes >> 4;
       const uint32_t sub_units = (static_cast<uint32_t>(kBM) * rb) >> 4;
-      ptx::mbar_wait(w_full, 0);
-      uint32_t it = 0, lb = 0;
-      int img = static_cast<int>(blockIdx.x) / a.bands_per_image;
-      int bi = static_cast<int>(blockIdx.x) - img * a.bands_per_image;      // band index inside the image
-      const int img_step = static_cast<int>(gridDim.x) / a.bands_per_image;
-      const int bi_step = static_cast<int>(gridDim.x) - img_step * a.bands_per_image;
-      for (int band = blockIdx.x; band < total_bands; band += gridDim.x, ++lb) {
-        const int p0 = bi * kBM * a.T;
+      if (a.w_resident) ptx::mbar_wait(w_full, 0);
+      uint32_t it = 0, lb = 0, bi = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lb) {
+        const int band = item / a.n_tiles;
+        const int img = a.tall ? 0 : band / bands_per_image;
+        const int p0 = (band - img * bands_per_image) * kBM * a.T;
         const int h_first = p0 / a.wp;
         const uint32_t local_units = (static_cast<uint32_t>(p0 - h_first * a.wp) * rb) >> 4;
         int nsub = (positions - p0 + kBM - 1) / kBM;                       // sub-tiles that hold outputs
         if (nsub > a.T) nsub = a.T;
-        const uint32_t as = lb & 1u;
-        ptx::mbar_wait(tmem_empty(as), ((lb >> 1) & 1u) ^ 1u);
+        const uint32_t as = lb % a.acc_sets;
+        ptx::mbar_wait(tmem_empty(as), ((lb / a.acc_sets) & 1u) ^ 1u);
         ptx::tc_fence_after();
+        const uint32_t tacc0 = tmem_base + as * a.acc_cols;
         for (int c = 0; c < a.chunks; ++c, ++it) {
           const uint32_t s = it % a.nstrips;
           ptx::mbar_wait(strip_full(s), (it / a.nstrips) & 1u);
           ptx::tc_fence_after();
           const uint32_t a_units0 = ((strip0 + s * a.strip_bytes) >> 4) + local_units;
-          const uint32_t b_units0 = (wbase >> 4) + static_cast<uint32_t>(c * taps) * tap_units;
-          for (int j = 0; j < nsub; ++j) {
-            const uint32_t tacc = tmem_base + as * a.acc_cols + j * a.n_tile;
-            const uint32_t a_units = a_units0 + j * sub_units;
-            uint32_t b_units = b_units0;
-            for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
-              const uint32_t au = a_units + tap_off[tap];
+          for (int tap = 0; tap < taps; ++tap) {
+            uint32_t b_units;
+            uint32_t sb = 0;
+            if (a.w_resident) {
+              b_units = (wbase >> 4) + static_cast<uint32_t>(c * taps + tap) * tap_units;
+            } else {
+              sb = bi % a.b_stages;
+              ptx::mbar_wait(b_full(sb), (bi / a.b_stages) & 1u);
+              ptx::tc_fence_after();
+              b_units = (wbase + sb * b_stride) >> 4;
+            }
+            const uint32_t au0 = a_units0 + tap_off[tap];
+            for (int j = 0; j < nsub; ++j) {
+              const uint32_t au = au0 + j * sub_units;
+              const uint32_t tacc = tacc0 + j * a.n_tile;
               for (int k = 0; k < ksteps; ++k)
                 ptx::umma_f16(tacc, desc_hi | (au + 2u * k), desc_hi | (b_units + 2u * k), idesc,
                               static_cast<uint32_t>(c | tap | k));
+            }
+            if (!a.w_resident) {
+              ptx::umma_commit(b_empty(sb));
+              ++bi;
             }
           }
           ptx::umma_commit(strip_empty(s));
         }
         ptx::umma_commit(tmem_full(as));
-        bi += bi_step;
-        img += img_step;
-        if (bi >= a.bands_per_image) { bi -= a.bands_per_image; ++img; }
       }
     }
   } else {
     // ---------------- epilogue (warps 2..5) ----------------
+    const int et = threadIdx.x - 64;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint32_t lb = 0;
-    for (int band = blockIdx.x; band < total_bands; band += gridDim.x, ++lb) {
-      const int img = band / a.bands_per_image;
-      const int p0 = (band - img * a.bands_per_image) * kBM * a.T;
-      const uint32_t as = lb & 1u;
-      ptx::mbar_wait(tmem_full(as), (lb >> 1) & 1u);
+    int loaded_n_base = -1;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lb) {
+      const int band = item / a.n_tiles;
+      const int n_base = (item - band * a.n_tiles) * a.n_tile;
+      const int img = a.tall ? 0 : band / bands_per_image;
+      const int p0 = (band - img * bands_per_image) * kBM * a.T;
+      if (n_base != loaded_n_base) {             // uniform across the 128 epilogue threads
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < a.n_tile; i += 128) {
+          s_scale[i] = __ldg(a.scale + n_base + i);
+          s_shift[i] = __ldg(a.shift + n_base + i);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        loaded_n_base = n_base;
+      }
+      const uint32_t as = lb % a.acc_sets;
+      ptx::mbar_wait(tmem_full(as), (lb / a.acc_sets) & 1u);
       ptx::tc_fence_after();
       for (int j = 0; j < a.T; ++j) {
         if (p0 + j * kBM >= positions) break;
         const int p = p0 + j * kBM + row;
-        const int oy = p / a.wp;
+        int oy = p / a.wp;                         // tall mode: row over all images
         const int ox = p - oy * a.wp;
-        const bool valid = (oy < a.oh) && (ox < a.ow);
-        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) +
-                         ((static_cast<size_t>(img) * a.oh + oy) * a.ow + ox) * a.ldo + a.coff;
+        int im = img;
+        if (a.tall) { im = oy / a.oh; oy -= im * a.oh; }
+        const bool valid = (im < a.n_images) && (oy < a.oh) && (ox < a.ow);
+        const size_t pix = a.transpose_out ? (static_cast<size_t>(im) * a.ow + ox) * a.oh + oy
+                                           : (static_cast<size_t>(im) * a.oh + oy) * a.ow + ox;
+        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + pix * a.ldo + a.coff + n_base;
         const uint32_t taddr = tmem_base + as * a.acc_cols + j * a.n_tile + (static_cast<uint32_t>(quarter * 32) << 16);
         for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
           uint32_t v[32];
@@ -244,8 +303,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 }
 
 inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes) {
-  return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 128 +
-         2048 + 256;   // + per-tap offset table
+  return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 256 +
+         2048 + 256;   // barriers, scale/shift, per-tap offset table
 }
 
 }  // namespace icp

@@ -301,15 +301,6 @@ static std::vector<uint16_t> pack_weights_halo(const float* w, int kh, int kw, i
   return out;
 }
 
-static int pick_row_bytes(int cin) {
-  int best = 128, best_pad = 1 << 30;
-  for (int rb : {128, 64, 32}) {
-    const int ck = rb / 2;
-    const int padded = (cin + ck - 1) / ck * ck;
-    if (padded < best_pad) { best_pad = padded; best = rb; }
-  }
-  return best;
-}
 static bool g_halo_attr_set = false;
 
 // in: NHWC buffer (pitch in.c) of which channels [in_coff, in_coff+cin) feed the conv.
@@ -317,7 +308,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
                            const float* w_hwio, int kh, int kw, int cout, int stride, bool same, const float* scale,
                            const float* shift, bool relu, const Act& out, int out_coff, int fmt,
                            const float* floor = nullptr, const Act* out2 = nullptr, int out2_coff = 0,
-                           int n_split = 0) {
+                           int n_split = 0, bool transpose_out = false) {
   if (same && stride != 1) fail(ICP_E_INVALID, "%s: SAME padding is only supported with stride 1", name.c_str());
   if (cout % 16) fail(ICP_E_INVALID, "%s: cout=%d is not a multiple of 16", name.c_str(), cout);
   if (cin % 8 || in.c % 8 || in_coff % 8 || out.c % 8 || out_coff % 8)
@@ -372,29 +363,49 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.persistent = persistent;
   static const bool force_im2col = getenv("ICP_FORCE_IM2COL") != nullptr;
   const bool im2col = force_im2col || !(kh == 1 && kw == 1 && stride == 1);
-  // Large stride-1 maps with a real filter footprint whose packed weights fit in shared memory: read input and
-  // weights once (conv_halo.cuh).  ICP_NO_HALO=1 falls back to the im2col kernel for A/B comparison.
+  // Stride-1 convs with a real filter footprint: halo-resident kernel (conv_halo.cuh).  Per-image bands need a
+  // map wide enough to fill 128-row tiles; 1 x k filters run in "tall" mode on any map size.
+  // ICP_NO_HALO=1 falls back to the im2col kernels for A/B comparison.
   static const bool no_halo = getenv("ICP_NO_HALO") != nullptr;
-  static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 100;   // stem only: measured slower on 35x35
-  if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && ow >= halo_min_w && in.w + 2 * pad_w <= 256 &&
-      cout <= 256) {
-    const int rb = pick_row_bytes(cin), ck = rb / 2;
+  static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 30;
+  const bool tall = (kh == 1);
+  if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && in.w + 2 * pad_w <= 256 &&
+      (tall || ow >= halo_min_w) && (!transpose_out || (tall && oh == ow))) {
+    const int rb = cin <= 32 ? 64 : 128, ck = rb / 2;
     const int wp = in.w + 2 * pad_w;
     const int chunks = (cin + ck - 1) / ck;
-    int T = 4;
-    while (T > 1 && 2 * T * cout > 512) T >>= 1;
-    const int w_bytes = chunks * kh * kw * cout * rb;
-    int strip_rows = 0, strip_bytes = 0, nstrips = 2;
-    size_t smem = 0;
-    for (; T >= 1; T >>= 1) {
+    const int taps = kh * kw;
+    // sub-tiles per band: double-buffered accumulators when they leave at least two sub-tiles, else one set
+    int T = 4, acc_sets = 2;
+    while (T > 1 && 2 * T * n_tile > 512) T >>= 1;
+    if (2 * T * n_tile > 512 || T == 1) {
+      acc_sets = 1;
+      T = 4;
+      while (T > 1 && T * n_tile > 512) T >>= 1;
+      if (2 * T * n_tile <= 512) acc_sets = 2;
+    }
+    const int tile_bytes = n_tile * rb;
+    const int tile_pitch = (tile_bytes + 1023) & ~1023;
+    const int res_bytes = chunks * taps * tile_bytes;
+    int strip_rows = 0, strip_bytes = 0, nstrips = 2, b_stages = 0, w_bytes = 0;
+    bool resident = false, ok = false;
+    for (; T >= 1 && !ok; T >>= 1) {
       strip_rows = (kh - 1) + 1 + (wp - 1 + (T * kBM - 1) + (kw - 1)) / wp;
       strip_bytes = ((strip_rows * wp * rb) + 1023) & ~1023;
-      smem = halo_smem_bytes(strip_bytes, 2, w_bytes);
-      if (smem <= 225 * 1024 && wp <= 256) break;
+      if (strip_rows > 256) continue;
+      if (L.n_tiles == 1 && halo_smem_bytes(strip_bytes, 2, res_bytes) <= 225 * 1024) {
+        resident = true; w_bytes = res_bytes; b_stages = 1; ok = true;
+      } else {
+        for (b_stages = 6; b_stages >= 3; --b_stages)
+          if (halo_smem_bytes(strip_bytes, 2, b_stages * tile_pitch) <= 225 * 1024) { ok = true; break; }
+        resident = false; w_bytes = b_stages * tile_pitch;
+      }
+      if (ok) break;
     }
-    while (nstrips < 4 && halo_smem_bytes(strip_bytes, nstrips + 1, w_bytes) <= 225 * 1024) ++nstrips;
-    smem = halo_smem_bytes(strip_bytes, nstrips, w_bytes);
-    if (T >= 1 && 2 * T * cout <= 512 && wp <= 256) {
+    if (ok) {
+      acc_sets = (2 * T * n_tile <= 512) ? 2 : 1;
+      while (nstrips < 4 && halo_smem_bytes(strip_bytes, nstrips + 1, w_bytes) <= 225 * 1024) ++nstrips;
+      const size_t smem = halo_smem_bytes(strip_bytes, nstrips, w_bytes);
       std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt);
       void* d_w = pool.alloc(wp_host.size() * 2);
       CK(cudaMemcpy(d_w, wp_host.data(), wp_host.size() * 2, cudaMemcpyHostToDevice));
@@ -402,18 +413,24 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       float* d_shift = static_cast<float*>(pool.alloc(cout * 4));
       CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
-      const uint64_t kp = static_cast<uint64_t>(chunks) * kh * kw * ck;
+      const uint64_t kp = static_cast<uint64_t>(chunks) * taps * ck;
       L.halo = true;
-      L.n_tiles = 1;
-      L.tm_b = make_tm_2d_rows(d_w, cout, kp, cout, rb, fmt);
-      L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
+      L.tm_b = make_tm_2d_rows(d_w, cout, kp, n_tile, rb, fmt);
+      if (tall)   // rows of all images form one grid: dims {C, W, N*H, 1}
+        L.tm_a = make_tm_strip(in.p + in_coff, 1, max_n * in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
+      else
+        L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
       HaloArgs& h = L.hargs;
       h.n_images = 0;
       h.oh = oh; h.ow = ow; h.wp = wp; h.pad_h = pad_h; h.pad_w = pad_w; h.kh = kh; h.kw = kw;
       h.chunks = chunks; h.row_bytes = rb; h.T = T; h.strip_rows = strip_rows; h.strip_bytes = strip_bytes;
       h.nstrips = nstrips;
       h.bands_per_image = (oh * wp + kBM * T - 1) / (kBM * T);
-      h.n_tile = cout; h.acc_cols = T * cout; h.tmem_cols = pow2_cols(2 * T * cout); h.w_bytes = w_bytes;
+      h.tall = tall ? 1 : 0;
+      h.transpose_out = transpose_out ? 1 : 0;
+      h.n_tile = n_tile; h.n_tiles = L.n_tiles;
+      h.acc_cols = T * n_tile; h.acc_sets = acc_sets; h.tmem_cols = pow2_cols(acc_sets * T * n_tile);
+      h.w_resident = resident ? 1 : 0; h.w_bytes = w_bytes; h.b_stages = b_stages;
       h.fmt = fmt; h.relu = relu ? 1 : 0;
       h.out = out.p; h.ldo = out.c; h.coff = out_coff; h.scale = d_scale; h.shift = d_shift;
       L.smem = smem;
@@ -427,6 +444,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       return L;
     }
   }
+  if (transpose_out) fail(ICP_E_INVALID, "%s: transposed output needs the halo kernel in tall mode", name.c_str());
 
   // weights + BN vectors to the device
   std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, ck, fmt);
@@ -502,8 +520,9 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
   if (L.halo) {
     HaloArgs h = L.hargs;
     h.n_images = n;
-    const int bands = h.bands_per_image * n;
-    conv_halo_kernel<<<bands < g_num_sms ? bands : g_num_sms, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, h);
+    const int bands = h.tall ? (n * h.oh * h.wp + kBM * h.T - 1) / (kBM * h.T) : h.bands_per_image * n;
+    const int items = bands * h.n_tiles;
+    conv_halo_kernel<<<items < g_num_sms ? items : g_num_sms, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, h);
     CK(cudaGetLastError());
     return;
   }
