@@ -367,8 +367,12 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   // map wide enough to fill 128-row tiles; 1 x k filters run in "tall" mode on any map size.
   // ICP_NO_HALO=1 falls back to the im2col kernels for A/B comparison.
   static const bool no_halo = getenv("ICP_NO_HALO") != nullptr;
-  static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 30;
-  const bool tall = (kh == 1);
+  // MEASURED (profiles/r01_halo_vs_im2col.md): the halo kernel wins only on the two 147/149-wide stem convs
+  // (0.29 vs 0.49 ms, 0.30 vs 0.57 ms); on 73/35-wide maps and in tall mode it is 10-60 % slower than the
+  // im2col kernels, so those stay opt-in (ICP_HALO_MIN_W=30, ICP_HALO_TALL=1) until that is understood.
+  static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 100;
+  static const bool halo_tall = getenv("ICP_HALO_TALL") != nullptr;
+  const bool tall = (kh == 1) && halo_tall;
   if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && in.w + 2 * pad_w <= 256 &&
       (tall || ow >= halo_min_w) && (!transpose_out || (tall && oh == ow))) {
     const int rb = cin <= 32 ? 64 : 128, ck = rb / 2;

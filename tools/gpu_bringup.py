@@ -257,6 +257,30 @@ def cmd_profile(args):
     return 0
 
 
+LAYERS = {
+    "conv4": (73, 73, 80, 3, 3, 192, 1, False),
+    "c17_1x7_192": (17, 17, 192, 1, 7, 192, 1, True),
+    "c17_1x1_768_704": (17, 17, 768, 1, 1, 704, 1, True),
+    "c35_3x3_96": (35, 35, 96, 3, 3, 96, 1, True),
+    "c8_3x3_448": (8, 8, 448, 3, 3, 384, 1, True),
+}
+
+
+def cmd_layer(args):
+    """One layer at batch n through the stateless entry, timed over `reps` launches (for ncu captures)."""
+    from tensorflow_web_deploy_b200 import engine
+    h, w, cin, kh, kw, cout, stride, same = LAYERS[args.name]
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((args.n, h, w, cin), dtype=np.float32)
+    wt = rng.standard_normal((kh, kw, cin, cout), dtype=np.float32) * np.float32(np.sqrt(2.0 / (kh * kw * cin)))
+    y, ms = engine.conv2d_bn_relu(x, wt, np.ones(cout, np.float32), np.zeros(cout, np.float32), stride, same, True,
+                                  args.precision, reps=args.reps)
+    oh, ow = y.shape[1:3]
+    fl = 2.0 * args.n * oh * ow * cout * kh * kw * cin
+    print("LAYER %s n=%d: %.4f ms -> %.1f TFLOP/s" % (args.name, args.n, ms, fl / (ms * 1e-3) / 1e12), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -268,8 +292,10 @@ def main():
     p.add_argument("--iters", type=int, default=10); p.add_argument("--graph", action="store_true")
     p = sub.add_parser("profile"); p.add_argument("--precision", default="bf16"); p.add_argument("--n", type=int, default=128)
     p.add_argument("--reps", type=int, default=5)
+    p = sub.add_parser("layer"); p.add_argument("--name", required=True); p.add_argument("--n", type=int, default=128)
+    p.add_argument("--precision", default="bf16"); p.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
-    rc = {"profile": cmd_profile, "conv": cmd_conv, "pools": cmd_pools, "tower": cmd_tower, "speed": cmd_speed}[args.cmd](args)
+    rc = {"layer": cmd_layer, "profile": cmd_profile, "conv": cmd_conv, "pools": cmd_pools, "tower": cmd_tower, "speed": cmd_speed}[args.cmd](args)
     sys.exit(rc)
 
 
