@@ -70,6 +70,14 @@ int icp_forward_topk(icp_engine* e, const float* x_host, int n, int k, float* pr
 int icp_forward_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host,
                    float* topk_vals_host, int32_t* topk_idx_host);
 
+/* Asynchronous two-slot variant for serving loops: icp_submit_u8 enqueues host->device copy (on a copy
+ * stream), tower and result copies for `slot` (0 or 1) and returns at once; icp_collect blocks until that slot's
+ * outputs are in the host buffers given at submit.  With both slots in use the PCIe copy of batch i+1 overlaps
+ * the tower of batch i.  x_host and the output buffers should be pinned and must stay valid until collect. */
+int icp_submit_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host,
+                  float* topk_vals_host, int32_t* topk_idx_host, int slot);
+int icp_collect(icp_engine* e, int slot);
+
 /* Per-launch profile of the tower: op i of icp_num_ops() is one kernel launch.  icp_op_info gives its
  * reference scope name, kind (ICP_OP_*), algorithmic FLOPs and algorithmic HBM bytes per image;
  * icp_profile_forward runs the tower `reps` times on the engine's resident input with a CUDA event

@@ -231,11 +231,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                              const ConvArgs a, const int m_tiles, const int n_tiles, const int csize) {
-  // csize > 1: launched as thread-block clusters of `csize` CTAs that walk `csize` consecutive M tiles of the
-  // same N tile in lock-step.  Each CTA fetches 1/csize of the weight tile (tm_b's box is n_tile/csize rows)
-  // and multicasts it into every CTA of the cluster, so the weight traffic across the L2->SM fabric — more
-  // than half of the total for n_tile >= 128 — drops by csize.  Stage release becomes cluster-wide: every
-  // MMA issuer's tcgen05.commit arrives on the empty barrier of all csize CTAs.
+  // csize == 2: launched as 2-CTA clusters = CTA pairs (cta_group::2).  The pair owns two consecutive M tiles
+  // (M = 256) of one N tile: each CTA loads its own 128 A rows and HALF of the weight tile (tm_b's box is
+  // n_tile/2 rows), the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 over both CTAs' shared memory,
+  // and the accumulator's two halves land in the two CTAs' TMEM.  Weight bytes through each SM's L2 port halve
+  // (the measured ceiling of this kernel), tile shape per SM is unchanged.  All loads complete on the leader's
+  // full barrier; stage release and accumulator-ready are tcgen05.commit multicasts to both CTAs; both CTAs'
+  // epilogue threads arrive on the leader's tmem_empty barrier.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -267,25 +269,32 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const uint32_t crank = csize > 1 ? ptx::cluster_ctarank() : 0u;
   const int first = static_cast<int>(blockIdx.x) / csize;
   const int step = static_cast<int>(gridDim.x) / csize;
-  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
-  const uint32_t slice_bytes = b_bytes / static_cast<uint32_t>(csize);
+  const bool pair = csize == 2;
+  const bool leader = crank == 0;
+  const uint32_t half_bytes = b_bytes / 2u;
+  const uint32_t pair_tx = 2u * (a_bytes + half_bytes);           // both CTAs' loads land on the leader's barrier
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
     for (int s = 0; s < a.stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), csize);     // one tcgen05.commit from every CTA of the cluster
+      ptx::mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
-      ptx::mbar_init(tmem_empty(i), 128);      // every epilogue thread arrives
+      ptx::mbar_init(tmem_empty(i), pair ? 256 : 128);   // every epilogue thread (of both CTAs) arrives
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 2 * a.tmem_cols);
-    ptx::tmem_relinquish();
+    if (pair) {
+      ptx::tmem_alloc_2sm(tmem_slot, 2 * a.tmem_cols);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, 2 * a.tmem_cols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -313,28 +322,37 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const int s = it % a.stages;
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-          ptx::mbar_expect_tx(full_bar(s), stage_tx);
           const uint32_t sa = base + s * stage_bytes;
-          if (a.im2col) {
-            const int r = tap / a.kw;
-            ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
-                                    static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
+          if (pair) {
+            if (leader) ptx::mbar_expect_tx(full_bar(s), pair_tx);
+            if (a.im2col) {
+              const int r = tap / a.kw;
+              ptx::tma_load_im2col_4d_2sm(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
+                                          static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
+            } else {
+              ptx::tma_load_2d_2sm(sa, &tm_a, full_bar(s), cb * ck, m0);
+            }
+            ptx::tma_load_2d_2sm(sa + a_bytes, &tm_b, full_bar(s), kb * ck,
+                                 n_base + static_cast<int>(crank) * (a.n_tile / 2));
           } else {
-            ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
-          }
-          if (csize > 1)
-            ptx::tma_load_2d_mcast(sa + a_bytes + crank * slice_bytes, &tm_b, full_bar(s), kb * ck,
-                                   n_base + static_cast<int>(crank) * (a.n_tile / csize), cmask);
-          else
+            ptx::mbar_expect_tx(full_bar(s), stage_tx);
+            if (a.im2col) {
+              const int r = tap / a.kw;
+              ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
+                                      static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
+            } else {
+              ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
+            }
             ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
+          }
           if (++cb == a.cblocks) { cb = 0; ++tap; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+    if (lane == 0 && (leader || !pair)) {
+      // ---------------- MMA issuer (the pair's leader issues for both CTAs) ----------------
+      const uint32_t idesc = ptx::make_idesc_f16(a.fmt, pair ? 2 * kBM : kBM, a.n_tile);
       const int ksteps = a.row_bytes / 32;
       uint32_t it = 0, lt = 0;
       for (int t = first; t < total_tiles; t += step, ++lt) {
@@ -350,16 +368,21 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t sa = base + s * stage_bytes;
           const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
           const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
-          if (ksteps == 4) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          if (pair) {
+            for (int k = 0; k < ksteps; ++k) ptx::umma_f16_2sm(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+            ptx::umma_commit_2sm(empty_bar(s), 3);       // frees stage s in both CTAs
           } else {
-            for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+            if (ksteps == 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+            } else {
+              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit(empty_bar(s));
           }
-          if (csize > 1) ptx::umma_commit_mcast(empty_bar(s), cmask);
-          else ptx::umma_commit(empty_bar(s));
         }
-        ptx::umma_commit(tmem_full(as));
+        if (pair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
+        else ptx::umma_commit(tmem_full(as));
       }
     }
   } else {
@@ -418,7 +441,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tmem_empty(as));          // 128 arrivals release the accumulator to the MMA issuer
+      if (pair) ptx::mbar_arrive_leader(tmem_empty(as));   // 2 x 128 arrivals on the leader's barrier
+      else ptx::mbar_arrive(tmem_empty(as));               // 128 arrivals release the accumulator to the MMA issuer
     }
   }
 
@@ -428,7 +452,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   if (warp == 1) {
     ptx::tc_fence_after();
     __syncwarp();
-    ptx::tmem_dealloc(tmem_base, 2 * a.tmem_cols);
+    if (pair) ptx::tmem_dealloc_2sm(tmem_base, 2 * a.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, 2 * a.tmem_cols);
   }
 }
 

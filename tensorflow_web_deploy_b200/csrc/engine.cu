@@ -460,14 +460,10 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
 
   const uint64_t kp = static_cast<uint64_t>(num_kb) * ck;
-  // Weight-tile multicast across a cluster is implemented and correct but measured SLOWER on B200 (lock-step
-  // coupling; L2 already de-duplicates neighbouring CTAs' identical requests): opt-in for experiments only.
-  static const int max_cluster = getenv("ICP_CLUSTER") ? atoi(getenv("ICP_CLUSTER")) : 1;
+  // CTA pairs (cta_group::2): two SMs share one M=256 tile and each loads half of the weight tile.
+  static const bool use_pair = !(getenv("ICP_PAIR") && atoi(getenv("ICP_PAIR")) == 0);
   int csize = 1;
-  if (persistent) {
-    if (max_cluster >= 4 && n_tile % 32 == 0) csize = 4;            // slices stay whole 8-row swizzle atoms
-    else if (max_cluster >= 2 && n_tile % 16 == 0) csize = 2;
-  }
+  if (persistent && use_pair && n_tile % 16 == 0) csize = 2;
   L.csize = csize;
   L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile / csize, fmt, rb);
   const uint16_t* a_ptr = in.p + in_coff;
@@ -612,7 +608,11 @@ struct icp_engine {
   int last_n = 0;
 
   float* d_input = nullptr;         // [max_batch, S, S, 3] f32
-  uint8_t* d_input_u8 = nullptr;    // [max_batch, S, S, 3] u8 (icp_forward_u8)
+  uint8_t* d_input_u8 = nullptr;    // [max_batch, S, S, 3] u8 (icp_forward_u8); also slot 0 of the async path
+  uint8_t* d_slot_u8[2] = {nullptr, nullptr};   // icp_submit_u8 double buffer
+  cudaStream_t copy_stream = nullptr;           // H2D of the next batch overlaps the tower of the current one
+  cudaEvent_t slot_h2d[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
   int graph_k = 5;
   uint8_t* d_rgb = nullptr;         // staging for icp_classify_rgb8
   size_t d_rgb_cap = 0;
@@ -634,6 +634,11 @@ struct icp_engine {
 
   ~icp_engine() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    for (int i = 0; i < 2; ++i) {
+      if (slot_h2d[i]) cudaEventDestroy(slot_h2d[i]);
+      if (slot_done[i]) cudaEventDestroy(slot_done[i]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -1147,6 +1152,13 @@ int icp_create(const icp_config* cfg, icp_engine** out) {
     CK(cudaEventCreate(&e->ev1));
     e->d_input = static_cast<float*>(e->pool.alloc(static_cast<size_t>(e->max_batch) * e->S * e->S * 3 * 4));
     e->d_input_u8 = static_cast<uint8_t*>(e->pool.alloc(static_cast<size_t>(e->max_batch) * e->S * e->S * 3));
+    e->d_slot_u8[0] = e->d_input_u8;
+    e->d_slot_u8[1] = static_cast<uint8_t*>(e->pool.alloc(static_cast<size_t>(e->max_batch) * e->S * e->S * 3));
+    CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&e->slot_h2d[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
+    }
     e->graph_k = e->C < 5 ? e->C : 5;
     Builder b{*e, blob, e->fmt, e->max_batch};
     b.build();
@@ -1267,6 +1279,48 @@ int icp_forward_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* pr
                          e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+int icp_submit_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host, float* topk_vals_host,
+                  int32_t* topk_idx_host, int slot) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!x_host) fail(ICP_E_INVALID, "null input");
+    if (slot < 0 || slot > 1) fail(ICP_E_INVALID, "slot must be 0 or 1");
+    if (e->slot_busy[slot]) fail(ICP_E_INVALID, "slot %d has an uncollected request", slot);
+    if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t in_bytes = static_cast<size_t>(n) * e->S * e->S * 3;
+    // the slot's input buffer is free once the tower that last read it has finished
+    CK(cudaStreamWaitEvent(e->copy_stream, e->slot_done[slot], 0));
+    CK(cudaMemcpyAsync(e->d_slot_u8[slot], x_host, in_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    CK(cudaEventRecord(e->slot_h2d[slot], e->copy_stream));
+    CK(cudaStreamWaitEvent(e->stream, e->slot_h2d[slot], 0));
+    const int kk = k > 0 ? k : 0;
+    run_tower(*e, e->d_slot_u8[slot], true, n, kk ? kk : e->graph_k, nullptr, e->stream, false);
+    if (probs_out_host)
+      CK(cudaMemcpyAsync(probs_out_host, e->d_probs, static_cast<size_t>(n) * e->C * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    if (kk && topk_vals_host)
+      CK(cudaMemcpyAsync(topk_vals_host, e->d_topk_val, static_cast<size_t>(n) * kk * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    if (kk && topk_idx_host)
+      CK(cudaMemcpyAsync(topk_idx_host, e->d_topk_idx, static_cast<size_t>(n) * kk * 4, cudaMemcpyDeviceToHost,
+                         e->stream));
+    CK(cudaEventRecord(e->slot_done[slot], e->stream));
+    e->slot_busy[slot] = true;
+  });
+}
+
+int icp_collect(icp_engine* e, int slot) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (slot < 0 || slot > 1) fail(ICP_E_INVALID, "slot must be 0 or 1");
+    if (!e->slot_busy[slot]) fail(ICP_E_INVALID, "slot %d has no request in flight", slot);
+    CK(cudaSetDevice(e->cfg.device));
+    e->slot_busy[slot] = false;
+    CK(cudaEventSynchronize(e->slot_done[slot]));
   });
 }
 

@@ -45,6 +45,8 @@ SIGNATURES = {
     "icp_forward": (C.c_int, [C.c_void_p, _f32p, C.c_int, _f32p]),
     "icp_forward_topk": (C.c_int, [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _i32p]),
     "icp_forward_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p, _f32p, _i32p]),
+    "icp_submit_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p, _f32p, _i32p, C.c_int]),
+    "icp_collect": (C.c_int, [C.c_void_p, C.c_int]),
     "icp_num_ops": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "icp_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
                               C.POINTER(C.c_double)]),
@@ -149,6 +151,30 @@ class Engine:
         _check(self._lib.icp_forward_u8(self._h, x.ctypes.data_as(_u8p), n, k, _f32(probs), _f32(vals),
                                         idx.ctypes.data_as(_i32p)), self._h)
         return probs, vals, idx
+
+    def submit_u8(self, x: np.ndarray, slot: int, k: int = 5, out=None):
+        """Asynchronous forward_u8 into `slot` (0/1).  `x` (and `out`, a (probs, vals, idx) triple of preallocated
+        arrays — pinned for real overlap) must stay alive until collect(slot), which returns the triple."""
+        if x.dtype != np.uint8 or not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("submit_u8 needs a C-contiguous uint8 array (no hidden copy: the transfer is asynchronous)")
+        s = self.image_size
+        if x.ndim != 4 or x.shape[1:] != (s, s, 3):
+            raise ValueError("expected uint8 [n,%d,%d,3], got %s" % (s, s, x.shape))
+        n = x.shape[0]
+        if out is None:
+            out = (np.empty((n, self.num_classes), np.float32), np.empty((n, k), np.float32), np.empty((n, k), np.int32))
+        probs, vals, idx = out
+        _check(self._lib.icp_submit_u8(self._h, x.ctypes.data_as(_u8p), n, k, _f32(probs), _f32(vals),
+                                       idx.ctypes.data_as(_i32p), slot), self._h)
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[slot] = (x, out)
+        return out
+
+    def collect(self, slot: int):
+        _check(self._lib.icp_collect(self._h, slot), self._h)
+        x, out = self._inflight.pop(slot)
+        return out
 
     def op_table(self):
         """[(name, kind, flops_per_image, bytes_per_image)] for every launch of one forward pass."""

@@ -213,6 +213,30 @@ def test_u8_entry_matches_float_entry(eng_mod, synth6):
     eng.close()
 
 
+def test_async_slots_match_sync_call(eng_mod, synth6):
+    """icp_submit_u8 / icp_collect (copy of batch i+1 overlapping tower i) returns exactly what the blocking call does."""
+    rng = np.random.default_rng(12)
+    batches = [rng.integers(0, 256, (4, 299, 299, 3), dtype=np.uint8) for _ in range(5)]
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=4, precision="fp16", use_cuda_graph=True)
+    want = [eng.forward_u8(b, 5) for b in batches]
+    got = []
+    eng.submit_u8(batches[0], 0)
+    for i in range(1, len(batches)):
+        eng.submit_u8(batches[i], i & 1)
+        got.append(tuple(a.copy() for a in eng.collect((i - 1) & 1)))
+    got.append(tuple(a.copy() for a in eng.collect((len(batches) - 1) & 1)))
+    for w, g in zip(want, got):
+        for a, b in zip(w, g):
+            np.testing.assert_array_equal(a, b)
+    with pytest.raises(eng_mod.EngineError):
+        eng.collect(0)                                   # nothing in flight
+    eng.submit_u8(batches[0], 1)
+    with pytest.raises(eng_mod.EngineError):
+        eng.submit_u8(batches[1], 1)                     # slot still busy
+    eng.collect(1)
+    eng.close()
+
+
 def test_full_size_batch_properties(eng_mod, synth6):
     """BASELINE size (128 images, bf16): size-independent properties instead of a 4-minute oracle run."""
     rng = np.random.default_rng(8)
