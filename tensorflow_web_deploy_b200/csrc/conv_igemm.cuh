@@ -28,6 +28,7 @@ constexpr int kBM = 128;                    // output pixels per CTA tile (UMMA 
 constexpr int kBK = 64;                     // K elements per pipeline stage (one 128-B swizzle row)
 constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kConvThreads = 192;
+constexpr int kPersistThreads = 224;        // + warp 6: second TMA producer (weight tiles)
 constexpr int kMaxStages = 12;
 
 struct ConvArgs {
@@ -228,7 +229,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 //     (tcgen05.ld -> BN/ReLU -> stores) overlaps the MMAs of tile i+1,
 //   * barrier init, TMEM allocation and descriptor prefetch are paid once per SM, not once per tile.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                              const ConvArgs a, const int m_tiles, const int n_tiles, const int csize) {
   // csize == 2: launched as 2-CTA clusters = CTA pairs (cta_group::2).  The pair owns two consecutive M tiles
@@ -272,13 +273,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const bool pair = csize == 2;
   const bool leader = crank == 0;
   const uint32_t half_bytes = b_bytes / 2u;
-  const uint32_t pair_tx = 2u * (a_bytes + half_bytes);           // both CTAs' loads land on the leader's barrier
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
     for (int s = 0; s < a.stages; ++s) {
-      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(full_bar(s), 2);          // two producer threads arrive: A (warp 0) and W (warp 6)
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -308,7 +308,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       uint32_t it = 0;
       for (int t = first; t < total_tiles; t += step) {
         const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
-        const int n_base = (t % n_tiles) * a.n_tile;
         int bw = 0, bh = 0, bn = 0;
         if (a.im2col) {
           const int q = m0 % a.ow;
@@ -324,7 +323,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = base + s * stage_bytes;
           if (pair) {
-            if (leader) ptx::mbar_expect_tx(full_bar(s), pair_tx);
+            if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * a_bytes);
             if (a.im2col) {
               const int r = tap / a.kw;
               ptx::tma_load_im2col_4d_2sm(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
@@ -332,10 +331,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             } else {
               ptx::tma_load_2d_2sm(sa, &tm_a, full_bar(s), cb * ck, m0);
             }
-            ptx::tma_load_2d_2sm(sa + a_bytes, &tm_b, full_bar(s), kb * ck,
-                                 n_base + static_cast<int>(crank) * (a.n_tile / 2));
           } else {
-            ptx::mbar_expect_tx(full_bar(s), stage_tx);
+            ptx::mbar_expect_tx(full_bar(s), a_bytes);
             if (a.im2col) {
               const int r = tap / a.kw;
               ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
@@ -343,9 +340,32 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             } else {
               ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
             }
-            ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
           }
           if (++cb == a.cblocks) { cb = 0; ++tap; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ---------------- TMA producer #2: weight tiles ----------------
+      // Issuing a TMA costs the issuing thread several hundred cycles; with one producer thread the A and W
+      // loads of a stage serialise (measured ~900 cycles per K block on every layer regardless of tile size),
+      // so the two operands get one issuing thread each.
+      uint32_t it = 0;
+      for (int t = first; t < total_tiles; t += step) {
+        const int n_base = (t % n_tiles) * a.n_tile;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sb = base + s * stage_bytes + a_bytes;
+          if (pair) {
+            if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * half_bytes);
+            ptx::tma_load_2d_2sm(sb, &tm_b, full_bar(s), kb * ck, n_base + static_cast<int>(crank) * (a.n_tile / 2));
+          } else {
+            ptx::mbar_expect_tx(full_bar(s), b_bytes);
+            ptx::tma_load_2d(sb, &tm_b, full_bar(s), kb * ck, n_base);
+          }
         }
       }
     }

@@ -534,14 +534,9 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     const int total = ((m_tiles + cs - 1) / cs) * L.n_tiles;          // (M-tile group, N tile) work items
     const int max_clusters = g_num_sms / cs;
     const int clusters = total < max_clusters ? total : max_clusters;
-    if (cs == 1) {
-      conv_igemm_persistent_kernel<<<clusters, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a, m_tiles, L.n_tiles, 1);
-      CK(cudaGetLastError());
-      return;
-    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cs);
-    cfg.blockDim = dim3(kConvThreads);
+    cfg.blockDim = dim3(kPersistThreads);
     cfg.dynamicSmemBytes = L.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -983,9 +978,14 @@ static int run_op(const Op& op, int n, int fmt, cudaStream_t st) {
     }
     case Op::AVGPOOL: {
       const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
-      avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff,
-          op.k, op.stride, op.pad, op.scale, op.shift, 1, fmt);
+      if (op.scale && op.k == 3 && op.stride == 1 && op.pad == 1)
+        avgpool3_bn_relu_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+            op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.c, op.out_coff, op.scale, op.shift,
+            fmt);
+      else
+        avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+            op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff,
+            op.k, op.stride, op.pad, op.scale, op.shift, 1, fmt);
       CK(cudaGetLastError());
       return 1;
     }

@@ -211,6 +211,56 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, in
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + coff + g * 8) = pack8(acc, fmt);
 }
 
+// 3x3 / stride 1 / SAME average pool (exclude-pad divisor) + the deferred BatchNorm + ReLU of the 1x1 projection
+// that ran before it (pool-after-projection, see engine.cu).  Fully unrolled: the nine 16-byte taps are issued
+// together (out-of-bounds taps read a clamped in-bounds address and are masked), one round trip per thread.
+__global__ void __launch_bounds__(256)
+avgpool3_bn_relu_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
+                        uint16_t* __restrict__ out, int ldo, int coff, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int fmt) {
+  const int cg = C >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(N) * H * W * cg;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % cg);
+  const long long pix = idx / cg;
+  const int ox = static_cast<int>(pix % W);
+  const int oy = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const uint16_t* base = in + (static_cast<size_t>(n) * H * W) * ldi + cin_off + g * 8;
+  uint4 v[9];
+  bool ok[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int iy = oy - 1 + r;
+    const bool oky = iy >= 0 && iy < H;
+    const int cy = min(max(iy, 0), H - 1);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ix = ox - 1 + q;
+      ok[r * 3 + q] = oky && ix >= 0 && ix < W;
+      const int cx = min(max(ix, 0), W - 1);
+      v[r * 3 + q] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(cy) * W + cx) * ldi));
+    }
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float f[8];
+    unpack8(v[t], f, fmt);
+    const float m = ok[t] ? 1.f : 0.f;
+    cnt += ok[t] ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], m, acc[j]);
+  }
+  const float inv = 1.0f / static_cast<float>(cnt);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    acc[j] = fmaxf(fmaf(acc[j] * inv, __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j)), 0.f);
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + coff + g * 8) = pack8(acc, fmt);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Head (inception_model.py:318-329 + PyClassification.py:163-164): global average pool over
 // HW -> flatten -> fc [F, C] + bias -> softmax -> top-k of the probabilities (descending, ties to
