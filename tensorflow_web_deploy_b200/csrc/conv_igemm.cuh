@@ -229,9 +229,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 //     (tcgen05.ld -> BN/ReLU -> stores) overlaps the MMAs of tile i+1,
 //   * barrier init, TMEM allocation and descriptor prefetch are paid once per SM, not once per tile.
 // ---------------------------------------------------------------------------------------------------
+template <bool kPair>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                             const ConvArgs a, const int m_tiles, const int n_tiles, const int csize) {
+                             const ConvArgs a, const int m_tiles, const int n_tiles) {
+  constexpr int csize = kPair ? 2 : 1;
   // csize == 2: launched as 2-CTA clusters = CTA pairs (cta_group::2).  The pair owns two consecutive M tiles
   // (M = 256) of one N tile: each CTA loads its own 128 A rows and HALF of the weight tile (tm_b's box is
   // n_tile/2 rows), the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 over both CTAs' shared memory,
@@ -249,9 +251,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
   const int ck = a.row_bytes / 2;
   const uint32_t a_bytes = static_cast<uint32_t>(kBM) * rb;
-  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;
-  const uint32_t stage_tx = a_bytes + b_bytes;                       // bytes TMA delivers per stage
-  const uint32_t stage_bytes = (stage_tx + 1023u) & ~1023u;          // stage pitch keeps every tile on a swizzle period
+  // weight rows held per CTA: the whole N tile, or half of it in a CTA pair
+  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile / csize) * rb;
+  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u; // stage pitch keeps every tile on a swizzle period
   const uint32_t bar_base = base + a.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
@@ -267,12 +269,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const int m_groups = (m_tiles + csize - 1) / csize;
   const int total_tiles = m_groups * n_tiles;
   const int num_kb = a.taps * a.cblocks;
-  const uint32_t crank = csize > 1 ? ptx::cluster_ctarank() : 0u;
+  uint32_t crank = 0u;
+  if constexpr (kPair) crank = ptx::cluster_ctarank();
   const int first = static_cast<int>(blockIdx.x) / csize;
   const int step = static_cast<int>(gridDim.x) / csize;
-  const bool pair = csize == 2;
+  constexpr bool pair = kPair;
   const bool leader = crank == 0;
-  const uint32_t half_bytes = b_bytes / 2u;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -288,7 +290,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    if (pair) {
+    if constexpr (kPair) {
       ptx::tmem_alloc_2sm(tmem_slot, 2 * a.tmem_cols);
       ptx::tmem_relinquish_2sm();
     } else {
@@ -298,7 +300,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (csize > 1) ptx::cluster_sync();          // peers' barriers exist before anything is multicast at them
+  if constexpr (kPair) ptx::cluster_sync();    // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
@@ -322,7 +324,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = base + s * stage_bytes;
-          if (pair) {
+          if constexpr (kPair) {
             if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * a_bytes);
             if (a.im2col) {
               const int r = tap / a.kw;
@@ -359,8 +361,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sb = base + s * stage_bytes + a_bytes;
-          if (pair) {
-            if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * half_bytes);
+          if constexpr (kPair) {
+            if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * b_bytes);
             ptx::tma_load_2d_2sm(sb, &tm_b, full_bar(s), kb * ck, n_base + static_cast<int>(crank) * (a.n_tile / 2));
           } else {
             ptx::mbar_expect_tx(full_bar(s), b_bytes);
@@ -388,7 +390,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t sa = base + s * stage_bytes;
           const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
           const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
-          if (pair) {
+          if constexpr (kPair) {
             for (int k = 0; k < ksteps; ++k) ptx::umma_f16_2sm(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
             ptx::umma_commit_2sm(empty_bar(s), 3);       // frees stage s in both CTAs
           } else {
@@ -401,7 +403,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             ptx::umma_commit(empty_bar(s));
           }
         }
-        if (pair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
+        if constexpr (kPair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
         else ptx::umma_commit(tmem_full(as));
       }
     }
@@ -461,18 +463,18 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         }
       }
       ptx::tc_fence_before();
-      if (pair) ptx::mbar_arrive_leader(tmem_empty(as));   // 2 x 128 arrivals on the leader's barrier
+      if constexpr (kPair) ptx::mbar_arrive_leader(tmem_empty(as));   // 2 x 128 arrivals on the leader's barrier
       else ptx::mbar_arrive(tmem_empty(as));               // 128 arrivals release the accumulator to the MMA issuer
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (csize > 1) ptx::cluster_sync();          // no CTA leaves while a peer can still write its smem / barriers
+  if constexpr (kPair) ptx::cluster_sync();    // no CTA leaves while its peer can still touch its smem / barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     __syncwarp();
-    if (pair) ptx::tmem_dealloc_2sm(tmem_base, 2 * a.tmem_cols);
+    if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, 2 * a.tmem_cols);
     else ptx::tmem_dealloc(tmem_base, 2 * a.tmem_cols);
   }
 }

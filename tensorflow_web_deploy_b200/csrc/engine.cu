@@ -344,6 +344,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.n_tiles = cout / n_tile;
   const int num_kb = kh * kw * cb;
   const size_t stage_bytes = conv_stage_bytes(n_tile, rb);
+  int pair_stage_n = 0;
   static const bool conv_v1 = getenv("ICP_CONV_V1") != nullptr;     // one tile per CTA (bring-up version)
   const size_t budget = conv_v1 ? ((n_tile <= 128) ? 100 * 1024 : 200 * 1024) : 196 * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
@@ -361,6 +362,17 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     if (stages < 1) stages = 1;
   }
   L.persistent = persistent;
+  // CTA pairs (cta_group::2): two SMs share one M=256 tile and each loads (and stores in smem) half of the
+  // weight tile, which also buys deeper pipelining from the same shared memory.
+  static const bool use_pair = !(getenv("ICP_PAIR") && atoi(getenv("ICP_PAIR")) == 0);
+  int csize = 1;
+  if (persistent && use_pair && n_tile % 16 == 0) {
+    csize = 2;
+    const size_t sb2 = conv_stage_bytes(n_tile / 2, rb);
+    stages = static_cast<int>(196 * 1024 / sb2);
+    if (stages > kMaxStages) stages = kMaxStages;
+    pair_stage_n = n_tile / 2;
+  }
   static const bool force_im2col = getenv("ICP_FORCE_IM2COL") != nullptr;
   const bool im2col = force_im2col || !(kh == 1 && kw == 1 && stride == 1);
   // Stride-1 convs with a real filter footprint: halo-resident kernel (conv_halo.cuh).  Per-image bands need a
@@ -460,10 +472,6 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
 
   const uint64_t kp = static_cast<uint64_t>(num_kb) * ck;
-  // CTA pairs (cta_group::2): two SMs share one M=256 tile and each loads half of the weight tile.
-  static const bool use_pair = !(getenv("ICP_PAIR") && atoi(getenv("ICP_PAIR")) == 0);
-  int csize = 1;
-  if (persistent && use_pair && n_tile % 16 == 0) csize = 2;
   L.csize = csize;
   L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile / csize, fmt, rb);
   const uint16_t* a_ptr = in.p + in_coff;
@@ -504,10 +512,11 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.ldo2 = out2 ? out2->c : 0;
   a.coff2 = out2_coff;
   a.n_split = out2 ? n_split : (1 << 30);
-  L.smem = conv_smem_bytes(stages, n_tile, rb);
+  L.smem = conv_smem_bytes(stages, pair_stage_n ? pair_stage_n : n_tile, rb);
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -534,6 +543,11 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     const int total = ((m_tiles + cs - 1) / cs) * L.n_tiles;          // (M-tile group, N tile) work items
     const int max_clusters = g_num_sms / cs;
     const int clusters = total < max_clusters ? total : max_clusters;
+    if (cs == 1) {
+      conv_igemm_persistent_kernel<false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, a, m_tiles, L.n_tiles);
+      CK(cudaGetLastError());
+      return;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cs);
     cfg.blockDim = dim3(kPersistThreads);
@@ -546,7 +560,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel, L.tm_a, L.tm_b, a, m_tiles, L.n_tiles, cs));
+    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true>, L.tm_a, L.tm_b, a, m_tiles, L.n_tiles));
   } else {
     dim3 grid(m_tiles, L.n_tiles);
     conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
