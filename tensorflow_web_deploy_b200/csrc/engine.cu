@@ -363,8 +363,10 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   }
   L.persistent = persistent;
   // CTA pairs (cta_group::2): two SMs share one M=256 tile and each loads (and stores in smem) half of the
-  // weight tile, which also buys deeper pipelining from the same shared memory.
-  static const bool use_pair = !(getenv("ICP_PAIR") && atoi(getenv("ICP_PAIR")) == 0);
+  // weight tile, which also buys a deeper ring from the same shared memory.  Implemented, parity-green, and
+  // MEASURED SLOWER than one CTA per SM on this tower (4.08 vs 3.74 ms/step; conv4 0.345 vs 0.278 ms), so it is
+  // opt-in (ICP_PAIR=1) — see profiles/r01_halo_vs_im2col.md.
+  static const bool use_pair = getenv("ICP_PAIR") && atoi(getenv("ICP_PAIR")) != 0;
   int csize = 1;
   if (persistent && use_pair && n_tile % 16 == 0) {
     csize = 2;
