@@ -47,6 +47,15 @@ def measured_peaks():
     return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def conv_traffic_per_launch(batch, precision):
+    """DRAM bytes per conv launch from the committed ncu capture (only valid for the configuration it was taken at)."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_traffic_final.json")
+    if batch != 128 or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_total"] / d["conv_launches_per_step"]
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -281,7 +290,10 @@ def main():
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                     "peak_source": peaks["source"] + " burst bf16 (MEASURED_PEAKS.json)",
                     "launches_per_step": n_conv, "avg_launch_us": 1e3 * conv_ms / n_conv,
-                    "share_of_step": conv_ms / float(per_op.sum()), "traffic": None,
+                    "share_of_step": conv_ms / float(per_op.sum()), "traffic": conv_traffic_per_launch(B, args.precision),
+                    "traffic_note": "dram__bytes_read+write per launch, mean over the 65 conv launches of one step, from "
+                                    "the committed ncu capture profiles/r01_conv_traffic_final.json (batch 128 bf16); "
+                                    "null for other configurations",
                     "whole_tower_frac": value / world * FLOP_PER_IMAGE / 1e12 / peaks["bf16_tflops"]}
         # ---------------- batch-1 latency (BASELINE configs[1]) ----------------
         lat = engine.Engine(wpath, C, device=local_rank, max_batch=1, precision=args.precision, use_cuda_graph=True)
