@@ -572,7 +572,8 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------ plan ops
 struct Op {
-  enum Kind { CONV, MAXPOOL, AVGPOOL } kind;
+  enum Kind { CONV, MAXPOOL, AVGPOOL, FORK, JOIN } kind;
+  int lane = 0;                   // independent branches of a block run on their own stream between FORK and JOIN
   ConvLayer conv;                 // CONV
   Act in, out;                    // pools
   int c = 0, in_coff = 0, out_coff = 0;   // pools: channels pooled, channel offsets in `in` / `out`
@@ -629,7 +630,8 @@ struct icp_engine {
   size_t d_rgb_cap = 0;
   Conv0Params conv0{};              // weights + folded BN of the Cin=3 stem conv, passed by value
   Act conv0_out;
-  std::vector<Op> ops;              // everything after conv0 up to the last block
+  std::vector<Op> ops;              // everything after conv0 up to the last block (incl. FORK/JOIN markers)
+  std::vector<int> launch_ops;      // indices into `ops` of the entries that launch a kernel
   Act final_act;                    // 8x8x2048
   float *d_fc_w = nullptr, *d_fc_b = nullptr;
   float *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
@@ -640,11 +642,21 @@ struct icp_engine {
   float *d_aux_w = nullptr, *d_aux_b = nullptr, *d_aux_logits = nullptr;
   std::map<std::string, Endpoint> endpoints;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  static constexpr int kLanes = 5;
+  cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] unused (= caller's stream)
+  cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t join_ev[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int lanes_max_batch = 8;          // branch concurrency pays when one layer cannot fill the GPU
   int launches = 0;
   long long conv_macs_per_image = 0;
 
   ~icp_engine() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    for (int i = 0; i < kLanes; ++i) {
+      if (lane_stream[i]) cudaStreamDestroy(lane_stream[i]);
+      if (join_ev[i]) cudaEventDestroy(join_ev[i]);
+    }
+    if (fork_ev) cudaEventDestroy(fork_ev);
     for (int i = 0; i < 2; ++i) {
       if (slot_h2d[i]) cudaEventDestroy(slot_h2d[i]);
       if (slot_done[i]) cudaEventDestroy(slot_done[i]);
@@ -664,6 +676,10 @@ struct Builder {
   const Blob& blob;
   int fmt;
   int maxn;
+  int lane = 0;        // lane of the ops being emitted
+
+  void fork(std::vector<Op>& ops) { Op op; op.kind = Op::FORK; ops.push_back(op); }
+  void join(std::vector<Op>& ops) { Op op; op.kind = Op::JOIN; ops.push_back(op); lane = 0; }
 
   Act alloc_act(int h, int w, int c) {
     Act a;
@@ -695,6 +711,7 @@ struct Builder {
     op.conv = make_conv(e.pool, scope, maxn, in, 0, in.c, w.data.data(), kh, kw, cout, stride, same, scale.data(),
                         shift.data(), true, out, coff, fmt);
     e.conv_macs_per_image += op.conv.macs_per_image;
+    op.lane = lane;
     ops.push_back(std::move(op));
   }
   Act conv_new(std::vector<Op>& ops, const std::string& scope, const Act& in, int cout, int kh, int kw, int stride = 1,
@@ -708,6 +725,7 @@ struct Builder {
     Op op;
     op.kind = Op::MAXPOOL;
     op.in = in; op.out = out; op.c = in.c; op.out_coff = coff;
+    op.lane = lane;
     ops.push_back(std::move(op));
   }
   Act avgpool_new(std::vector<Op>& ops, const Act& in, int k, int stride, bool same) {
@@ -716,6 +734,7 @@ struct Builder {
     Op op;
     op.kind = Op::AVGPOOL;
     op.in = in; op.out = out; op.c = in.c; op.k = k; op.stride = stride; op.pad = pad;
+    op.lane = lane;
     ops.push_back(std::move(op));
     return out;
   }
@@ -786,6 +805,7 @@ struct Builder {
     else
       op.conv = make_conv(e.pool, name, maxn, x, 0, cin, w.data(), 1, 1, total, 1, true, scale.data(), shift.data(),
                           true, f.temp, 0, fmt, floor.data());
+    op.lane = lane;
     ops.push_back(std::move(op));
     return f;
   }
@@ -800,6 +820,7 @@ struct Builder {
     op.conv = make_conv(e.pool, scope, maxn, in, in_coff, cin, w.data.data(), kh, kw, cout, stride, same, scale.data(),
                         shift.data(), true, out, coff, fmt);
     e.conv_macs_per_image += op.conv.macs_per_image;
+    op.lane = lane;
     ops.push_back(std::move(op));
   }
   Act conv_slice_new(std::vector<Op>& ops, const std::string& scope, const Act& in, int in_coff, int cin, int cout,
@@ -821,6 +842,7 @@ struct Builder {
     CK(cudaMemcpy(d_sc, f.pool_scale.data(), c * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_sh, f.pool_shift.data(), c * 4, cudaMemcpyHostToDevice));
     op.scale = d_sc; op.shift = d_sh;
+    op.lane = lane;
     ops.push_back(std::move(op));
   }
 
@@ -830,10 +852,15 @@ struct Builder {
     Fused f = fused_1x1(ops, s, x, {{s + "/branch1x1/Conv", 64, false}, {s + "/branch5x5/Conv", 48, false},
                                     {s + "/branch3x3dbl/Conv", 64, false}, {s + "/branch_pool/Conv", pool_c, true}},
                         true, out, 0);
+    fork(ops);
+    lane = 1;
     conv_slice(ops, s + "/branch5x5/Conv_1", f.temp, f.temp_off[1], 48, 64, 5, 5, 1, true, out, 64);
+    lane = 0;
     Act t = conv_slice_new(ops, s + "/branch3x3dbl/Conv_1", f.temp, f.temp_off[2], 64, 96, 3, 3);
     conv(ops, s + "/branch3x3dbl/Conv_2", t, 96, 3, 3, 1, true, out, 128);
+    lane = 2;
     pool_after_projection(ops, s + "/branch_pool", f, f.temp_off[3], pool_c, out, 224);
+    join(ops);
     tap(s, out);
     return out;
   }
@@ -841,11 +868,16 @@ struct Builder {
   Act block_red_a(std::vector<Op>& ops, const std::string& s, const Act& x) {
     const int oh = (x.h - 3) / 2 + 1, ow = (x.w - 3) / 2 + 1;
     Act out = alloc_act(oh, ow, 384 + 96 + x.c);
+    fork(ops);
+    lane = 1;
     conv(ops, s + "/branch3x3/Conv", x, 384, 3, 3, 2, false, out, 0);
+    lane = 0;
     Act t = conv_new(ops, s + "/branch3x3dbl/Conv", x, 64, 1, 1);
     t = conv_new(ops, s + "/branch3x3dbl/Conv_1", t, 96, 3, 3);
     conv(ops, s + "/branch3x3dbl/Conv_2", t, 96, 3, 3, 2, false, out, 384);
+    lane = 2;
     maxpool(ops, x, out, 480);
+    join(ops);
     tap(s, out);
     return out;
   }
@@ -855,13 +887,18 @@ struct Builder {
     Fused f = fused_1x1(ops, s, x, {{s + "/branch1x1/Conv", 192, false}, {s + "/branch7x7/Conv", m, false},
                                     {s + "/branch7x7dbl/Conv", m, false}, {s + "/branch_pool/Conv", 192, true}},
                         true, out, 0);
+    fork(ops);
+    lane = 1;
     Act t = conv_slice_new(ops, s + "/branch7x7/Conv_1", f.temp, f.temp_off[1], m, m, 1, 7);
     conv(ops, s + "/branch7x7/Conv_2", t, 192, 7, 1, 1, true, out, 192);
+    lane = 0;
     t = conv_slice_new(ops, s + "/branch7x7dbl/Conv_1", f.temp, f.temp_off[2], m, m, 7, 1);
     t = conv_new(ops, s + "/branch7x7dbl/Conv_2", t, m, 1, 7);
     t = conv_new(ops, s + "/branch7x7dbl/Conv_3", t, m, 7, 1);
     conv(ops, s + "/branch7x7dbl/Conv_4", t, 192, 1, 7, 1, true, out, 384);
+    lane = 2;
     pool_after_projection(ops, s + "/branch_pool", f, f.temp_off[3], 192, out, 576);
+    join(ops);
     tap(s, out);
     return out;
   }
@@ -871,11 +908,16 @@ struct Builder {
     Act out = alloc_act(oh, ow, 320 + 192 + x.c);
     Fused f = fused_1x1(ops, s, x, {{s + "/branch3x3/Conv", 192, false}, {s + "/branch7x7x3/Conv", 192, false}}, false,
                         out, 0);
+    fork(ops);
+    lane = 1;
     conv_slice(ops, s + "/branch3x3/Conv_1", f.temp, f.temp_off[0], 192, 320, 3, 3, 2, false, out, 0);
+    lane = 0;
     Act t = conv_slice_new(ops, s + "/branch7x7x3/Conv_1", f.temp, f.temp_off[1], 192, 192, 1, 7);
     t = conv_new(ops, s + "/branch7x7x3/Conv_2", t, 192, 7, 1);
     conv(ops, s + "/branch7x7x3/Conv_3", t, 192, 3, 3, 2, false, out, 320);
+    lane = 2;
     maxpool(ops, x, out, 512);
+    join(ops);
     tap(s, out);
     return out;
   }
@@ -885,12 +927,18 @@ struct Builder {
     Fused f = fused_1x1(ops, s, x, {{s + "/branch1x1/Conv", 320, false}, {s + "/branch3x3/Conv", 384, false},
                                     {s + "/branch3x3dbl/Conv", 448, false}, {s + "/branch_pool/Conv", 192, true}},
                         true, out, 0);
+    fork(ops);
+    lane = 1;
     conv_slice(ops, s + "/branch3x3/Conv_1", f.temp, f.temp_off[1], 384, 384, 1, 3, 1, true, out, 320);
+    lane = 2;
     conv_slice(ops, s + "/branch3x3/Conv_2", f.temp, f.temp_off[1], 384, 384, 3, 1, 1, true, out, 704);
+    lane = 0;
     Act t = conv_slice_new(ops, s + "/branch3x3dbl/Conv_1", f.temp, f.temp_off[2], 448, 384, 3, 3);
     conv(ops, s + "/branch3x3dbl/Conv_2", t, 384, 1, 3, 1, true, out, 1088);
     conv(ops, s + "/branch3x3dbl/Conv_3", t, 384, 3, 1, 1, true, out, 1472);
+    lane = 4;
     pool_after_projection(ops, s + "/branch_pool", f, f.temp_off[3], 192, out, 1856);
+    join(ops);
     tap(s, out);
     return out;
   }
@@ -1041,8 +1089,33 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
     ++launches;
     if (tm) tm->mark();
   }
+  // Independent branches of an inception block run on side streams between FORK and JOIN markers when one
+  // layer cannot fill the GPU (small batches); captured into the same CUDA graph as parallel branches.
+  const bool use_lanes = !tm && n <= e.lanes_max_batch;
+  bool lane_live[icp_engine::kLanes] = {false, false, false, false, false};
   for (const Op& op : e.ops) {
-    launches += run_op(op, n, fmt, st);
+    if (op.kind == Op::FORK) {
+      if (use_lanes) CK(cudaEventRecord(e.fork_ev, st));
+      continue;
+    }
+    if (op.kind == Op::JOIN) {
+      for (int i = 1; i < icp_engine::kLanes; ++i)
+        if (lane_live[i]) {
+          CK(cudaEventRecord(e.join_ev[i], e.lane_stream[i]));
+          CK(cudaStreamWaitEvent(st, e.join_ev[i], 0));
+          lane_live[i] = false;
+        }
+      continue;
+    }
+    cudaStream_t os = st;
+    if (use_lanes && op.lane > 0) {
+      os = e.lane_stream[op.lane];
+      if (!lane_live[op.lane]) {
+        CK(cudaStreamWaitEvent(os, e.fork_ev, 0));
+        lane_live[op.lane] = true;
+      }
+    }
+    launches += run_op(op, n, fmt, os);
     if (tm) tm->mark();
   }
   if (e.cfg.enable_aux && !tm) {
@@ -1171,6 +1244,12 @@ int icp_create(const icp_config* cfg, icp_engine** out) {
     e->d_slot_u8[0] = e->d_input_u8;
     e->d_slot_u8[1] = static_cast<uint8_t*>(e->pool.alloc(static_cast<size_t>(e->max_batch) * e->S * e->S * 3));
     CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 1; i < icp_engine::kLanes; ++i) {
+      CK(cudaStreamCreateWithFlags(&e->lane_stream[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&e->join_ev[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
+    if (const char* v = getenv("ICP_LANES_MAX_BATCH")) e->lanes_max_batch = atoi(v);
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&e->slot_h2d[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
@@ -1178,6 +1257,8 @@ int icp_create(const icp_config* cfg, icp_engine** out) {
     e->graph_k = e->C < 5 ? e->C : 5;
     Builder b{*e, blob, e->fmt, e->max_batch};
     b.build();
+    for (size_t i = 0; i < e->ops.size(); ++i)
+      if (e->ops[i].kind != Op::FORK && e->ops[i].kind != Op::JOIN) e->launch_ops.push_back(static_cast<int>(i));
     CK(cudaDeviceSynchronize());
   });
   if (rc == ICP_OK) *out = e.release();
@@ -1342,7 +1423,7 @@ int icp_collect(icp_engine* e, int slot) {
 
 int icp_num_ops(icp_engine* e, int* num_ops) {
   if (!e || !num_ops) return ICP_E_INVALID;
-  *num_ops = static_cast<int>(e->ops.size()) + 2;   // conv0 + plan + head
+  *num_ops = static_cast<int>(e->launch_ops.size()) + 2;   // conv0 + plan + head
   return ICP_OK;
 }
 
@@ -1350,7 +1431,7 @@ int icp_op_info(icp_engine* e, int i, char* name, int name_cap, int* kind, doubl
                 double* bytes_per_image) {
   if (!e) return ICP_E_INVALID;
   return guard(e, [&] {
-    const int nops = static_cast<int>(e->ops.size()) + 2;
+    const int nops = static_cast<int>(e->launch_ops.size()) + 2;
     if (i < 0 || i >= nops) fail(ICP_E_INVALID, "op index %d outside [0, %d)", i, nops);
     std::string nm;
     int kd = 0;
@@ -1366,7 +1447,7 @@ int icp_op_info(icp_engine* e, int i, char* name, int name_cap, int* kind, doubl
       fl = 2.0 * f.c * e->C;
       by = static_cast<double>(f.h) * f.w * f.c * 2;
     } else {
-      const Op& op = e->ops[i - 1];
+      const Op& op = e->ops[e->launch_ops[i - 1]];
       if (op.kind == Op::CONV) {
         const ConvLayer& L = op.conv;
         nm = L.name; kd = ICP_OP_CONV_IGEMM;
@@ -1395,7 +1476,7 @@ int icp_profile_forward(icp_engine* e, int n, int reps, float* ms_per_op) {
     if (!ms_per_op || reps < 1) fail(ICP_E_INVALID, "bad argument");
     if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
     CK(cudaSetDevice(e->cfg.device));
-    const int nops = static_cast<int>(e->ops.size()) + 2;
+    const int nops = static_cast<int>(e->launch_ops.size()) + 2;
     std::vector<double> acc(nops, 0.0);
     for (int r = 0; r < reps; ++r) {
       std::vector<cudaEvent_t> ev;
