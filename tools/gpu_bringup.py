@@ -263,6 +263,11 @@ LAYERS = {
     "c17_1x1_768_704": (17, 17, 768, 1, 1, 704, 1, True),
     "c35_3x3_96": (35, 35, 96, 3, 3, 96, 1, True),
     "c8_3x3_448": (8, 8, 448, 3, 3, 384, 1, True),
+    # synthetic shapes that isolate the main loop (many full waves of tiles, long K)
+    "gemm_k1024_n256": (64, 64, 1024, 1, 1, 256, 1, True),
+    "gemm_k1024_n128": (64, 64, 1024, 1, 1, 128, 1, True),
+    "gemm_k1024_n192": (64, 64, 1024, 1, 1, 192, 1, True),
+    "conv3x3_k256_n256": (64, 64, 256, 3, 3, 256, 1, True),
 }
 
 

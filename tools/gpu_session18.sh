@@ -17,5 +17,6 @@ run speed_b32_lanes 300 env ICP_LANES_MAX_BATCH=128 python tools/gpu_bringup.py 
 run speed_b32_nolanes 300 env ICP_LANES_MAX_BATCH=0 python tools/gpu_bringup.py speed --precision bf16 --n 32 --graph --iters 30
 run speed_b128_lanes 300 env ICP_LANES_MAX_BATCH=128 python tools/gpu_bringup.py speed --precision bf16 --n 128 --graph
 run speed_b128_graph 300 python tools/gpu_bringup.py speed --precision bf16 --n 128 --graph
+for L in gemm_k1024_n256 gemm_k1024_n192 gemm_k1024_n128 conv3x3_k256_n256; do run "layer_$L" 300 python tools/gpu_bringup.py layer --name $L --reps 10 --n 64; done
 run pytest_gpu 900 python -m pytest tests -x -q -m gpu
-grep -E "^===|max \|dprob|SPEED|passed|failed|icp:" gpurun_out/session18.log | cut -c1-300
+grep -E "^===|max \|dprob|SPEED|LAYER|passed|failed|icp:" gpurun_out/session18.log | cut -c1-300
