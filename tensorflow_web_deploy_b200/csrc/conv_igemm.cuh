@@ -29,6 +29,8 @@ constexpr int kBK = 64;                     // K elements per pipeline stage (on
 constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kConvThreads = 192;
 constexpr int kPersistThreads = 224;        // + warp 6: second TMA producer (weight tiles)
+constexpr int kPersistLsuThreads = 352;     // + warps 7..10: weight tiles through the LSU (cp.async) instead of TMA
+constexpr int kLsuLag = 2;                  // cp.async groups a loader thread keeps in flight
 constexpr int kMaxStages = 12;
 
 struct ConvArgs {
@@ -60,6 +62,8 @@ struct ConvArgs {
   int coff2;
   int n_split;         // multiple of 16; >= cout when there is no second destination
   const float* floor;
+  const void* w_gmem;  // packed K-major weights [cout][w_kp] (LSU weight path)
+  int w_kp;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
@@ -229,8 +233,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 //     (tcgen05.ld -> BN/ReLU -> stores) overlaps the MMAs of tile i+1,
 //   * barrier init, TMEM allocation and descriptor prefetch are paid once per SM, not once per tile.
 // ---------------------------------------------------------------------------------------------------
-template <bool kPair>
-__global__ void __launch_bounds__(kPersistThreads, 1)
+template <bool kPair, bool kLsuB>
+__global__ void __launch_bounds__(kLsuB ? kPersistLsuThreads : kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                              const ConvArgs a, const int m_tiles, const int n_tiles) {
   constexpr int csize = kPair ? 2 : 1;
@@ -280,7 +284,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
     for (int s = 0; s < a.stages; ++s) {
-      ptx::mbar_init(full_bar(s), 2);          // two producer threads arrive: A (warp 0) and W (warp 6)
+      // arrivals per stage: the A producer + either the W producer thread (TMA) or the 128 LSU loader threads
+      ptx::mbar_init(full_bar(s), kLsuB ? 129 : 2);
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -305,8 +310,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
+    {
+      // ---------------- TMA producer (warp-converged; one elected lane issues) ----------------
       uint32_t it = 0;
       for (int t = first; t < total_tiles; t += step) {
         const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
@@ -324,31 +329,34 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = base + s * stage_bytes;
-          if constexpr (kPair) {
-            if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * a_bytes);
-            if (a.im2col) {
-              const int r = tap / a.kw;
-              ptx::tma_load_im2col_4d_2sm(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
-                                          static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
+          if (ptx::elect_one()) {
+            if constexpr (kPair) {
+              if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * a_bytes);
+              if (a.im2col) {
+                const int r = tap / a.kw;
+                ptx::tma_load_im2col_4d_2sm(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
+                                            static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
+              } else {
+                ptx::tma_load_2d_2sm(sa, &tm_a, full_bar(s), cb * ck, m0);
+              }
             } else {
-              ptx::tma_load_2d_2sm(sa, &tm_a, full_bar(s), cb * ck, m0);
-            }
-          } else {
-            ptx::mbar_expect_tx(full_bar(s), a_bytes);
-            if (a.im2col) {
-              const int r = tap / a.kw;
-              ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
-                                      static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
-            } else {
-              ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
+              ptx::mbar_expect_tx(full_bar(s), a_bytes);
+              if (a.im2col) {
+                const int r = tap / a.kw;
+                ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
+                                        static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
+              } else {
+                ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
+              }
             }
           }
+          __syncwarp();
           if (++cb == a.cblocks) { cb = 0; ++tap; }
         }
       }
     }
   } else if (warp == 6) {
-    if (lane == 0) {
+    if (!kLsuB) {
       // ---------------- TMA producer #2: weight tiles ----------------
       // Issuing a TMA costs the issuing thread several hundred cycles; with one producer thread the A and W
       // loads of a stage serialise (measured ~900 cycles per K block on every layer regardless of tile size),
@@ -361,19 +369,61 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sb = base + s * stage_bytes + a_bytes;
-          if constexpr (kPair) {
-            if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * b_bytes);
-            ptx::tma_load_2d_2sm(sb, &tm_b, full_bar(s), kb * ck, n_base + static_cast<int>(crank) * (a.n_tile / 2));
-          } else {
-            ptx::mbar_expect_tx(full_bar(s), b_bytes);
-            ptx::tma_load_2d(sb, &tm_b, full_bar(s), kb * ck, n_base);
+          if (ptx::elect_one()) {
+            if constexpr (kPair) {
+              if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * b_bytes);
+              ptx::tma_load_2d_2sm(sb, &tm_b, full_bar(s), kb * ck, n_base + static_cast<int>(crank) * (a.n_tile / 2));
+            } else {
+              ptx::mbar_expect_tx(full_bar(s), b_bytes);
+              ptx::tma_load_2d(sb, &tm_b, full_bar(s), kb * ck, n_base);
+            }
           }
+          __syncwarp();
         }
       }
     }
+  } else if (warp >= 7) {
+    if constexpr (kLsuB) {
+      // ---------------- LSU weight loaders (warps 7..10) ----------------
+      // MEASURED: the TMA unit retires about one <=128-byte box row per 2.7 cycles per SM, and with both operands
+      // on it every layer sits at ~870 cycles per K block (128 A rows + n_tile W rows) while the MMAs need 2*n_tile.
+      // The weight tile therefore comes in through the other path into shared memory: 128 threads x 16-byte
+      // cp.async (8 threads per 128-byte row, swizzle applied by hand), kLsuLag groups in flight per thread, then
+      // fence.proxy.async + a plain mbarrier arrive once a group has landed.
+      const int lt = static_cast<int>(threadIdx.x) - 224;          // 0..127
+      const int chunk = lt & 7;
+      const int row0 = lt >> 3;                                    // rows row0, row0+16, ...
+      const uint32_t dst_off = static_cast<uint32_t>(row0) * 128u + (static_cast<uint32_t>(chunk ^ (row0 & 7)) << 4);
+      const uint16_t* wsrc = static_cast<const uint16_t*>(a.w_gmem);
+      const int passes = a.n_tile / 16;
+      uint32_t it = 0;
+      for (int t = first; t < total_tiles; t += step) {
+        const int n_base = (t % n_tiles) * a.n_tile;
+        const uint16_t* src_t = wsrc + static_cast<size_t>(n_base + row0) * a.w_kp + chunk * 8;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % a.stages;
+          ptx::mbar_wait(empty_bar(s), ((it / a.stages) & 1) ^ 1u);
+          const uint32_t dst = base + s * stage_bytes + a_bytes + dst_off;
+          const uint16_t* src = src_t + kb * kBK;
+          for (int i = 0; i < passes; ++i)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 2048u),
+                         "l"(src + static_cast<size_t>(i) * 16 * a.w_kp)
+                         : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (it >= kLsuLag) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kLsuLag) : "memory");
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(full_bar((it - kLsuLag) % a.stages));
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      ptx::fence_proxy_async_smem();
+      for (uint32_t j = (it > kLsuLag ? it - kLsuLag : 0u); j < it; ++j) ptx::mbar_arrive(full_bar(j % a.stages));
+    }
   } else if (warp == 1) {
-    if (lane == 0 && (leader || !pair)) {
-      // ---------------- MMA issuer (the pair's leader issues for both CTAs) ----------------
+    if (leader || !pair) {
+      // ---------------- MMA issuer: warp-converged loop, one elected lane issues (pair: leader CTA only) ----------------
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, pair ? 2 * kBM : kBM, a.n_tile);
       const int ksteps = a.row_bytes / 32;
       uint32_t it = 0, lt = 0;
@@ -390,21 +440,27 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t sa = base + s * stage_bytes;
           const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
           const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
-          if constexpr (kPair) {
-            for (int k = 0; k < ksteps; ++k) ptx::umma_f16_2sm(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-            ptx::umma_commit_2sm(empty_bar(s), 3);       // frees stage s in both CTAs
-          } else {
-            if (ksteps == 4) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          if (ptx::elect_one()) {
+            if constexpr (kPair) {
+              for (int k = 0; k < ksteps; ++k) ptx::umma_f16_2sm(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+              ptx::umma_commit_2sm(empty_bar(s), 3);       // frees stage s in both CTAs
             } else {
-              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+              if (ksteps == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+              } else {
+                for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+              }
+              ptx::umma_commit(empty_bar(s));
             }
-            ptx::umma_commit(empty_bar(s));
           }
+          __syncwarp();
         }
-        if constexpr (kPair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
-        else ptx::umma_commit(tmem_full(as));
+        if (ptx::elect_one()) {
+          if constexpr (kPair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
+          else ptx::umma_commit(tmem_full(as));
+        }
+        __syncwarp();
       }
     }
   } else {
