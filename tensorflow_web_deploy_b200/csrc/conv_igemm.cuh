@@ -64,6 +64,7 @@ struct ConvArgs {
   const float* floor;
   const void* w_gmem;  // packed K-major weights [cout][w_kp] (LSU weight path)
   int w_kp;
+  int split_n;         // experiment: issue each K step as two N/2 MMAs into disjoint accumulator columns
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
@@ -445,7 +446,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
               for (int k = 0; k < ksteps; ++k) ptx::umma_f16_2sm(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
               ptx::umma_commit_2sm(empty_bar(s), 3);       // frees stage s in both CTAs
             } else {
-              if (ksteps == 4) {
+              if (a.split_n) {
+                // two independent accumulation chains (left / right half of the N tile) interleaved
+                const uint32_t idesc_h = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile / 2);
+                const uint64_t db2 = ptx::make_smem_desc_rows(sa + a_bytes + (a.n_tile / 2) * rb, rb);
+                for (int k = 0; k < ksteps; ++k) {
+                  ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc_h, (kb | k) != 0);
+                  ptx::umma_f16(tacc + a.n_tile / 2, da + 2u * k, db2 + 2u * k, idesc_h, (kb | k) != 0);
+                }
+              } else if (ksteps == 4) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
               } else {

@@ -504,6 +504,8 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.coff = out_coff;
   a.scale = d_scale;
   a.shift = d_shift;
+  static const bool split_n = getenv("ICP_SPLIT_N") != nullptr;
+  a.split_n = (split_n && n_tile % 32 == 0) ? 1 : 0;
   a.w_gmem = d_w;
   a.w_kp = static_cast<int>(kp);
   a.floor = nullptr;
@@ -549,7 +551,8 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     const int max_clusters = g_num_sms / cs;
     const int clusters = total < max_clusters ? total : max_clusters;
     if (cs == 1) {
-      static const bool lsu_b = !(getenv("ICP_LSU_B") && atoi(getenv("ICP_LSU_B")) == 0);
+      // cp.async weight loaders: correct, measured slower than the TMA weight path (3.71 vs 3.22 ms/step) -> opt-in
+      static const bool lsu_b = getenv("ICP_LSU_B") && atoi(getenv("ICP_LSU_B")) != 0;
       if (lsu_b && a.row_bytes == 128)
         conv_igemm_persistent_kernel<false, true><<<clusters, kPersistLsuThreads, L.smem, st>>>(L.tm_a, L.tm_b, a, m_tiles, L.n_tiles);
       else
