@@ -30,6 +30,7 @@ constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kConvThreads = 192;
 constexpr int kPersistThreads = 224;        // + warp 6: second TMA producer (weight tiles)
 constexpr int kPersistLsuThreads = 352;     // + warps 7..10: weight tiles through the LSU (cp.async) instead of TMA
+constexpr uint32_t kOutStageBytes = 16384;  // epilogue staging (persistent kernel)
 constexpr int kLsuLag = 2;                  // cp.async groups a loader thread keeps in flight
 constexpr int kMaxStages = 12;
 
@@ -237,6 +238,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 template <bool kPair, bool kLsuB>
 __global__ void __launch_bounds__(kLsuB ? kPersistLsuThreads : kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                             const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                              const ConvArgs a, const int m_tiles, const int n_tiles) {
   constexpr int csize = kPair ? 2 : 1;
   // csize == 2: launched as 2-CTA clusters = CTA pairs (cta_group::2).  The pair owns two consecutive M tiles
@@ -259,14 +261,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   // weight rows held per CTA: the whole N tile, or half of it in a CTA pair
   const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile / csize) * rb;
   const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u; // stage pitch keeps every tile on a swizzle period
-  const uint32_t bar_base = base + a.stages * stage_bytes;
+  const uint32_t out_stage = base + a.stages * stage_bytes;    // 16 KiB epilogue staging: 4 x [128 rows x 32 B]
+  const uint32_t bar_base = out_stage + kOutStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
   const uint32_t acc_bar = bar_base + 16u * a.stages;          // tmem_full[2], tmem_empty[2]
   auto tmem_full = [&](int i) { return acc_bar + 8u * i; };
   auto tmem_empty = [&](int i) { return acc_bar + 16u + 8u * i; };
   const uint32_t tmem_slot = acc_bar + 32u;
-  float* s_scale = reinterpret_cast<float*>(gbase + a.stages * stage_bytes + 256);
+  float* s_scale = reinterpret_cast<float*>(gbase + a.stages * stage_bytes + kOutStageBytes + 256);
   float* s_shift = s_scale + 256;
   float* s_floor = s_shift + 256;
 
@@ -284,6 +287,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
+    ptx::prefetch_tmap(&tm_o);
+    ptx::prefetch_tmap(&tm_o2);
     for (int s = 0; s < a.stages; ++s) {
       // arrivals per stage: the A producer + either the W producer thread (TMA) or the 128 LSU loader threads
       ptx::mbar_init(full_bar(s), kLsuB ? 129 : 2);
@@ -496,41 +501,68 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-      const int m = m0 + row;
-      const bool valid = m < a.m_total;
-      uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(m) * a.ldo + a.coff + n_base;
-      uint16_t* orow2 =
-          reinterpret_cast<uint16_t*>(a.out2) + static_cast<size_t>(m) * a.ldo2 + a.coff2 + n_base - a.n_split;
-      for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
-        uint32_t v[32];
-        const bool two = c0 + 16 < a.n_tile;
-        ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        if (two) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+      // The accumulator leaves through shared memory and TMA stores: each thread owns one output pixel (TMEM
+      // lane), converts 64 columns at a time, writes them as four [128 rows x 32 B] sub-boxes, and one thread
+      // stores the sub-boxes into the destination slice(s).  (Row-per-thread 16-byte global stores, the first
+      // version, cost 8.8k + 40*n_tile cycles per tile and bounded every layer.)  Rows past the last valid pixel
+      // land in the unused tail of the buffer or are clipped by the tensor map.
+      for (int c0 = 0; c0 < a.n_tile; c0 += 64) {
+        const int nsub = (a.n_tile - c0 >= 64) ? 4 : (a.n_tile - c0) / 16;
+        uint32_t v[64];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nsub) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
         ptx::tmem_ld_wait();
+        if (c0 + 64 >= a.n_tile) {               // last TMEM read of this tile: hand the accumulator back early
+          ptx::tc_fence_before();
+          if constexpr (kPair) ptx::mbar_arrive_leader(tmem_empty(as));   // 2 x 128 arrivals on the leader's barrier
+          else ptx::mbar_arrive(tmem_empty(as));           // 128 arrivals release the accumulator to the MMA issuer
+        }
+        uint32_t pk[32];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 1 && !two) break;
-          const int cc = c0 + 16 * h;
-          uint32_t p[8];
+        for (int j = 0; j < 4; ++j) {
+          if (j < nsub) {
+            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0 + 16 * j);
+            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0 + 16 * j);
+            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + c0 + 16 * j);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x0 = fmaf(__uint_as_float(v[16 * h + 2 * j]), s_scale[cc + 2 * j], s_shift[cc + 2 * j]);
-            float x1 = fmaf(__uint_as_float(v[16 * h + 2 * j + 1]), s_scale[cc + 2 * j + 1], s_shift[cc + 2 * j + 1]);
-            x0 = fmaxf(x0, s_floor[cc + 2 * j]);
-            x1 = fmaxf(x1, s_floor[cc + 2 * j + 1]);
-            p[j] = pack2(x0, x1, a.fmt);
-          }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>((n_base + cc < a.n_split ? orow : orow2) + cc);
-            dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
-            dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+            for (int q = 0; q < 4; ++q) {
+              const float4 sc = sc4[q], sh = sh4[q], fl = fl4[q];
+              const float x0 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 0]), sc.x, sh.x), fl.x);
+              const float x1 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 1]), sc.y, sh.y), fl.y);
+              const float x2 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 2]), sc.z, sh.z), fl.z);
+              const float x3 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 3]), sc.w, sh.w), fl.w);
+              pk[8 * j + 2 * q] = pack2(x0, x1, a.fmt);
+              pk[8 * j + 2 * q + 1] = pack2(x2, x3, a.fmt);
+            }
           }
         }
+        // staging buffer is free once the previous chunk's stores have read it
+        if (et == 0) ptx::tma_store_wait_read();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nsub) {
+            const uint32_t dst = out_stage + j * 4096u + static_cast<uint32_t>(row) * 32u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[8 * j]), "r"(pk[8 * j + 1]),
+                         "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[8 * j + 4]),
+                         "r"(pk[8 * j + 5]), "r"(pk[8 * j + 6]), "r"(pk[8 * j + 7]) : "memory");
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          for (int j = 0; j < nsub; ++j) {
+            const int col = n_base + c0 + 16 * j;
+            if (col < a.n_split) ptx::tma_store_2d(&tm_o, out_stage + j * 4096u, a.coff + col, m0);
+            else ptx::tma_store_2d(&tm_o2, out_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
+          }
+          ptx::tma_store_commit();
+        }
       }
-      ptx::tc_fence_before();
-      if constexpr (kPair) ptx::mbar_arrive_leader(tmem_empty(as));   // 2 x 128 arrivals on the leader's barrier
-      else ptx::mbar_arrive(tmem_empty(as));               // 128 arrivals release the accumulator to the MMA issuer
     }
+    if (et == 0) ptx::tma_store_wait_all();      // smem must outlive the last store's read
   }
 
   ptx::tc_fence_before();
@@ -547,8 +579,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 inline size_t conv_stage_bytes(int n_tile, int row_bytes) {
   return (static_cast<size_t>(kBM + n_tile) * row_bytes + 1023) & ~size_t(1023);
 }
-inline size_t conv_smem_bytes(int stages, int n_tile, int row_bytes) {
-  return 1024 + static_cast<size_t>(stages) * conv_stage_bytes(n_tile, row_bytes) + 256 + 3072;
+inline size_t conv_smem_bytes(int stages, int n_tile, int row_bytes, bool persistent = false) {
+  return 1024 + static_cast<size_t>(stages) * conv_stage_bytes(n_tile, row_bytes) + (persistent ? kOutStageBytes : 0) + 256 +
+         3072;
 }
 
 }  // namespace icp

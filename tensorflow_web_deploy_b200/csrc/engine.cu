@@ -98,6 +98,21 @@ static CUtensorMap make_tm_2d(const void* ptr, uint64_t rows, uint64_t cols, uin
   return m;
 }
 
+// Output slice map for the TMA-store epilogue: [rows, ld] 16-bit matrix, box = 128 rows x 16 channels (32 B), no swizzle.
+static CUtensorMap make_tm_out(const void* ptr, uint64_t rows, uint64_t ld_elems, int fmt) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {ld_elems, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {16, static_cast<cuuint32_t>(kBM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&m, tm_dtype(fmt), 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(ICP_E_CUDA, "cuTensorMapEncodeTiled(out) failed (%d) rows=%llu ld=%llu", (int)r,
+                              (unsigned long long)rows, (unsigned long long)ld_elems);
+  return m;
+}
+
 // 2-D K-major weight matrix with rows of `row_bytes` per box (halo kernel's B operand).
 static CUtensorMap make_tm_2d_rows(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int row_bytes,
                                    int fmt) {
@@ -244,6 +259,7 @@ struct Act {   // NHWC 16-bit activation for max_batch images
 struct ConvLayer {
   std::string name;
   CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_o, tm_o2;   // destination slices (persistent kernel's TMA-store epilogue)
   ConvArgs args{};
   int cout = 0;
   int n_tiles = 1;
@@ -346,7 +362,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   const size_t stage_bytes = conv_stage_bytes(n_tile, rb);
   int pair_stage_n = 0;
   static const bool conv_v1 = getenv("ICP_CONV_V1") != nullptr;     // one tile per CTA (bring-up version)
-  const size_t budget = conv_v1 ? ((n_tile <= 128) ? 100 * 1024 : 200 * 1024) : 196 * 1024;
+  const size_t budget = conv_v1 ? ((n_tile <= 128) ? 100 * 1024 : 200 * 1024) : 204 * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (conv_v1 && stages > num_kb) stages = num_kb;
@@ -371,7 +387,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   if (persistent && use_pair && n_tile % 16 == 0) {
     csize = 2;
     const size_t sb2 = conv_stage_bytes(n_tile / 2, rb);
-    stages = static_cast<int>(196 * 1024 / sb2);
+    stages = static_cast<int>(204 * 1024 / sb2);
     if (stages > kMaxStages) stages = kMaxStages;
     pair_stage_n = n_tile / 2;
   }
@@ -518,7 +534,12 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.ldo2 = out2 ? out2->c : 0;
   a.coff2 = out2_coff;
   a.n_split = out2 ? n_split : (1 << 30);
-  L.smem = conv_smem_bytes(stages, pair_stage_n ? pair_stage_n : n_tile, rb);
+  L.smem = conv_smem_bytes(stages, pair_stage_n ? pair_stage_n : n_tile, rb, persistent);
+  {
+    const uint64_t out_rows = static_cast<uint64_t>(max_n) * oh * ow;
+    L.tm_o = make_tm_out(out.p, out_rows, out.c, fmt);
+    L.tm_o2 = out2 ? make_tm_out(out2->p, out_rows, out2->c, fmt) : L.tm_o;
+  }
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -554,9 +575,9 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
       // cp.async weight loaders: correct, measured slower than the TMA weight path (3.71 vs 3.22 ms/step) -> opt-in
       static const bool lsu_b = getenv("ICP_LSU_B") && atoi(getenv("ICP_LSU_B")) != 0;
       if (lsu_b && a.row_bytes == 128)
-        conv_igemm_persistent_kernel<false, true><<<clusters, kPersistLsuThreads, L.smem, st>>>(L.tm_a, L.tm_b, a, m_tiles, L.n_tiles);
+        conv_igemm_persistent_kernel<false, true><<<clusters, kPersistLsuThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, a, m_tiles, L.n_tiles);
       else
-        conv_igemm_persistent_kernel<false, false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, a, m_tiles, L.n_tiles);
+        conv_igemm_persistent_kernel<false, false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, a, m_tiles, L.n_tiles);
       CK(cudaGetLastError());
       return;
     }
@@ -572,7 +593,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true, false>, L.tm_a, L.tm_b, a, m_tiles, L.n_tiles));
+    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true, false>, L.tm_a, L.tm_b, L.tm_o, L.tm_o2, a, m_tiles, L.n_tiles));
   } else {
     dim3 grid(m_tiles, L.n_tiles);
     conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
