@@ -66,6 +66,7 @@ struct ConvArgs {
   const void* w_gmem;  // packed K-major weights [cout][w_kp] (LSU weight path)
   int w_kp;
   int split_n;         // experiment: issue each K step as two N/2 MMAs into disjoint accumulator columns
+  long long* dbg;      // optional timeline buffer (CTA 0 only): [role][event] clock64 stamps, see tools/timeline.py
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
@@ -334,6 +335,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const int s = it % a.stages;
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[0 * 512 + it] = clock64();
           const uint32_t sa = base + s * stage_bytes;
           if (ptx::elect_one()) {
             if constexpr (kPair) {
@@ -374,6 +376,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const int s = it % a.stages;
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[1 * 512 + it] = clock64();
           const uint32_t sb = base + s * stage_bytes + a_bytes;
           if (ptx::elect_one()) {
             if constexpr (kPair) {
@@ -443,6 +446,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(full_bar(s), ph);
           ptx::tc_fence_after();
+          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[2 * 512 + it] = clock64();
           const uint32_t sa = base + s * stage_bytes;
           const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
           const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
@@ -469,6 +473,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             }
           }
           __syncwarp();
+          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[3 * 512 + it] = clock64();
         }
         if (ptx::elect_one()) {
           if constexpr (kPair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
@@ -498,8 +503,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         loaded_n_base = n_base;
       }
       const uint32_t as = lt & 1u;
+      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[6 * 512 + lt] = clock64();
       ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
       ptx::tc_fence_after();
+      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[4 * 512 + lt] = clock64();
       const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
       // The accumulator leaves through shared memory and TMA stores: each thread owns one output pixel (TMEM
       // lane), converts 64 columns at a time, writes them as four [128 rows x 32 B] sub-boxes, and one thread
@@ -561,6 +568,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           ptx::tma_store_commit();
         }
       }
+      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[5 * 512 + lt] = clock64();
     }
     if (et == 0) ptx::tma_store_wait_all();      // smem must outlive the last store's read
   }

@@ -522,6 +522,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.shift = d_shift;
   static const bool split_n = getenv("ICP_SPLIT_N") != nullptr;
   a.split_n = (split_n && n_tile % 32 == 0) ? 1 : 0;
+  a.dbg = nullptr;
   a.w_gmem = d_w;
   a.w_kp = static_cast<int>(kp);
   a.floor = nullptr;
@@ -1621,7 +1622,21 @@ int icp_conv2d_bn_relu(int device, int precision, const float* x, int n, int h, 
     CK(cudaMemsetAsync(out.p, 0xFF, out_elems * 2, st));   // NaN pattern: unwritten outputs are visible
     ConvLayer L = make_conv(pool, "conv2d_bn_relu", n, in, 0, cin, wgt, kh, kw, cout, stride, same != 0, scale, shift,
                             relu != 0, out, 0, fmt);
+    const char* tl_path = getenv("ICP_TIMELINE");
+    long long* d_dbg = nullptr;
+    if (tl_path && L.persistent && !L.halo) {
+      d_dbg = static_cast<long long*>(pool.alloc(7 * 512 * 8));
+      CK(cudaMemsetAsync(d_dbg, 0, 7 * 512 * 8, st));
+      L.args.dbg = d_dbg;
+    }
     launch_conv(L, n, st);
+    if (d_dbg) {
+      std::vector<long long> hd(7 * 512);
+      CK(cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (FILE* f = fopen(tl_path, "wb")) { fwrite(hd.data(), 8, hd.size(), f); fclose(f); }
+      L.args.dbg = nullptr;
+    }
     h16_to_f32_kernel<<<static_cast<unsigned>((out_elems + 255) / 256), 256, 0, st>>>(out.p, d_yf,
                                                                                      static_cast<size_t>(n) * oh * ow,
                                                                                      cout, cout, 0, fmt);
