@@ -130,17 +130,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (lane == 0) {
       // ---------------- strip producer ----------------
       const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;                // ring position kept incrementally: no division in the loops
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int band = item / a.n_tiles;
         const int img = a.tall ? 0 : band / bands_per_image;
         const int p0 = (band - img * bands_per_image) * kBM * a.T;
         const int h_first = p0 / a.wp;
-        for (int c = 0; c < a.chunks; ++c, ++it) {
-          const uint32_t s = it % a.nstrips;
-          ptx::mbar_wait(strip_empty(s), ((it / a.nstrips) & 1u) ^ 1u);
+        for (int c = 0; c < a.chunks; ++c) {
+          ptx::mbar_wait(strip_empty(s), ph ^ 1u);
           ptx::mbar_expect_tx(strip_full(s), strip_tx);
           ptx::tma_load_4d(strip0 + s * a.strip_bytes, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h, img);
+          if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -151,14 +151,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes);
         for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
       } else {
-        uint32_t bi = 0;
+        uint32_t sb = 0, phb = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
           const int n_base = (item % a.n_tiles) * a.n_tile;
-          for (int i = 0; i < a.chunks * taps; ++i, ++bi) {
-            const uint32_t sb = bi % a.b_stages;
-            ptx::mbar_wait(b_empty(sb), ((bi / a.b_stages) & 1u) ^ 1u);
+          for (int i = 0; i < a.chunks * taps; ++i) {
+            ptx::mbar_wait(b_empty(sb), phb ^ 1u);
             ptx::mbar_expect_tx(b_full(sb), tap_bytes);
             ptx::tma_load_2d(wbase + sb * b_stride, &tm_b, b_full(sb), i * ck, n_base);
+            if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
           }
         }
       }
@@ -179,8 +179,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t tap_units = tap_bytes >> 4;
       const uint32_t sub_units = (static_cast<uint32_t>(kBM) * rb) >> 4;
       if (a.w_resident) ptx::mbar_wait(w_full, 0);
-      uint32_t it = 0, lb = 0, bi = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lb) {
+      uint32_t s = 0, ph = 0, sb = 0, phb = 0, as = 0, pha = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int band = item / a.n_tiles;
         const int img = a.tall ? 0 : band / bands_per_image;
         const int p0 = (band - img * bands_per_image) * kBM * a.T;
@@ -188,23 +188,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t local_units = (static_cast<uint32_t>(p0 - h_first * a.wp) * rb) >> 4;
         int nsub = (positions - p0 + kBM - 1) / kBM;                       // sub-tiles that hold outputs
         if (nsub > a.T) nsub = a.T;
-        const uint32_t as = lb % a.acc_sets;
-        ptx::mbar_wait(tmem_empty(as), ((lb / a.acc_sets) & 1u) ^ 1u);
+        ptx::mbar_wait(tmem_empty(as), pha ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tacc0 = tmem_base + as * a.acc_cols;
-        for (int c = 0; c < a.chunks; ++c, ++it) {
-          const uint32_t s = it % a.nstrips;
-          ptx::mbar_wait(strip_full(s), (it / a.nstrips) & 1u);
+        for (int c = 0; c < a.chunks; ++c) {
+          ptx::mbar_wait(strip_full(s), ph);
           ptx::tc_fence_after();
           const uint32_t a_units0 = ((strip0 + s * a.strip_bytes) >> 4) + local_units;
           for (int tap = 0; tap < taps; ++tap) {
             uint32_t b_units;
-            uint32_t sb = 0;
             if (a.w_resident) {
               b_units = (wbase >> 4) + static_cast<uint32_t>(c * taps + tap) * tap_units;
             } else {
-              sb = bi % a.b_stages;
-              ptx::mbar_wait(b_full(sb), (bi / a.b_stages) & 1u);
+              ptx::mbar_wait(b_full(sb), phb);
               ptx::tc_fence_after();
               b_units = (wbase + sb * b_stride) >> 4;
             }
@@ -218,12 +214,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             if (!a.w_resident) {
               ptx::umma_commit(b_empty(sb));
-              ++bi;
+              if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
             }
           }
           ptx::umma_commit(strip_empty(s));
+          if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(tmem_full(as));
+        if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
       }
     }
   } else {
@@ -231,9 +229,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int et = threadIdx.x - 64;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    uint32_t lb = 0;
+    uint32_t as = 0, pha = 0;
     int loaded_n_base = -1;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lb) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int band = item / a.n_tiles;
       const int n_base = (item - band * a.n_tiles) * a.n_tile;
       const int img = a.tall ? 0 : band / bands_per_image;
@@ -247,8 +245,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         asm volatile("bar.sync 1, 128;" ::: "memory");
         loaded_n_base = n_base;
       }
-      const uint32_t as = lb % a.acc_sets;
-      ptx::mbar_wait(tmem_full(as), (lb / a.acc_sets) & 1u);
+      ptx::mbar_wait(tmem_full(as), pha);
       ptx::tc_fence_after();
       for (int j = 0; j < a.T; ++j) {
         if (p0 + j * kBM >= positions) break;
@@ -290,6 +287,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(tmem_empty(as));
+      if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
     }
   }
 

@@ -138,9 +138,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         bn = t / a.oh;
       }
       int tap = 0, cb = 0;
+      int s = 0;
+      uint32_t ph = 0;                       // stage index / phase kept incrementally: no division in the loop
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % a.stages;
-        const uint32_t ph = (kb / a.stages) & 1;
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
         ptx::mbar_expect_tx(full_bar(s), stage_tx);
         const uint32_t sa = base + s * stage_bytes;
@@ -153,6 +153,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
         ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
         if (++cb == a.cblocks) { cb = 0; ++tap; }
+        if (++s == a.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -160,9 +161,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
       const int ksteps = a.row_bytes / 32;
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % a.stages;
-        const uint32_t ph = (kb / a.stages) & 1;
         ptx::mbar_wait(full_bar(s), ph);
         ptx::tc_fence_after();
         const uint32_t sa = base + s * stage_bytes;
@@ -173,6 +174,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
         }
         ptx::umma_commit(empty_bar(s));      // smem slot free once these MMAs retire
+        if (++s == a.stages) { s = 0; ph ^= 1u; }
       }
       ptx::umma_commit(tmem_full_bar);       // accumulator complete
     }
@@ -320,6 +322,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     {
       // ---------------- TMA producer (warp-converged; one elected lane issues) ----------------
       uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;                       // ring position kept incrementally: no division in the K loop
       for (int t = first; t < total_tiles; t += step) {
         const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
         int bw = 0, bh = 0, bn = 0;
@@ -332,8 +336,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         }
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[0 * 512 + it] = clock64();
           const uint32_t sa = base + s * stage_bytes;
@@ -360,6 +362,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           }
           __syncwarp();
           if (++cb == a.cblocks) { cb = 0; ++tap; }
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -370,11 +373,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       // loads of a stage serialise (measured ~900 cycles per K block on every layer regardless of tile size),
       // so the two operands get one issuing thread each.
       uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = first; t < total_tiles; t += step) {
         const int n_base = (t % n_tiles) * a.n_tile;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
           if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[1 * 512 + it] = clock64();
           const uint32_t sb = base + s * stage_bytes + a_bytes;
@@ -388,6 +391,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             }
           }
           __syncwarp();
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -436,14 +440,14 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       const uint32_t idesc = ptx::make_idesc_f16(a.fmt, pair ? 2 * kBM : kBM, a.n_tile);
       const int ksteps = a.row_bytes / 32;
       uint32_t it = 0, lt = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = first; t < total_tiles; t += step, ++lt) {
         const uint32_t as = lt & 1u;
         ptx::mbar_wait(tmem_empty(as), ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tacc = tmem_base + as * a.tmem_cols;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1;
           ptx::mbar_wait(full_bar(s), ph);
           ptx::tc_fence_after();
           if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[2 * 512 + it] = clock64();
@@ -474,6 +478,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           }
           __syncwarp();
           if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[3 * 512 + it] = clock64();
+          if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
         if (ptx::elect_one()) {
           if constexpr (kPair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
