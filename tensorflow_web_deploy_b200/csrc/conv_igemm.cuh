@@ -242,6 +242,7 @@ template <bool kPair, bool kLsuB>
 __global__ void __launch_bounds__(kLsuB ? kPersistLsuThreads : kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                              const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
+                             const __grid_constant__ CUtensorMap tm_o64, const __grid_constant__ CUtensorMap tm_o64_2,
                              const ConvArgs a, const int m_tiles, const int n_tiles) {
   constexpr int csize = kPair ? 2 : 1;
   // csize == 2: launched as 2-CTA clusters = CTA pairs (cta_group::2).  The pair owns two consecutive M tiles
@@ -292,6 +293,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     ptx::prefetch_tmap(&tm_b);
     ptx::prefetch_tmap(&tm_o);
     ptx::prefetch_tmap(&tm_o2);
+    ptx::prefetch_tmap(&tm_o64);
+    ptx::prefetch_tmap(&tm_o64_2);
     for (int s = 0; s < a.stages; ++s) {
       // arrivals per stage: the A producer + either the W producer thread (TMA) or the 128 LSU loader threads
       ptx::mbar_init(full_bar(s), kLsuB ? 129 : 2);
@@ -552,23 +555,42 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         // staging buffer is free once the previous chunk's stores have read it
         if (et == 0) ptx::tma_store_wait_read();
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        // A full 64-column chunk that lies in one destination goes out as ONE [128 rows x 128 B] box (128-byte
+        // swizzled staging: conflict-free 16-byte writes, and a quarter of the box rows the TMA unit has to walk
+        // compared with four 32-byte-row boxes); tails and chunks straddling n_split use 16-column boxes.
+        const int col0 = n_base + c0;
+        const bool wide = (nsub == 4) && (col0 >= a.n_split || col0 + 64 <= a.n_split);
+        if (wide) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < nsub) {
-            const uint32_t dst = out_stage + j * 4096u + static_cast<uint32_t>(row) * 32u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[8 * j]), "r"(pk[8 * j + 1]),
-                         "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[8 * j + 4]),
-                         "r"(pk[8 * j + 5]), "r"(pk[8 * j + 6]), "r"(pk[8 * j + 7]) : "memory");
+          for (int q = 0; q < 8; ++q) {            // 16-byte chunk q of this thread's 128-byte row
+            const uint32_t dst = out_stage + static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(q ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nsub) {
+              const uint32_t dst = out_stage + j * 4096u + static_cast<uint32_t>(row) * 32u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[8 * j]), "r"(pk[8 * j + 1]),
+                           "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[8 * j + 4]),
+                           "r"(pk[8 * j + 5]), "r"(pk[8 * j + 6]), "r"(pk[8 * j + 7]) : "memory");
+            }
           }
         }
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
-          for (int j = 0; j < nsub; ++j) {
-            const int col = n_base + c0 + 16 * j;
-            if (col < a.n_split) ptx::tma_store_2d(&tm_o, out_stage + j * 4096u, a.coff + col, m0);
-            else ptx::tma_store_2d(&tm_o2, out_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
+          if (wide) {
+            if (col0 < a.n_split) ptx::tma_store_2d(&tm_o64, out_stage, a.coff + col0, m0);
+            else ptx::tma_store_2d(&tm_o64_2, out_stage, a.coff2 + col0 - a.n_split, m0);
+          } else {
+            for (int j = 0; j < nsub; ++j) {
+              const int col = col0 + 16 * j;
+              if (col < a.n_split) ptx::tma_store_2d(&tm_o, out_stage + j * 4096u, a.coff + col, m0);
+              else ptx::tma_store_2d(&tm_o2, out_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
+            }
           }
           ptx::tma_store_commit();
         }

@@ -99,15 +99,15 @@ static CUtensorMap make_tm_2d(const void* ptr, uint64_t rows, uint64_t cols, uin
 }
 
 // Output slice map for the TMA-store epilogue: [rows, ld] 16-bit matrix, box = 128 rows x 16 channels (32 B), no swizzle.
-static CUtensorMap make_tm_out(const void* ptr, uint64_t rows, uint64_t ld_elems, int fmt) {
+static CUtensorMap make_tm_out(const void* ptr, uint64_t rows, uint64_t ld_elems, int fmt, int box_cols = 16) {
   CUtensorMap m;
   cuuint64_t dims[2] = {ld_elems, rows};
   cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {16, static_cast<cuuint32_t>(kBM)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(kBM)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(&m, tm_dtype(fmt), 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(ICP_E_CUDA, "cuTensorMapEncodeTiled(out) failed (%d) rows=%llu ld=%llu", (int)r,
                               (unsigned long long)rows, (unsigned long long)ld_elems);
   return m;
@@ -259,7 +259,8 @@ struct Act {   // NHWC 16-bit activation for max_batch images
 struct ConvLayer {
   std::string name;
   CUtensorMap tm_a, tm_b;
-  CUtensorMap tm_o, tm_o2;   // destination slices (persistent kernel's TMA-store epilogue)
+  CUtensorMap tm_o, tm_o2;   // destination slices (persistent kernel's TMA-store epilogue): 16-column boxes
+  CUtensorMap tm_o64, tm_o64_2;   // same, 64-column (128-byte, swizzled) boxes
   ConvArgs args{};
   int cout = 0;
   int n_tiles = 1;
@@ -540,6 +541,8 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     const uint64_t out_rows = static_cast<uint64_t>(max_n) * oh * ow;
     L.tm_o = make_tm_out(out.p, out_rows, out.c, fmt);
     L.tm_o2 = out2 ? make_tm_out(out2->p, out_rows, out2->c, fmt) : L.tm_o;
+    L.tm_o64 = make_tm_out(out.p, out_rows, out.c, fmt, 64);
+    L.tm_o64_2 = out2 ? make_tm_out(out2->p, out_rows, out2->c, fmt, 64) : L.tm_o64;
   }
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -576,9 +579,9 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
       // cp.async weight loaders: correct, measured slower than the TMA weight path (3.71 vs 3.22 ms/step) -> opt-in
       static const bool lsu_b = getenv("ICP_LSU_B") && atoi(getenv("ICP_LSU_B")) != 0;
       if (lsu_b && a.row_bytes == 128)
-        conv_igemm_persistent_kernel<false, true><<<clusters, kPersistLsuThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, a, m_tiles, L.n_tiles);
+        conv_igemm_persistent_kernel<false, true><<<clusters, kPersistLsuThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
       else
-        conv_igemm_persistent_kernel<false, false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, a, m_tiles, L.n_tiles);
+        conv_igemm_persistent_kernel<false, false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
       CK(cudaGetLastError());
       return;
     }
@@ -594,7 +597,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true, false>, L.tm_a, L.tm_b, L.tm_o, L.tm_o2, a, m_tiles, L.n_tiles));
+    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true, false>, L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles));
   } else {
     dim3 grid(m_tiles, L.n_tiles);
     conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
