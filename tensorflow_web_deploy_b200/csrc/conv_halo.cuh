@@ -24,13 +24,13 @@
 //    k x 1 filters run as 1 x k on transposed storage: `transpose_out` makes the epilogue store pixel (y,x) at
 //    (x,y), so a 1x7 -> 7x1 chain alternates layouts for free.
 //
-// Warp roles: 0 = strip producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue, 6 = weight producer.
+// Warp roles: 0 = strip producer, 1 = TMEM owner + MMA issuer, 2..5 and 7..10 = epilogue, 6 = weight producer.
 #pragma once
 #include "conv_igemm.cuh"
 
 namespace icp {
 
-constexpr int kHaloThreads = 224;
+constexpr int kHaloThreads = 352;
 
 struct HaloArgs {
   int n_images;
@@ -60,6 +60,7 @@ struct HaloArgs {
   int ldo, coff;
   const float* scale;
   const float* shift;
+  long long* dbg;       // optional timeline buffer (CTA 0 only), same rows as the persistent kernel (tools/timeline.py)
 };
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
@@ -88,6 +89,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   float* s_scale = reinterpret_cast<float*>(gbase + (bar_base - base) + 256);
   float* s_shift = s_scale + 256;
   uint32_t* tap_off = reinterpret_cast<uint32_t*>(s_shift + 256);    // [taps] A shift of tap (r,s), 16-B units
+  int* s_pix = reinterpret_cast<int*>(tap_off + 64);                 // [128] output pixel of each sub-tile row, -1 = none
+  const uint32_t stage_base = bar_base + 256u + 2048u + 256u + 512u; // epilogue staging: 128 rows x 128 B
 
   const int taps = a.kh * a.kw;
   const int ck = a.row_bytes / 2;
@@ -108,7 +111,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
-      ptx::mbar_init(tmem_empty(i), 128);
+      ptx::mbar_init(tmem_empty(i), 256);
     }
     ptx::mbar_init(w_full, 1);
     for (int i = 0; i < a.b_stages; ++i) {
@@ -126,167 +129,292 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
+  // Every role loop runs warp-converged and hands the uniform-datapath instructions (TMA, MMA, commit) to one
+  // elected lane: under `if (lane == 0)` the compiler wraps each of them in an ELECT/branch loop, which cost this
+  // kernel ~160 cycles per MMA (timeline of conv1: 72 MMAs in 11.6k cycles) against ~32 of tensor-pipe time.
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- strip producer ----------------
-      const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
-      uint32_t s = 0, ph = 0;                // ring position kept incrementally: no division in the loops
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int band = item / a.n_tiles;
-        const int img = a.tall ? 0 : band / bands_per_image;
-        const int p0 = (band - img * bands_per_image) * kBM * a.T;
-        const int h_first = p0 / a.wp;
-        for (int c = 0; c < a.chunks; ++c) {
-          ptx::mbar_wait(strip_empty(s), ph ^ 1u);
+    // ---------------- strip producer ----------------
+    const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
+    uint32_t s = 0, ph = 0;                // ring position kept incrementally: no division in the loops
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int band = item / a.n_tiles;
+      const int img = a.tall ? 0 : band / bands_per_image;
+      const int p0 = (band - img * bands_per_image) * kBM * a.T;
+      const int h_first = p0 / a.wp;
+      for (int c = 0; c < a.chunks; ++c) {
+        ptx::mbar_wait(strip_empty(s), ph ^ 1u);
+        if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[0 * 512 + it] = clock64();
+        ++it;
+        if (ptx::elect_one()) {
           ptx::mbar_expect_tx(strip_full(s), strip_tx);
           ptx::tma_load_4d(strip0 + s * a.strip_bytes, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h, img);
-          if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 6) {
-    if (lane == 0) {
-      // ---------------- weight producer ----------------
-      if (a.w_resident) {
+    // ---------------- weight producer ----------------
+    if (a.w_resident) {
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes);
         for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
-      } else {
-        uint32_t sb = 0, phb = 0;
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-          const int n_base = (item % a.n_tiles) * a.n_tile;
-          for (int i = 0; i < a.chunks * taps; ++i) {
-            ptx::mbar_wait(b_empty(sb), phb ^ 1u);
+      }
+      __syncwarp();
+    } else {
+      uint32_t sb = 0, phb = 0;
+      int n_idx = blockIdx.x % a.n_tiles;
+      const int n_step = gridDim.x % a.n_tiles;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int n_base = n_idx * a.n_tile;
+        n_idx += n_step;
+        if (n_idx >= a.n_tiles) n_idx -= a.n_tiles;
+        for (int i = 0; i < a.chunks * taps; ++i) {
+          ptx::mbar_wait(b_empty(sb), phb ^ 1u);
+          if (ptx::elect_one()) {
             ptx::mbar_expect_tx(b_full(sb), tap_bytes);
             ptx::tma_load_2d(wbase + sb * b_stride, &tm_b, b_full(sb), i * ck, n_base);
-            if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
           }
+          __syncwarp();
+          if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      // The issuing thread must stay lean (an M128 x N32 x K16 MMA holds the tensor pipe for 16 cycles): no
-      // division and no 64-bit descriptor construction in the inner loops — descriptors differ only in their
-      // 14-bit address field (16-byte units), advanced with a per-tap table.
-      const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
-      const int ksteps = a.row_bytes / 32;
-      const uint64_t desc_hi = ptx::make_smem_desc_rows(0, rb);          // everything but the address
-      for (int tap = 0; tap < taps; ++tap) {
-        const int r = tap / a.kw;
-        tap_off[tap] = (static_cast<uint32_t>(r * a.wp + (tap - r * a.kw)) * rb) >> 4;
-      }
-      const uint32_t tap_units = tap_bytes >> 4;
-      const uint32_t sub_units = (static_cast<uint32_t>(kBM) * rb) >> 4;
-      if (a.w_resident) ptx::mbar_wait(w_full, 0);
-      uint32_t s = 0, ph = 0, sb = 0, phb = 0, as = 0, pha = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int band = item / a.n_tiles;
-        const int img = a.tall ? 0 : band / bands_per_image;
-        const int p0 = (band - img * bands_per_image) * kBM * a.T;
-        const int h_first = p0 / a.wp;
-        const uint32_t local_units = (static_cast<uint32_t>(p0 - h_first * a.wp) * rb) >> 4;
-        int nsub = (positions - p0 + kBM - 1) / kBM;                       // sub-tiles that hold outputs
-        if (nsub > a.T) nsub = a.T;
-        ptx::mbar_wait(tmem_empty(as), pha ^ 1u);
+    // ---------------- MMA issuer ----------------
+    // Descriptors differ only in their 14-bit address field (16-byte units), advanced with a per-tap table.
+    const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+    const int ksteps = a.row_bytes / 32;
+    const uint64_t desc_hi = ptx::make_smem_desc_rows(0, rb);          // everything but the address
+    for (int tap = lane; tap < taps; tap += 32) {
+      const int r = tap / a.kw;
+      tap_off[tap] = (static_cast<uint32_t>(r * a.wp + (tap - r * a.kw)) * rb) >> 4;
+    }
+    __syncwarp();
+    const uint32_t tap_units = tap_bytes >> 4;
+    const uint32_t sub_units = (static_cast<uint32_t>(kBM) * rb) >> 4;
+    if (a.w_resident) ptx::mbar_wait(w_full, 0);
+    uint32_t s = 0, ph = 0, sb = 0, phb = 0, as = 0, pha = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int band = item / a.n_tiles;
+      const int img = a.tall ? 0 : band / bands_per_image;
+      const int p0 = (band - img * bands_per_image) * kBM * a.T;
+      const int h_first = p0 / a.wp;
+      const uint32_t local_units = (static_cast<uint32_t>(p0 - h_first * a.wp) * rb) >> 4;
+      int nsub = (positions - p0 + kBM - 1) / kBM;                       // sub-tiles that hold outputs
+      if (nsub > a.T) nsub = a.T;
+      ptx::mbar_wait(tmem_empty(as), pha ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t tacc0 = tmem_base + as * a.acc_cols;
+      for (int c = 0; c < a.chunks; ++c) {
+        ptx::mbar_wait(strip_full(s), ph);
         ptx::tc_fence_after();
-        const uint32_t tacc0 = tmem_base + as * a.acc_cols;
-        for (int c = 0; c < a.chunks; ++c) {
-          ptx::mbar_wait(strip_full(s), ph);
-          ptx::tc_fence_after();
-          const uint32_t a_units0 = ((strip0 + s * a.strip_bytes) >> 4) + local_units;
-          for (int tap = 0; tap < taps; ++tap) {
-            uint32_t b_units;
-            if (a.w_resident) {
-              b_units = (wbase >> 4) + static_cast<uint32_t>(c * taps + tap) * tap_units;
-            } else {
-              ptx::mbar_wait(b_full(sb), phb);
-              ptx::tc_fence_after();
-              b_units = (wbase + sb * b_stride) >> 4;
+        if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[2 * 512 + it] = clock64();
+        const uint32_t a_units0 = ((strip0 + s * a.strip_bytes) >> 4) + local_units;
+        if (a.w_resident) {
+          if (ptx::elect_one()) {
+            uint32_t b_units = (wbase >> 4) + static_cast<uint32_t>(c * taps) * tap_units;
+            for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
+              uint32_t au = a_units0 + tap_off[tap];
+              uint32_t tacc = tacc0;
+              const uint32_t acc = static_cast<uint32_t>(c | tap);
+              for (int j = 0; j < nsub; ++j, au += sub_units, tacc += a.n_tile) {
+                if (ksteps == 2) {
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
+                } else {
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
+                  ptx::umma_f16(tacc, desc_hi | (au + 4u), desc_hi | (b_units + 4u), idesc, 1u);
+                  ptx::umma_f16(tacc, desc_hi | (au + 6u), desc_hi | (b_units + 6u), idesc, 1u);
+                }
+              }
             }
-            const uint32_t au0 = a_units0 + tap_off[tap];
-            for (int j = 0; j < nsub; ++j) {
-              const uint32_t au = au0 + j * sub_units;
-              const uint32_t tacc = tacc0 + j * a.n_tile;
-              for (int k = 0; k < ksteps; ++k)
-                ptx::umma_f16(tacc, desc_hi | (au + 2u * k), desc_hi | (b_units + 2u * k), idesc,
-                              static_cast<uint32_t>(c | tap | k));
-            }
-            if (!a.w_resident) {
-              ptx::umma_commit(b_empty(sb));
-              if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
-            }
+            ptx::umma_commit(strip_empty(s));
           }
-          ptx::umma_commit(strip_empty(s));
-          if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
+          __syncwarp();
+        } else {
+          for (int tap = 0; tap < taps; ++tap) {
+            ptx::mbar_wait(b_full(sb), phb);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t b_units = (wbase + sb * b_stride) >> 4;
+              uint32_t au = a_units0 + tap_off[tap];
+              uint32_t tacc = tacc0;
+              const uint32_t acc = static_cast<uint32_t>(c | tap);
+              for (int j = 0; j < nsub; ++j, au += sub_units, tacc += a.n_tile) {
+                if (ksteps == 2) {
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
+                } else {
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
+                  ptx::umma_f16(tacc, desc_hi | (au + 4u), desc_hi | (b_units + 4u), idesc, 1u);
+                  ptx::umma_f16(tacc, desc_hi | (au + 6u), desc_hi | (b_units + 6u), idesc, 1u);
+                }
+              }
+              ptx::umma_commit(b_empty(sb));
+              if (tap == taps - 1) ptx::umma_commit(strip_empty(s));
+            }
+            __syncwarp();
+            if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
+          }
         }
-        ptx::umma_commit(tmem_full(as));
-        if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
+        if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[3 * 512 + it] = clock64();
+        ++it;
+        if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
       }
+      if (ptx::elect_one()) ptx::umma_commit(tmem_full(as));
+      __syncwarp();
+      if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
     }
   } else {
-    // ---------------- epilogue (warps 2..5) ----------------
-    const int et = threadIdx.x - 64;
+    // ---------------- epilogue (warps 2..5 and 7..10) ----------------
+    // Two warps per TMEM lane quarter, each owning half of the 16-column pieces of a <=64-column chunk; the loads
+    // of unit u+1 (next chunk / next sub-tile) are issued before the arithmetic of unit u (tcgen05.ld moves only
+    // 64 B/cycle/SM and one warp per scheduler issues the convert/pack code slowly — see conv_igemm.cuh).
+    // TMEM -> registers -> scale/shift/ReLU -> 16-bit -> shared staging (128 rows x 128 B, 16-byte chunks XOR-
+    // swizzled by row) -> global with 8 consecutive lanes per pixel, so every warp store covers whole lines.
+    const int grp = warp >= 7 ? 1 : 0;
+    const int et = grp ? static_cast<int>(threadIdx.x) - 224 + 128 : static_cast<int>(threadIdx.x) - 64;   // 0..255
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint32_t as = 0, pha = 0;
     int loaded_n_base = -1;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int lt = 0;
+    uint8_t* stage_g = gbase + (stage_base - base);
+    const int cl = et & 7;                     // chunk lane of the copy-out: 8 lanes cover one pixel's 128 bytes
+    const int r0 = et >> 3;                    // copy-out rows r0, r0+32, r0+64, r0+96
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lt) {
       const int band = item / a.n_tiles;
       const int n_base = (item - band * a.n_tiles) * a.n_tile;
       const int img = a.tall ? 0 : band / bands_per_image;
       const int p0 = (band - img * bands_per_image) * kBM * a.T;
-      if (n_base != loaded_n_base) {             // uniform across the 128 epilogue threads
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < a.n_tile; i += 128) {
+      if (n_base != loaded_n_base) {             // uniform across the epilogue threads
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < a.n_tile; i += 256) {
           s_scale[i] = __ldg(a.scale + n_base + i);
           s_shift[i] = __ldg(a.shift + n_base + i);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         loaded_n_base = n_base;
       }
+      int nsub = (positions - p0 + kBM - 1) / kBM;
+      if (nsub > a.T) nsub = a.T;
+      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[6 * 512 + lt] = clock64();
       ptx::mbar_wait(tmem_full(as), pha);
       ptx::tc_fence_after();
-      for (int j = 0; j < a.T; ++j) {
-        if (p0 + j * kBM >= positions) break;
-        const int p = p0 + j * kBM + row;
-        int oy = p / a.wp;                         // tall mode: row over all images
-        const int ox = p - oy * a.wp;
-        int im = img;
-        if (a.tall) { im = oy / a.oh; oy -= im * a.oh; }
-        const bool valid = (im < a.n_images) && (oy < a.oh) && (ox < a.ow);
-        const size_t pix = a.transpose_out ? (static_cast<size_t>(im) * a.ow + ox) * a.oh + oy
-                                           : (static_cast<size_t>(im) * a.oh + oy) * a.ow + ox;
-        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + pix * a.ldo + a.coff + n_base;
-        const uint32_t taddr = tmem_base + as * a.acc_cols + j * a.n_tile + (static_cast<uint32_t>(quarter * 32) << 16);
-        for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
-          uint32_t v[32];
-          const bool two = c0 + 16 < a.n_tile;
-          ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          if (two) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-          ptx::tmem_ld_wait();
+      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[4 * 512 + lt] = clock64();
+      const uint32_t tbase = tmem_base + as * a.acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+
+      // 16-column pieces of the chunk at c0 owned by this thread: [first, first + np)
+      auto geom = [&](int c0, int& cp, int& first, int& np) {
+        cp = (a.n_tile - c0) >> 4;
+        if (cp > 4) cp = 4;
+        const int h0 = (cp + 1) >> 1;
+        first = grp ? h0 : 0;
+        np = grp ? cp - h0 : h0;
+      };
+      auto issue = [&](uint32_t (&v)[32], int j, int c0) {
+        int cp, first, np;
+        geom(c0, cp, first, np);
+        const uint32_t t0 = tbase + j * a.n_tile + c0 + 16 * first;
+        if (np > 0) ptx::tmem_ld_32x32b_x16(t0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if (np > 1) ptx::tmem_ld_32x32b_x16(t0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+      };
+      auto process = [&](uint32_t (&v)[32], int j, int c0) {
+        int cp, first, np;
+        geom(c0, cp, first, np);
+        int pix = -1;
+        if (c0 == 0 && grp == 0) {               // one thread per row maps the sub-tile's positions to output pixels
+          const int p = p0 + j * kBM + row;
+          int oy = p / a.wp;                     // tall mode: row over all images
+          const int ox = p - oy * a.wp;
+          int im = img;
+          if (a.tall) { im = oy / a.oh; oy -= im * a.oh; }
+          if ((im < a.n_images) && (oy < a.oh) && (ox < a.ow))
+            pix = a.transpose_out ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
+        }
+        uint32_t q[16];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !two) break;
-            const int cc = c0 + 16 * h;
-            uint32_t q[8];
+        for (int jj = 0; jj < 2; ++jj) {
+          if (jj < np) {
+            const int cc = c0 + 16 * (first + jj);
+            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cc);
+            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cc);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float x0 = fmaf(__uint_as_float(v[16 * h + 2 * i]), s_scale[cc + 2 * i], s_shift[cc + 2 * i]);
-              float x1 = fmaf(__uint_as_float(v[16 * h + 2 * i + 1]), s_scale[cc + 2 * i + 1], s_shift[cc + 2 * i + 1]);
-              if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-              q[i] = pack2(x0, x1, a.fmt);
-            }
-            if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>(orow + cc);
-              dst[0] = make_uint4(q[0], q[1], q[2], q[3]);
-              dst[1] = make_uint4(q[4], q[5], q[6], q[7]);
+            for (int i = 0; i < 4; ++i) {
+              const float4 sc = sc4[i], sh = sh4[i];
+              float x0 = fmaf(__uint_as_float(v[16 * jj + 4 * i]), sc.x, sh.x);
+              float x1 = fmaf(__uint_as_float(v[16 * jj + 4 * i + 1]), sc.y, sh.y);
+              float x2 = fmaf(__uint_as_float(v[16 * jj + 4 * i + 2]), sc.z, sh.z);
+              float x3 = fmaf(__uint_as_float(v[16 * jj + 4 * i + 3]), sc.w, sh.w);
+              if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+              q[8 * jj + 2 * i] = pack2(x0, x1, a.fmt);
+              q[8 * jj + 2 * i + 1] = pack2(x2, x3, a.fmt);
             }
           }
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");                 // staging free (previous copy-out finished)
+        if (c0 == 0 && grp == 0) s_pix[row] = pix;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          if (jj < np) {
+            const int ch = 2 * (first + jj);       // 16-byte chunk index within the 128-byte staging row
+            *reinterpret_cast<uint4*>(stage_g + row * 128 + ((ch ^ (row & 7)) << 4)) =
+                make_uint4(q[8 * jj], q[8 * jj + 1], q[8 * jj + 2], q[8 * jj + 3]);
+            *reinterpret_cast<uint4*>(stage_g + row * 128 + (((ch + 1) ^ (row & 7)) << 4)) =
+                make_uint4(q[8 * jj + 4], q[8 * jj + 5], q[8 * jj + 6], q[8 * jj + 7]);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * a.T + j < 512) a.dbg[8 * 512 + lt * a.T + j] = clock64();
+        if (cl < 2 * cp) {                         // lane's 8 columns exist in this chunk
+          int px[4];
+          uint4 val[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) px[i] = s_pix[r0 + 32 * i];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + 32 * i;
+            val[i] = *reinterpret_cast<const uint4*>(stage_g + r * 128 + ((cl ^ (r & 7)) << 4));
+          }
+          uint16_t* dst = reinterpret_cast<uint16_t*>(a.out) + a.coff + n_base + c0 + cl * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (px[i] >= 0) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(px[i]) * a.ldo) = val[i];
+        }
+        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * a.T + j < 512) a.dbg[9 * 512 + lt * a.T + j] = clock64();
+      };
+      auto release = [&]() {                       // accumulator fully read: hand it back to the MMA issuer
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(tmem_empty(as));
+      };
+      // units (sub-tile j, chunk c0) in order; the next unit's loads are in flight while this one is converted
+      uint32_t va[32], vb[32];
+      int j = 0, c0 = 0;
+      issue(va, 0, 0);
+      while (true) {
+        int nj = j, nc = c0 + 64;
+        if (nc >= a.n_tile) { nc = 0; ++nj; }
+        ptx::tmem_ld_wait();
+        if (a.dbg && blockIdx.x == 0 && et == 0 && c0 == 0 && lt * a.T + j < 512) a.dbg[7 * 512 + lt * a.T + j] = clock64();
+        if (nj < nsub) issue(vb, nj, nc); else release();
+        process(va, j, c0);
+        if (nj >= nsub) break;
+        j = nj; c0 = nc;
+        nc = c0 + 64;
+        if (nc >= a.n_tile) { nc = 0; ++nj; }
+        ptx::tmem_ld_wait();
+        if (a.dbg && blockIdx.x == 0 && et == 0 && c0 == 0 && lt * a.T + j < 512) a.dbg[7 * 512 + lt * a.T + j] = clock64();
+        if (nj < nsub) issue(va, nj, nc); else release();
+        process(vb, j, c0);
+        if (nj >= nsub) break;
+        j = nj; c0 = nc;
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(tmem_empty(as));
+      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[5 * 512 + lt] = clock64();
       if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
     }
   }
@@ -302,7 +430,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
 inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes) {
   return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 256 +
-         2048 + 256;   // barriers, scale/shift, per-tap offset table
+         2048 + 256 + 512 + 16384;   // barriers, scale/shift, per-tap offset table, row->pixel table, epilogue staging
 }
 
 }  // namespace icp

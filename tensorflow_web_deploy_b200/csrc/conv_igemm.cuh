@@ -28,10 +28,9 @@ constexpr int kBM = 128;                    // output pixels per CTA tile (UMMA 
 constexpr int kBK = 64;                     // K elements per pipeline stage (one 128-B swizzle row)
 constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kConvThreads = 192;
-constexpr int kPersistThreads = 224;        // + warp 6: second TMA producer (weight tiles)
-constexpr int kPersistLsuThreads = 352;     // + warps 7..10: weight tiles through the LSU (cp.async) instead of TMA
+constexpr int kPersistThreads = 352;        // warps 0/6 TMA producers, 1 MMA issuer, 2..5 and 7..10 epilogue
+constexpr int kEpiThreads = 256;            // two epilogue warps per TMEM lane quarter (one per half of a 64-column chunk)
 constexpr uint32_t kOutStageBytes = 16384;  // epilogue staging (persistent kernel)
-constexpr int kLsuLag = 2;                  // cp.async groups a loader thread keeps in flight
 constexpr int kMaxStages = 12;
 
 struct ConvArgs {
@@ -65,7 +64,7 @@ struct ConvArgs {
   const float* floor;
   const void* w_gmem;  // packed K-major weights [cout][w_kp] (LSU weight path)
   int w_kp;
-  int split_n;         // experiment: issue each K step as two N/2 MMAs into disjoint accumulator columns
+  int epi_staged;      // one-tile kernel: 1 = epilogue through shared staging + coalesced stores, 0 = row-per-thread stores
   long long* dbg;      // optional timeline buffer (CTA 0 only): [role][event] clock64 stamps, see tools/timeline.py
 };
 
@@ -94,10 +93,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;
   const uint32_t stage_tx = a_bytes + b_bytes;                       // bytes TMA delivers per stage
   const uint32_t stage_bytes = (stage_tx + 1023u) & ~1023u;          // stage pitch keeps every tile on a swizzle period
-  const uint32_t bar_base = base + a.stages * stage_bytes;
+  const uint32_t ring_bytes = a.stages * stage_bytes < kOutStageBytes ? kOutStageBytes : a.stages * stage_bytes;
+  const uint32_t bar_base = base + ring_bytes;
   const uint32_t tmem_full_bar = bar_base + 16u * a.stages;
   const uint32_t tmem_slot = tmem_full_bar + 8u;
-  float* s_scale = reinterpret_cast<float*>(gbase + a.stages * stage_bytes + 256);
+  float* s_scale = reinterpret_cast<float*>(gbase + ring_bytes + 256);
   float* s_shift = s_scale + 256;
   float* s_floor = s_shift + 256;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -126,93 +126,176 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
+  // Role loops run warp-converged; one elected lane issues the TMA / MMA / commit instructions (under a plain
+  // `if (lane == 0)` the compiler wraps each of them in an ELECT + branch loop).
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      int bw = 0, bh = 0, bn = 0;
-      if (a.im2col) {
-        const int q = m0 % a.ow;
-        const int t = m0 / a.ow;
-        bw = q * a.stride - a.pad_w;
-        bh = (t % a.oh) * a.stride - a.pad_h;
-        bn = t / a.oh;
-      }
-      int tap = 0, cb = 0;
-      int s = 0;
-      uint32_t ph = 0;                       // stage index / phase kept incrementally: no division in the loop
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+    // ---------------- TMA producer ----------------
+    int bw = 0, bh = 0, bn = 0;
+    if (a.im2col) {
+      const int q = m0 % a.ow;
+      const int t = m0 / a.ow;
+      bw = q * a.stride - a.pad_w;
+      bh = (t % a.oh) * a.stride - a.pad_h;
+      bn = t / a.oh;
+    }
+    int tap = 0, cb = 0, tr = 0, ts = 0;
+    int s = 0;
+    uint32_t ph = 0;                       // stage index / phase kept incrementally: no division in the loop
+    for (int kb = 0; kb < num_kb; ++kb) {
+      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(full_bar(s), stage_tx);
         const uint32_t sa = base + s * stage_bytes;
         if (a.im2col) {
-          const int r = tap / a.kw;
-          ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(tap - r * a.kw),
-                                  static_cast<uint16_t>(r));
+          ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
+                                  static_cast<uint16_t>(tr));
         } else {
           ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
         }
         ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
-        if (++cb == a.cblocks) { cb = 0; ++tap; }
-        if (++s == a.stages) { s = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      if (++cb == a.cblocks) {
+        cb = 0; ++tap;
+        if (++ts == a.kw) { ts = 0; ++tr; }
+      }
+      if (++s == a.stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
-      const int ksteps = a.row_bytes / 32;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(full_bar(s), ph);
-        ptx::tc_fence_after();
-        const uint32_t sa = base + s * stage_bytes;
-        const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
-        const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
-        for (int k = 0; k < ksteps; ++k) {
-          // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
-          ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+    const int ksteps = a.row_bytes / 32;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      ptx::mbar_wait(full_bar(s), ph);
+      ptx::tc_fence_after();
+      const uint32_t sa = base + s * stage_bytes;
+      const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
+      const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
+      if (ptx::elect_one()) {
+        // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
+        if (ksteps == 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+        } else {
+          for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
         }
         ptx::umma_commit(empty_bar(s));      // smem slot free once these MMAs retire
-        if (++s == a.stages) { s = 0; ph ^= 1u; }
+        if (kb == num_kb - 1) ptx::umma_commit(tmem_full_bar);       // accumulator complete
       }
-      ptx::umma_commit(tmem_full_bar);       // accumulator complete
+      __syncwarp();
+      if (++s == a.stages) { s = 0; ph ^= 1u; }
     }
   } else {
     // ---------------- epilogue (warps 2..5) ----------------
+    // TMEM -> registers -> BN/ReLU -> 16-bit -> shared staging (a 128 x 64-column chunk; it aliases pipeline stage
+    // 0, idle once tmem_full has fired because this CTA owns a single tile) -> global with 8 consecutive lanes per
+    // pixel, so each warp store covers whole 128-byte lines instead of 32 different ones.
     const int et = threadIdx.x - 64;         // 0..127
     for (int i = et; i < a.n_tile; i += 128) {
       s_scale[i] = __ldg(a.scale + n_base + i);
       s_shift[i] = __ldg(a.shift + n_base + i);
       s_floor[i] = a.floor ? __ldg(a.floor + n_base + i) : (a.relu ? 0.f : -INFINITY);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
     const int quarter = warp & 3;            // TMEM lanes this warp may touch: [32q, 32q+32)
     const int row = quarter * 32 + lane;
-    const int m = m0 + row;
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(m) * a.ldo + a.coff + n_base;
-    uint16_t* orow2 = reinterpret_cast<uint16_t*>(a.out2) + static_cast<size_t>(m) * a.ldo2 + a.coff2 + n_base - a.n_split;
-    const bool valid = m < a.m_total;
-    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-      uint32_t v[16];
-      ptx::tmem_ld_32x32b_x16(taddr + c0, v);
-      ptx::tmem_ld_wait();
-      uint32_t p[8];
+    if (!a.epi_staged) {
+      // Row-per-thread stores straight from registers: no barriers, lowest latency for this one-tile-per-CTA kernel
+      // (MEASURED on conv3, 73x73 1x1 64->80: 0.031 ms against 0.050 ms for the staged variant below).
+      asm volatile("bar.sync 1, 128;" ::: "memory");                   // scale/shift visible
+      const int m = m0 + row;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(m) * a.ldo + a.coff + n_base;
+      uint16_t* orow2 = reinterpret_cast<uint16_t*>(a.out2) + static_cast<size_t>(m) * a.ldo2 + a.coff2 + n_base - a.n_split;
+      const bool valid = m < a.m_total;
+      for (int c0 = 0; c0 < a.n_tile; c0 += 64) {
+        const int cp = (a.n_tile - c0 >= 64) ? 4 : (a.n_tile - c0) / 16;
+        uint32_t v[4][16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float x0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0 + 2 * j], s_shift[c0 + 2 * j]);
-        float x1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 2 * j + 1], s_shift[c0 + 2 * j + 1]);
-        x0 = fmaxf(x0, s_floor[c0 + 2 * j]);
-        x1 = fmaxf(x1, s_floor[c0 + 2 * j + 1]);
-        p[j] = pack2(x0, x1, a.fmt);
+        for (int hh = 0; hh < 4; ++hh)
+          if (hh < cp) ptx::tmem_ld_32x32b_x16(taddr + c0 + hh * 16, v[hh]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          if (hh < cp) {
+            const int cc = c0 + hh * 16;
+            uint32_t q[8];
+            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cc);
+            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cc);
+            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + cc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 sc = sc4[i], sh = sh4[i], fl = fl4[i];
+              const float x0 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i]), sc.x, sh.x), fl.x);
+              const float x1 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 1]), sc.y, sh.y), fl.y);
+              const float x2 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 2]), sc.z, sh.z), fl.z);
+              const float x3 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 3]), sc.w, sh.w), fl.w);
+              q[2 * i] = pack2(x0, x1, a.fmt);
+              q[2 * i + 1] = pack2(x2, x3, a.fmt);
+            }
+            if (valid) {
+              uint4* dst = reinterpret_cast<uint4*>((n_base + cc < a.n_split ? orow : orow2) + cc);
+              dst[0] = make_uint4(q[0], q[1], q[2], q[3]);
+              dst[1] = make_uint4(q[4], q[5], q[6], q[7]);
+            }
+          }
+        }
       }
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>((n_base + c0 < a.n_split ? orow : orow2) + c0);
-        dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
-        dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+    } else {
+      uint8_t* stage_g = gbase;                // start of the (now idle) ring, at least kOutStageBytes long
+      const int cl = et & 7;                   // chunk lane of the copy-out: 8 lanes cover one pixel's 128 bytes
+      for (int c0 = 0; c0 < a.n_tile; c0 += 64) {
+        const int cw = (a.n_tile - c0 < 64) ? (a.n_tile - c0) : 64;     // multiple of 16
+        asm volatile("bar.sync 1, 128;" ::: "memory");                 // scale/shift visible; staging free
+        uint32_t v[4][16];
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh)
+          if (hh * 16 < cw) ptx::tmem_ld_32x32b_x16(taddr + c0 + hh * 16, v[hh]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          if (hh * 16 < cw) {
+            uint32_t q[8];
+            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0 + hh * 16);
+            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0 + hh * 16);
+            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + c0 + hh * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 sc = sc4[i], sh = sh4[i], fl = fl4[i];
+              const float x0 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i]), sc.x, sh.x), fl.x);
+              const float x1 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 1]), sc.y, sh.y), fl.y);
+              const float x2 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 2]), sc.z, sh.z), fl.z);
+              const float x3 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 3]), sc.w, sh.w), fl.w);
+              q[2 * i] = pack2(x0, x1, a.fmt);
+              q[2 * i + 1] = pack2(x2, x3, a.fmt);
+            }
+            const int ch = hh * 2;
+            *reinterpret_cast<uint4*>(stage_g + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(q[0], q[1], q[2], q[3]);
+            *reinterpret_cast<uint4*>(stage_g + row * 128 + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(q[4], q[5], q[6], q[7]);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (cl * 8 < cw) {
+          const int col = n_base + c0 + cl * 8;
+          uint16_t* dst_base = (col < a.n_split)
+                                   ? reinterpret_cast<uint16_t*>(a.out) + a.coff + col
+                                   : reinterpret_cast<uint16_t*>(a.out2) + a.coff2 + col - a.n_split;
+          const size_t ld = (col < a.n_split) ? a.ldo : a.ldo2;
+          uint4 val[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (et >> 3) + 16 * i;
+            val[i] = *reinterpret_cast<const uint4*>(stage_g + r * 128 + ((cl ^ (r & 7)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + (et >> 3) + 16 * i;
+            if (m < a.m_total) *reinterpret_cast<uint4*>(dst_base + static_cast<size_t>(m) * ld) = val[i];
+          }
+        }
       }
     }
   }
@@ -238,8 +321,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 //     (tcgen05.ld -> BN/ReLU -> stores) overlaps the MMAs of tile i+1,
 //   * barrier init, TMEM allocation and descriptor prefetch are paid once per SM, not once per tile.
 // ---------------------------------------------------------------------------------------------------
-template <bool kPair, bool kLsuB>
-__global__ void __launch_bounds__(kLsuB ? kPersistLsuThreads : kPersistThreads, 1)
+template <bool kPair>
+__global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                              const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                              const __grid_constant__ CUtensorMap tm_o64, const __grid_constant__ CUtensorMap tm_o64_2,
@@ -296,13 +379,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     ptx::prefetch_tmap(&tm_o64);
     ptx::prefetch_tmap(&tm_o64_2);
     for (int s = 0; s < a.stages; ++s) {
-      // arrivals per stage: the A producer + either the W producer thread (TMA) or the 128 LSU loader threads
-      ptx::mbar_init(full_bar(s), kLsuB ? 129 : 2);
+      ptx::mbar_init(full_bar(s), 2);          // arrivals per stage: the A producer and the W producer
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
-      ptx::mbar_init(tmem_empty(i), pair ? 256 : 128);   // every epilogue thread (of both CTAs) arrives
+      ptx::mbar_init(tmem_empty(i), pair ? 2 * kEpiThreads : kEpiThreads);   // every epilogue thread (of both CTAs) arrives
     }
     ptx::fence_mbar_init();
   }
@@ -370,11 +452,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       }
     }
   } else if (warp == 6) {
-    if (!kLsuB) {
+    {
       // ---------------- TMA producer #2: weight tiles ----------------
       // Issuing a TMA costs the issuing thread several hundred cycles; with one producer thread the A and W
-      // loads of a stage serialise (measured ~900 cycles per K block on every layer regardless of tile size),
-      // so the two operands get one issuing thread each.
+      // loads of a stage serialise, so the two operands get one issuing warp each.
       uint32_t it = 0;
       int s = 0;
       uint32_t ph = 0;
@@ -397,45 +478,6 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
       }
-    }
-  } else if (warp >= 7) {
-    if constexpr (kLsuB) {
-      // ---------------- LSU weight loaders (warps 7..10) ----------------
-      // MEASURED: the TMA unit retires about one <=128-byte box row per 2.7 cycles per SM, and with both operands
-      // on it every layer sits at ~870 cycles per K block (128 A rows + n_tile W rows) while the MMAs need 2*n_tile.
-      // The weight tile therefore comes in through the other path into shared memory: 128 threads x 16-byte
-      // cp.async (8 threads per 128-byte row, swizzle applied by hand), kLsuLag groups in flight per thread, then
-      // fence.proxy.async + a plain mbarrier arrive once a group has landed.
-      const int lt = static_cast<int>(threadIdx.x) - 224;          // 0..127
-      const int chunk = lt & 7;
-      const int row0 = lt >> 3;                                    // rows row0, row0+16, ...
-      const uint32_t dst_off = static_cast<uint32_t>(row0) * 128u + (static_cast<uint32_t>(chunk ^ (row0 & 7)) << 4);
-      const uint16_t* wsrc = static_cast<const uint16_t*>(a.w_gmem);
-      const int passes = a.n_tile / 16;
-      uint32_t it = 0;
-      for (int t = first; t < total_tiles; t += step) {
-        const int n_base = (t % n_tiles) * a.n_tile;
-        const uint16_t* src_t = wsrc + static_cast<size_t>(n_base + row0) * a.w_kp + chunk * 8;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % a.stages;
-          ptx::mbar_wait(empty_bar(s), ((it / a.stages) & 1) ^ 1u);
-          const uint32_t dst = base + s * stage_bytes + a_bytes + dst_off;
-          const uint16_t* src = src_t + kb * kBK;
-          for (int i = 0; i < passes; ++i)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 2048u),
-                         "l"(src + static_cast<size_t>(i) * 16 * a.w_kp)
-                         : "memory");
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          if (it >= kLsuLag) {
-            asm volatile("cp.async.wait_group %0;" ::"n"(kLsuLag) : "memory");
-            ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(full_bar((it - kLsuLag) % a.stages));
-          }
-        }
-      }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      ptx::fence_proxy_async_smem();
-      for (uint32_t j = (it > kLsuLag ? it - kLsuLag : 0u); j < it; ++j) ptx::mbar_arrive(full_bar(j % a.stages));
     }
   } else if (warp == 1) {
     if (leader || !pair) {
@@ -462,15 +504,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
               for (int k = 0; k < ksteps; ++k) ptx::umma_f16_2sm(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
               ptx::umma_commit_2sm(empty_bar(s), 3);       // frees stage s in both CTAs
             } else {
-              if (a.split_n) {
-                // two independent accumulation chains (left / right half of the N tile) interleaved
-                const uint32_t idesc_h = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile / 2);
-                const uint64_t db2 = ptx::make_smem_desc_rows(sa + a_bytes + (a.n_tile / 2) * rb, rb);
-                for (int k = 0; k < ksteps; ++k) {
-                  ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc_h, (kb | k) != 0);
-                  ptx::umma_f16(tacc + a.n_tile / 2, da + 2u * k, db2 + 2u * k, idesc_h, (kb | k) != 0);
-                }
-              } else if (ksteps == 4) {
+              if (ksteps == 4) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
               } else {
@@ -491,8 +525,14 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       }
     }
   } else {
-    // ---------------- epilogue (warps 2..5) ----------------
-    const int et = threadIdx.x - 64;
+    // ---------------- epilogue (warps 2..5 and 7..10) ----------------
+    // MEASURED (timeline, profiles/r01_epilogue.md): with four epilogue warps a 128 x 64 chunk cost ~1600 cycles —
+    // 512 of TMEM read (tcgen05.ld moves 64 B/cycle/SM) followed, serially, by ~900 cycles of convert/pack code
+    // issued by ONE warp per scheduler — so every short-K layer (35x35 1x1s, the stem) was epilogue-bound.  Now each
+    // TMEM lane quarter has two warps (w and w+5 share w & 3), each owning 32 of the chunk's 64 columns, and the
+    // loads of chunk i+1 are issued before the arithmetic of chunk i, so the chunk time approaches the TMEM floor.
+    const int grp = warp >= 7 ? 1 : 0;                 // column half of each 64-column chunk
+    const int et = grp ? static_cast<int>(threadIdx.x) - 224 + 128 : static_cast<int>(threadIdx.x) - 64;   // 0..255
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint32_t lt = 0;
@@ -500,14 +540,14 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     for (int t = first; t < total_tiles; t += step, ++lt) {
       const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
       const int n_base = (t % n_tiles) * a.n_tile;
-      if (n_base != loaded_n_base) {             // uniform across the 128 epilogue threads
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < a.n_tile; i += 128) {
+      if (n_base != loaded_n_base) {               // uniform across the epilogue threads
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < a.n_tile; i += kEpiThreads) {
           s_scale[i] = __ldg(a.scale + n_base + i);
           s_shift[i] = __ldg(a.shift + n_base + i);
           s_floor[i] = a.floor ? __ldg(a.floor + n_base + i) : (a.relu ? 0.f : -INFINITY);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         loaded_n_base = n_base;
       }
       const uint32_t as = lt & 1u;
@@ -516,30 +556,36 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       ptx::tc_fence_after();
       if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[4 * 512 + lt] = clock64();
       const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-      // The accumulator leaves through shared memory and TMA stores: each thread owns one output pixel (TMEM
-      // lane), converts 64 columns at a time, writes them as four [128 rows x 32 B] sub-boxes, and one thread
-      // stores the sub-boxes into the destination slice(s).  (Row-per-thread 16-byte global stores, the first
-      // version, cost 8.8k + 40*n_tile cycles per tile and bounded every layer.)  Rows past the last valid pixel
-      // land in the unused tail of the buffer or are clipped by the tensor map.
-      for (int c0 = 0; c0 < a.n_tile; c0 += 64) {
-        const int nsub = (a.n_tile - c0 >= 64) ? 4 : (a.n_tile - c0) / 16;
-        uint32_t v[64];
+
+      // 16-column pieces of the chunk at c0 owned by this thread: [first, first + np) of the chunk's cp (<= 4) pieces
+      auto geom = [&](int c0, int& cp, int& first, int& np) {
+        cp = (a.n_tile - c0) >> 4;
+        if (cp > 4) cp = 4;
+        const int h0 = (cp + 1) >> 1;
+        first = grp ? h0 : 0;
+        np = grp ? cp - h0 : h0;
+      };
+      auto issue = [&](uint32_t (&v)[32], int c0) {
+        int cp, first, np;
+        geom(c0, cp, first, np);
+        if (np > 0) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * first, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if (np > 1) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * first + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+      };
+      // The accumulator leaves through shared memory and TMA stores: each thread converts its 32 columns of one
+      // output pixel (TMEM lane), writes them into the 16 KiB staging buffer, and one thread stores the chunk into
+      // the destination slice(s).  Rows past the last valid pixel land in the unused tail of the buffer or are
+      // clipped by the tensor map.
+      auto process = [&](uint32_t (&v)[32], int c0) {
+        int chunk_pieces, first, np;
+        geom(c0, chunk_pieces, first, np);
+        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nsub) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
-        ptx::tmem_ld_wait();
-        if (c0 + 64 >= a.n_tile) {               // last TMEM read of this tile: hand the accumulator back early
-          ptx::tc_fence_before();
-          if constexpr (kPair) ptx::mbar_arrive_leader(tmem_empty(as));   // 2 x 128 arrivals on the leader's barrier
-          else ptx::mbar_arrive(tmem_empty(as));           // 128 arrivals release the accumulator to the MMA issuer
-        }
-        uint32_t pk[32];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < nsub) {
-            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0 + 16 * j);
-            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0 + 16 * j);
-            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + c0 + 16 * j);
+        for (int j = 0; j < 2; ++j) {
+          if (j < np) {
+            const int cc = c0 + 16 * (first + j);
+            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cc);
+            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cc);
+            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + cc);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 sc = sc4[q], sh = sh4[q], fl = fl4[q];
@@ -554,24 +600,25 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         }
         // staging buffer is free once the previous chunk's stores have read it
         if (et == 0) ptx::tma_store_wait_read();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         // A full 64-column chunk that lies in one destination goes out as ONE [128 rows x 128 B] box (128-byte
         // swizzled staging: conflict-free 16-byte writes, and a quarter of the box rows the TMA unit has to walk
         // compared with four 32-byte-row boxes); tails and chunks straddling n_split use 16-column boxes.
         const int col0 = n_base + c0;
-        const bool wide = (nsub == 4) && (col0 >= a.n_split || col0 + 64 <= a.n_split);
+        const bool wide = (chunk_pieces == 4) && (col0 >= a.n_split || col0 + 64 <= a.n_split);
         if (wide) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {            // 16-byte chunk q of this thread's 128-byte row
-            const uint32_t dst = out_stage + static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>(q ^ (row & 7)) << 4);
+          for (int q = 0; q < 4; ++q) {            // 16-byte chunk 4*grp+q of this thread's 128-byte row
+            const uint32_t dst = out_stage + static_cast<uint32_t>(row) * 128u +
+                                 (static_cast<uint32_t>((4 * grp + q) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
                          "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nsub) {
-              const uint32_t dst = out_stage + j * 4096u + static_cast<uint32_t>(row) * 32u;
+          for (int j = 0; j < 2; ++j) {
+            if (j < np) {
+              const uint32_t dst = out_stage + (first + j) * 4096u + static_cast<uint32_t>(row) * 32u;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[8 * j]), "r"(pk[8 * j + 1]),
                            "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]) : "memory");
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[8 * j + 4]),
@@ -580,13 +627,13 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           }
         }
         ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
           if (wide) {
             if (col0 < a.n_split) ptx::tma_store_2d(&tm_o64, out_stage, a.coff + col0, m0);
             else ptx::tma_store_2d(&tm_o64_2, out_stage, a.coff2 + col0 - a.n_split, m0);
           } else {
-            for (int j = 0; j < nsub; ++j) {
+            for (int j = 0; j < chunk_pieces; ++j) {
               const int col = col0 + 16 * j;
               if (col < a.n_split) ptx::tma_store_2d(&tm_o, out_stage + j * 4096u, a.coff + col, m0);
               else ptx::tma_store_2d(&tm_o2, out_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
@@ -594,6 +641,27 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           }
           ptx::tma_store_commit();
         }
+      };
+      auto release = [&]() {                       // last TMEM read of this tile has landed: hand the accumulator back
+        ptx::tc_fence_before();
+        if constexpr (kPair) ptx::mbar_arrive_leader(tmem_empty(as));
+        else ptx::mbar_arrive(tmem_empty(as));
+      };
+
+      uint32_t va[32], vb[32];
+      int c0 = 0;
+      issue(va, 0);
+      while (true) {
+        ptx::tmem_ld_wait();
+        if (c0 + 64 < a.n_tile) issue(vb, c0 + 64); else release();
+        process(va, c0);
+        c0 += 64;
+        if (c0 >= a.n_tile) break;
+        ptx::tmem_ld_wait();
+        if (c0 + 64 < a.n_tile) issue(va, c0 + 64); else release();
+        process(vb, c0);
+        c0 += 64;
+        if (c0 >= a.n_tile) break;
       }
       if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[5 * 512 + lt] = clock64();
     }
@@ -615,8 +683,9 @@ inline size_t conv_stage_bytes(int n_tile, int row_bytes) {
   return (static_cast<size_t>(kBM + n_tile) * row_bytes + 1023) & ~size_t(1023);
 }
 inline size_t conv_smem_bytes(int stages, int n_tile, int row_bytes, bool persistent = false) {
-  return 1024 + static_cast<size_t>(stages) * conv_stage_bytes(n_tile, row_bytes) + (persistent ? kOutStageBytes : 0) + 256 +
-         3072;
+  size_t ring = static_cast<size_t>(stages) * conv_stage_bytes(n_tile, row_bytes);
+  if (!persistent && ring < kOutStageBytes) ring = kOutStageBytes;   // the one-tile kernel stages its epilogue in the ring
+  return 1024 + ring + (persistent ? kOutStageBytes : 0) + 256 + 3072;
 }
 
 }  // namespace icp

@@ -521,8 +521,8 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.coff = out_coff;
   a.scale = d_scale;
   a.shift = d_shift;
-  static const bool split_n = getenv("ICP_SPLIT_N") != nullptr;
-  a.split_n = (split_n && n_tile % 32 == 0) ? 1 : 0;
+  static const bool v1_staged = getenv("ICP_V1_STAGED") != nullptr;
+  a.epi_staged = v1_staged ? 1 : 0;
   a.dbg = nullptr;
   a.w_gmem = d_w;
   a.w_kp = static_cast<int>(kp);
@@ -546,9 +546,8 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   }
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -576,12 +575,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     const int max_clusters = g_num_sms / cs;
     const int clusters = total < max_clusters ? total : max_clusters;
     if (cs == 1) {
-      // cp.async weight loaders: correct, measured slower than the TMA weight path (3.71 vs 3.22 ms/step) -> opt-in
-      static const bool lsu_b = getenv("ICP_LSU_B") && atoi(getenv("ICP_LSU_B")) != 0;
-      if (lsu_b && a.row_bytes == 128)
-        conv_igemm_persistent_kernel<false, true><<<clusters, kPersistLsuThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
-      else
-        conv_igemm_persistent_kernel<false, false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
+      conv_igemm_persistent_kernel<false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
       CK(cudaGetLastError());
       return;
     }
@@ -597,7 +591,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true, false>, L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles));
+    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true>, L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles));
   } else {
     dim3 grid(m_tiles, L.n_tiles);
     conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
@@ -1069,8 +1063,8 @@ static int run_op(const Op& op, int n, int fmt, cudaStream_t st) {
       launch_conv(op.conv, n, st);
       return 1;
     case Op::MAXPOOL: {
-      const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
-      maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      const unsigned per_image = static_cast<unsigned>(op.out.h) * ((op.out.w + 1) / 2) * (op.c / 8);
+      maxpool3s2_kernel<<<dim3((per_image + 255) / 256, n), 256, 0, st>>>(
           op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, 0, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff, fmt);
       CK(cudaGetLastError());
       return 1;
@@ -1627,18 +1621,20 @@ int icp_conv2d_bn_relu(int device, int precision, const float* x, int n, int h, 
                             relu != 0, out, 0, fmt);
     const char* tl_path = getenv("ICP_TIMELINE");
     long long* d_dbg = nullptr;
-    if (tl_path && L.persistent && !L.halo) {
-      d_dbg = static_cast<long long*>(pool.alloc(7 * 512 * 8));
-      CK(cudaMemsetAsync(d_dbg, 0, 7 * 512 * 8, st));
+    if (tl_path && (L.persistent || L.halo)) {
+      d_dbg = static_cast<long long*>(pool.alloc(10 * 512 * 8));
+      CK(cudaMemsetAsync(d_dbg, 0, 10 * 512 * 8, st));
       L.args.dbg = d_dbg;
+      L.hargs.dbg = d_dbg;
     }
     launch_conv(L, n, st);
     if (d_dbg) {
-      std::vector<long long> hd(7 * 512);
+      std::vector<long long> hd(10 * 512);
       CK(cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       if (FILE* f = fopen(tl_path, "wb")) { fwrite(hd.data(), 8, hd.size(), f); fclose(f); }
       L.args.dbg = nullptr;
+      L.hargs.dbg = nullptr;
     }
     h16_to_f32_kernel<<<static_cast<unsigned>((out_elems + 255) / 256), 256, 0, st>>>(out.p, d_yf,
                                                                                      static_cast<size_t>(n) * oh * ow,
@@ -1687,7 +1683,7 @@ int icp_pool2d(int device, int precision, int kind, const float* x, int n, int h
     f32_to_h16_kernel<<<static_cast<unsigned>((in_elems + 255) / 256), 256>>>(d_xf, d_x, in_elems, fmt);
     const long long total = static_cast<long long>(n) * oh * ow * (c / 8);
     if (kind == 0)
-      maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_x, n, h, w, c, c, 0, d_y, oh, ow, c, 0,
+      maxpool3s2_kernel<<<dim3((static_cast<unsigned>(oh) * ((ow + 1) / 2) * (c / 8) + 255) / 256, n), 256>>>(d_x, n, h, w, c, c, 0, d_y, oh, ow, c, 0,
                                                                              fmt);
     else
       avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(d_x, n, h, w, c, c, 0, d_y, oh, ow, c, 0, k,

@@ -130,34 +130,55 @@ conv0_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_const
 
 // ---------------------------------------------------------------------------------------------
 // max_pool 3x3 / stride 2 / VALID (ops.py:367-370).  Output may be a channel slice of a concat
-// buffer (ldo/coff).  One thread = one output pixel x 8 channels.
+// buffer (ldo/coff).  One thread = TWO horizontally adjacent output pixels x 8 channels: the two windows share a
+// column, so 15 16-byte loads feed two outputs; max is exact in the storage type, so it runs as packed 16-bit
+// HMNMX2 without widening.  blockIdx.y = image, all index arithmetic 32-bit.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t max2_h16(uint32_t a, uint32_t b, int fmt) {
+  if (fmt) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 max8_h16(const uint4& a, const uint4& b, int fmt) {
+  return make_uint4(max2_h16(a.x, b.x, fmt), max2_h16(a.y, b.y, fmt), max2_h16(a.z, b.z, fmt), max2_h16(a.w, b.w, fmt));
+}
 __global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
                                   uint16_t* __restrict__ out, int OH, int OW, int ldo, int coff, int fmt) {
-  const int cg = C / 8;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * OH * OW * cg;
-  if (idx >= total) return;
-  const int g = static_cast<int>(idx % cg);
-  const long long pix = idx / cg;
-  const int ox = static_cast<int>(pix % OW);
-  const int oy = static_cast<int>((pix / OW) % OH);
-  const int n = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
-  float m[8];
+  const unsigned cg = static_cast<unsigned>(C) >> 3;
+  const unsigned pairs = (static_cast<unsigned>(OW) + 1u) >> 1;
+  const unsigned per_image = static_cast<unsigned>(OH) * pairs * cg;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_image) return;
+  const unsigned n = blockIdx.y;
+  const unsigned g = idx % cg;
+  const unsigned t = idx / cg;
+  const unsigned px = t % pairs;
+  const unsigned oy = t / pairs;
+  const unsigned ox = px * 2u;
+  const bool second = ox + 1u < static_cast<unsigned>(OW);
+  const uint16_t* base = in + ((static_cast<size_t>(n) * H + oy * 2u) * W + ox * 2u) * ldi + cin_off + g * 8u;
+  uint4 m0, m1;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const size_t off = ((static_cast<size_t>(n) * H + oy * 2 + r) * W + ox * 2 + s) * ldi + cin_off + g * 8;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + off));
-      float f[8];
-      unpack8(v, f, fmt);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+  for (int r = 0; r < 3; ++r) {
+    const uint16_t* row = base + static_cast<size_t>(r) * W * ldi;
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(row));
+    const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(row + ldi));
+    const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(row + 2 * ldi));
+    uint4 a = max8_h16(max8_h16(v0, v1, fmt), v2, fmt);
+    m0 = r ? max8_h16(m0, a, fmt) : a;
+    if (second) {
+      const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(row + 3 * ldi));
+      const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(row + 4 * ldi));
+      uint4 b = max8_h16(max8_h16(v2, v3, fmt), v4, fmt);
+      m1 = r ? max8_h16(m1, b, fmt) : b;
     }
-  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + coff + g * 8) = pack8(m, fmt);
+  }
+  uint16_t* o = out + ((static_cast<size_t>(n) * OH + oy) * OW + ox) * ldo + coff + g * 8u;
+  *reinterpret_cast<uint4*>(o) = m0;
+  if (second) *reinterpret_cast<uint4*>(o + ldo) = m1;
 }
 
 // ---------------------------------------------------------------------------------------------

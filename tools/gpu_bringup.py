@@ -263,6 +263,11 @@ LAYERS = {
     "c17_1x1_768_704": (17, 17, 768, 1, 1, 704, 1, True),
     "c35_3x3_96": (35, 35, 96, 3, 3, 96, 1, True),
     "c8_3x3_448": (8, 8, 448, 3, 3, 384, 1, True),
+    "conv1": (149, 149, 32, 3, 3, 32, 1, False),
+    "conv2": (147, 147, 32, 3, 3, 64, 1, True),
+    "conv3": (73, 73, 64, 1, 1, 80, 1, False),
+    "c35_5x5_48_64": (35, 35, 48, 5, 5, 64, 1, True),
+    "c35_3x3_64_96": (35, 35, 64, 3, 3, 96, 1, True),
     # synthetic shapes that isolate the main loop (many full waves of tiles, long K)
     "gemm_k1024_n256": (64, 64, 1024, 1, 1, 256, 1, True),
     "gemm_k1024_n128": (64, 64, 1024, 1, 1, 128, 1, True),

@@ -4,7 +4,7 @@ rows: 0 A-producer passed empty wait, 1 W-producer passed empty wait, 2 MMA saw 
 4 epilogue saw tmem_full, 5 epilogue done, 6 epilogue started waiting."""
 import sys
 import numpy as np
-d = np.fromfile(sys.argv[1], dtype=np.int64).reshape(7, 512)
+d = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, 512)
 num_kb = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 t0 = d[d > 0].min()
 r = np.where(d > 0, d - t0, -1)
@@ -21,3 +21,9 @@ print("load latency (A issue -> MMA sees full): median %d" % np.median(r[2, :n] 
 nt = int((r[4] >= 0).sum())
 for t in range(min(nt, 12)):
     print("tile %2d: epi wait-start %8d  got full %8d  done %8d  (epilogue %d cycles)" % (t, r[6, t], r[4, t], r[5, t], r[5, t] - r[4, t]))
+
+if r.shape[0] >= 10 and (r[7] >= 0).any():
+    ns = int((r[7] >= 0).sum())
+    print("halo epilogue sub-tiles (rows 7/8/9: TMEM read done, staging written+barrier, copy-out issued):")
+    for q in range(min(ns, 24)):
+        print("  sub %3d: tmem %8d  staged %8d (+%d)  stored %8d (+%d)" % (q, r[7, q], r[8, q], r[8, q] - r[7, q], r[9, q], r[9, q] - r[8, q]))
