@@ -58,14 +58,12 @@ struct HaloArgs {
   int relu;
   void* out;
   int ldo, coff;
-  const float* scale;
-  const float* shift;
   long long* dbg;       // optional timeline buffer (CTA 0 only), same rows as the persistent kernel (tools/timeline.py)
 };
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const HaloArgs a) {
+                 const __grid_constant__ CUtensorMap tm_bias, const HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -86,11 +84,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   auto b_full = [&](int i) { return bar_base + 104u + 8u * i; };
   auto b_empty = [&](int i) { return bar_base + 168u + 8u * i; };
   const uint32_t tmem_slot = bar_base + 232u;
-  float* s_scale = reinterpret_cast<float*>(gbase + (bar_base - base) + 256);
-  float* s_shift = s_scale + 256;
-  uint32_t* tap_off = reinterpret_cast<uint32_t*>(s_shift + 256);    // [taps] A shift of tap (r,s), 16-B units
+  uint32_t* tap_off = reinterpret_cast<uint32_t*>(gbase + (bar_base - base) + 256);   // [taps] A shift of tap (r,s), 16-B units
   int* s_pix = reinterpret_cast<int*>(tap_off + 64);                 // [128] output pixel of each sub-tile row, -1 = none
-  const uint32_t stage_base = bar_base + 256u + 2048u + 256u + 512u; // epilogue staging: 128 rows x 128 B
+  const uint32_t stage_base = bar_base + 1024u;                      // epilogue staging: 128 rows x 128 B
+  const uint32_t ones_base = stage_base + 16384u;                    // constant A tile of the bias MMA (conv_igemm.cuh)
+  const uint32_t bias_base = ones_base + kOnesBytes;                 // resident weights: the [n_tile x 16] shift tile
 
   const int taps = a.kh * a.kw;
   const int ck = a.row_bytes / 2;
@@ -105,6 +103,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
+    ptx::prefetch_tmap(&tm_bias);
     for (int i = 0; i < a.nstrips; ++i) {
       ptx::mbar_init(strip_full(i), 1);
       ptx::mbar_init(strip_empty(i), 1);
@@ -123,6 +122,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, a.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (warp >= 2 && warp <= 5) {
+    write_ones_row(gbase + (ones_base - base), static_cast<int>(threadIdx.x) - 64, a.fmt);
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -158,7 +161,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ---------------- weight producer ----------------
     if (a.w_resident) {
       if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes);
+        ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes + static_cast<uint32_t>(a.n_tile) * 32u);
+        ptx::tma_load_2d(bias_base, &tm_bias, w_full, 0, 0);
         for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
       }
       __syncwarp();
@@ -170,11 +174,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int n_base = n_idx * a.n_tile;
         n_idx += n_step;
         if (n_idx >= a.n_tiles) n_idx -= a.n_tiles;
-        for (int i = 0; i < a.chunks * taps; ++i) {
+        for (int i = -1; i < a.chunks * taps; ++i) {       // i = -1: the shift tile of the bias MMA
           ptx::mbar_wait(b_empty(sb), phb ^ 1u);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(b_full(sb), tap_bytes);
-            ptx::tma_load_2d(wbase + sb * b_stride, &tm_b, b_full(sb), i * ck, n_base);
+            if (i < 0) {
+              ptx::mbar_expect_tx(b_full(sb), static_cast<uint32_t>(a.n_tile) * 32u);
+              ptx::tma_load_2d(wbase + sb * b_stride, &tm_bias, b_full(sb), 0, n_base);
+            } else {
+              ptx::mbar_expect_tx(b_full(sb), tap_bytes);
+              ptx::tma_load_2d(wbase + sb * b_stride, &tm_b, b_full(sb), i * ck, n_base);
+            }
           }
           __syncwarp();
           if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
@@ -187,6 +196,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
     const int ksteps = a.row_bytes / 32;
     const uint64_t desc_hi = ptx::make_smem_desc_rows(0, rb);          // everything but the address
+    const uint64_t desc32 = ptx::make_smem_desc_rows(0, 32);
+    const uint64_t d_ones = desc32 | (ones_base >> 4);
     for (int tap = lane; tap < taps; tap += 32) {
       const int r = tap / a.kw;
       tap_off[tap] = (static_cast<uint32_t>(r * a.wp + (tap - r * a.kw)) * rb) >> 4;
@@ -208,6 +219,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       ptx::mbar_wait(tmem_empty(as), pha ^ 1u);
       ptx::tc_fence_after();
       const uint32_t tacc0 = tmem_base + as * a.acc_cols;
+      // every sub-tile's accumulator starts at the BatchNorm shift: ones tile x (hi, lo) shift tile, K = 16
+      if (a.w_resident) {
+        if (ptx::elect_one())
+          for (int j = 0; j < nsub; ++j) ptx::umma_f16(tacc0 + j * a.n_tile, d_ones, desc32 | (bias_base >> 4), idesc, 0u);
+        __syncwarp();
+      } else {
+        ptx::mbar_wait(b_full(sb), phb);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          for (int j = 0; j < nsub; ++j)
+            ptx::umma_f16(tacc0 + j * a.n_tile, d_ones, desc32 | ((wbase + sb * b_stride) >> 4), idesc, 0u);
+          ptx::umma_commit(b_empty(sb));
+        }
+        __syncwarp();
+        if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
+      }
       for (int c = 0; c < a.chunks; ++c) {
         ptx::mbar_wait(strip_full(s), ph);
         ptx::tc_fence_after();
@@ -219,13 +246,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
               uint32_t au = a_units0 + tap_off[tap];
               uint32_t tacc = tacc0;
-              const uint32_t acc = static_cast<uint32_t>(c | tap);
               for (int j = 0; j < nsub; ++j, au += sub_units, tacc += a.n_tile) {
                 if (ksteps == 2) {
-                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
                 } else {
-                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 4u), desc_hi | (b_units + 4u), idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 6u), desc_hi | (b_units + 6u), idesc, 1u);
@@ -243,13 +269,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               const uint32_t b_units = (wbase + sb * b_stride) >> 4;
               uint32_t au = a_units0 + tap_off[tap];
               uint32_t tacc = tacc0;
-              const uint32_t acc = static_cast<uint32_t>(c | tap);
               for (int j = 0; j < nsub; ++j, au += sub_units, tacc += a.n_tile) {
                 if (ksteps == 2) {
-                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
                 } else {
-                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, acc);
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 4u), desc_hi | (b_units + 4u), idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 6u), desc_hi | (b_units + 6u), idesc, 1u);
@@ -282,7 +307,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint32_t as = 0, pha = 0;
-    int loaded_n_base = -1;
     int lt = 0;
     uint8_t* stage_g = gbase + (stage_base - base);
     const int cl = et & 7;                     // chunk lane of the copy-out: 8 lanes cover one pixel's 128 bytes
@@ -292,15 +316,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int n_base = (item - band * a.n_tiles) * a.n_tile;
       const int img = a.tall ? 0 : band / bands_per_image;
       const int p0 = (band - img * bands_per_image) * kBM * a.T;
-      if (n_base != loaded_n_base) {             // uniform across the epilogue threads
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = et; i < a.n_tile; i += 256) {
-          s_scale[i] = __ldg(a.scale + n_base + i);
-          s_shift[i] = __ldg(a.shift + n_base + i);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        loaded_n_base = n_base;
-      }
       int nsub = (positions - p0 + kBM - 1) / kBM;
       if (nsub > a.T) nsub = a.T;
       if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[6 * 512 + lt] = clock64();
@@ -324,9 +339,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (np > 0) ptx::tmem_ld_32x32b_x16(t0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         if (np > 1) ptx::tmem_ld_32x32b_x16(t0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
       };
-      auto process = [&](uint32_t (&v)[32], int j, int c0) {
+      auto process = [&](uint32_t (&v)[32], uint32_t (&vn)[32], int j, int c0, bool more, int nj, int nc) {
         int cp, first, np;
         geom(c0, cp, first, np);
+        if (more) issue(vn, nj, nc);
         int pix = -1;
         if (c0 == 0 && grp == 0) {               // one thread per row maps the sub-tile's positions to output pixels
           const int p = p0 + j * kBM + row;
@@ -339,24 +355,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         uint32_t q[16];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          if (jj < np) {
-            const int cc = c0 + 16 * (first + jj);
-            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cc);
-            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 sc = sc4[i], sh = sh4[i];
-              float x0 = fmaf(__uint_as_float(v[16 * jj + 4 * i]), sc.x, sh.x);
-              float x1 = fmaf(__uint_as_float(v[16 * jj + 4 * i + 1]), sc.y, sh.y);
-              float x2 = fmaf(__uint_as_float(v[16 * jj + 4 * i + 2]), sc.z, sh.z);
-              float x3 = fmaf(__uint_as_float(v[16 * jj + 4 * i + 3]), sc.w, sh.w);
-              if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-              q[8 * jj + 2 * i] = pack2(x0, x1, a.fmt);
-              q[8 * jj + 2 * i + 1] = pack2(x2, x3, a.fmt);
-            }
-          }
-        }
+        for (int jj = 0; jj < 2; ++jj)
+          if (jj < np) convert16(&v[16 * jj], &q[8 * jj], a.relu != 0, a.fmt);
         asm volatile("bar.sync 1, 256;" ::: "memory");                 // staging free (previous copy-out finished)
         if (c0 == 0 && grp == 0) s_pix[row] = pix;
 #pragma unroll
@@ -401,16 +401,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (nc >= a.n_tile) { nc = 0; ++nj; }
         ptx::tmem_ld_wait();
         if (a.dbg && blockIdx.x == 0 && et == 0 && c0 == 0 && lt * a.T + j < 512) a.dbg[7 * 512 + lt * a.T + j] = clock64();
-        if (nj < nsub) issue(vb, nj, nc); else release();
-        process(va, j, c0);
+        if (nj >= nsub) release();
+        process(va, vb, j, c0, nj < nsub, nj, nc);
         if (nj >= nsub) break;
         j = nj; c0 = nc;
         nc = c0 + 64;
         if (nc >= a.n_tile) { nc = 0; ++nj; }
         ptx::tmem_ld_wait();
         if (a.dbg && blockIdx.x == 0 && et == 0 && c0 == 0 && lt * a.T + j < 512) a.dbg[7 * 512 + lt * a.T + j] = clock64();
-        if (nj < nsub) issue(va, nj, nc); else release();
-        process(vb, j, c0);
+        if (nj >= nsub) release();
+        process(vb, va, j, c0, nj < nsub, nj, nc);
         if (nj >= nsub) break;
         j = nj; c0 = nc;
       }
@@ -429,8 +429,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 }
 
 inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes) {
-  return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 256 +
-         2048 + 256 + 512 + 16384;   // barriers, scale/shift, per-tap offset table, row->pixel table, epilogue staging
+  return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 1024 +
+         16384 + kOnesBytes + 8192;   // barriers + per-tap offsets + row->pixel table, epilogue staging, ones tile, shift tile
 }
 
 }  // namespace icp

@@ -1,6 +1,6 @@
 // Implicit-GEMM convolution + BatchNorm(scale/shift) + ReLU for sm_100a.
 //
-//   D[M = n*oh*ow, N = cout]  =  sum over (tap r,s ; channel block)  A_tap[M, 64] * W[N, 64]^T
+//   D[M = n*oh*ow, N = cout]  =  shift[N]  +  sum over (tap r,s ; channel block)  A_tap[M, 64] * (scale * W)[N, 64]^T
 //
 // Restates ops.conv2d (/root/reference/inception/slim/ops.py:229-245): tf.nn.conv2d (NHWC x HWIO,
 // no bias) -> batch_norm inference branch (ops.py:122-128, folded to y = x*scale + shift) -> relu.
@@ -9,13 +9,20 @@
 //   im2col mode straight from the NHWC activation tensor: no im2col buffer exists in HBM, SAME padding
 //   and ragged channel counts are the unit's out-of-bounds zero fill.  1x1/stride-1 layers use the
 //   plain 2-D tiled mode on the [pixels, channels] view.
-// * W tiles ([n_tile x 64] of the packed K-major weight matrix) come in by 2-D tiled TMA.
+// * W tiles ([n_tile x 64] of the packed K-major weight matrix, BatchNorm scale already multiplied in on the
+//   host) come in by 2-D tiled TMA.
 // * Both land in shared memory with the 128-byte swizzle and feed tcgen05.mma (kind::f16, M=128,
-//   N=n_tile<=256, K=16) issued by one thread; the fp32 accumulator lives in TMEM.
-// * 4 epilogue warps pull the accumulator with tcgen05.ld, apply scale/shift/ReLU in fp32, convert to
-//   bf16/fp16 and store directly into the channel slice of the (possibly concatenated) NHWC output —
-//   tf.concat (inception_model.py:125...) never runs as a kernel.
-// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+//   N=n_tile<=256, K=16) issued by one elected lane; the fp32 accumulator lives in TMEM.
+// * The BatchNorm shift enters through the tensor core as well: every tile starts with ONE K=16 MMA of a
+//   constant [128 x 16] tile whose first two K columns are 1 against a [n_tile x 16] tile holding
+//   (hi, lo) 16-bit halves of shift — so the accumulator already is conv*scale + shift and the epilogue is
+//   ReLU + convert only.  MEASURED (profiles/r01_epilogue.md): with per-column scale/shift/floor vectors read
+//   from shared memory by every lane, each 128 x 64 chunk cost 768 cycles of shared-memory bandwidth (24
+//   LDS.128 per thread), more than its TMEM read (512), and the shared-memory pipe is the same one the MMA
+//   operands come through: every short-K layer was epilogue-bound.
+// * Epilogue warps pull the accumulator with tcgen05.ld, ReLU, convert to bf16/fp16 and store into the channel
+//   slice of the (possibly concatenated) NHWC output — tf.concat (inception_model.py:125...) never runs as
+//   a kernel.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -27,10 +34,11 @@ namespace icp {
 constexpr int kBM = 128;                    // output pixels per CTA tile (UMMA M)
 constexpr int kBK = 64;                     // K elements per pipeline stage (one 128-B swizzle row)
 constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;           // one-tile kernel: warps 0 TMA, 1 MMA, 2..5 epilogue
 constexpr int kPersistThreads = 352;        // warps 0/6 TMA producers, 1 MMA issuer, 2..5 and 7..10 epilogue
 constexpr int kEpiThreads = 256;            // two epilogue warps per TMEM lane quarter (one per half of a 64-column chunk)
-constexpr uint32_t kOutStageBytes = 16384;  // epilogue staging (persistent kernel)
+constexpr uint32_t kOutStageBytes = 16384;  // epilogue staging
+constexpr uint32_t kOnesBytes = 4096;       // [128 x 16] 16-bit "ones" A tile of the bias MMA (32-byte rows, SWIZZLE_32B)
 constexpr int kMaxStages = 12;
 
 struct ConvArgs {
@@ -41,29 +49,24 @@ struct ConvArgs {
   int kw;          // filter width (S)
   int taps;        // R * S
   int cblocks;     // ceil(cin / ck), ck = row_bytes / 2 channels per K block
-  int row_bytes;   // bytes per operand row in smem: 32 / 64 / 128 (SWIZZLE_32B/64B/128B), chosen per layer so that
-                   // Cin = 48 / 80 / 96 / 160 pad to (almost) nothing instead of to a multiple of 64
+  int row_bytes;   // bytes per operand row in smem: 32 / 64 / 128 (SWIZZLE_32B/64B/128B)
   int n_tile;      // output channels per CTA, multiple of 16, <= 256
   int tmem_cols;   // power of two >= max(32, n_tile)
   int stages;
   int im2col;      // 1: A via im2col TMA, 0: A via 2-D tiled TMA
   int fmt;         // 0 fp16, 1 bf16
-  int relu;
   void* out;       // NHWC output buffer (16-bit elements)
   int ldo;         // channels in the output buffer (concat width)
   int coff;        // first channel this layer owns in the output buffer
-  const float* scale;  // [cout] rsqrt(var + eps)
-  const float* shift;  // [cout] beta - mean * scale
   // Horizontally fused sibling 1x1 convs (one GEMM over the concatenated output channels):
-  // columns >= n_split go to a second buffer (out2/ldo2/coff2); `floor` (nullable) is a per-channel
-  // activation floor — 0 for ReLU channels, -inf for channels that stay linear (pool-after-projection).
+  // columns >= n_split go to a second buffer (out2/ldo2/coff2).
   void* out2;
   int ldo2;
   int coff2;
   int n_split;         // multiple of 16; >= cout when there is no second destination
-  const float* floor;
-  const void* w_gmem;  // packed K-major weights [cout][w_kp] (LSU weight path)
-  int w_kp;
+  // ReLU applies to output columns [relu_lo, relu_hi) (multiples of 16); the rest stay linear
+  // (pool-after-projection: BatchNorm shift + ReLU of those channels run after the pool).
+  int relu_lo, relu_hi;
   int epi_staged;      // one-tile kernel: 1 = epilogue through shared staging + coalesced stores, 0 = row-per-thread stores
   long long* dbg;      // optional timeline buffer (CTA 0 only): [role][event] clock64 stamps, see tools/timeline.py
 };
@@ -77,9 +80,47 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 16 fp32 accumulator values -> 8 packed 16-bit pairs, optional ReLU (packed max against +0 after the conversion:
+// half the instructions of an fp32 max per element, same result).
+__device__ __forceinline__ void convert16(const uint32_t* v, uint32_t* q, bool relu, int fmt) {
+  if (fmt) {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      if (relu) h = __hmax2(h, z);
+      q[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  } else {
+    const __half2 z = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __half2 h = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      if (relu) h = __hmax2(h, z);
+      q[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+}
+
+// The constant A tile of the bias MMA: row r = (1, 1, 0, ..., 0) as 16 x 16-bit, 32-byte rows in the SWIZZLE_32B
+// layout (16-byte chunk index XOR address bit 7, i.e. XOR bit 2 of the row).  Written by 128 threads (r = 0..127)
+// with generic stores; the caller fences to the async proxy before the tensor core reads it.
+__device__ __forceinline__ void write_ones_row(uint8_t* ones, int r, int fmt) {
+  const uint32_t one = fmt ? 0x3F80u : 0x3C00u;
+  const int sw = (r >> 2) & 1;
+  *reinterpret_cast<uint4*>(ones + r * 32 + ((0 ^ sw) << 4)) = make_uint4(one | (one << 16), 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(ones + r * 32 + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One tile per CTA (used for narrow layers, n_tile < 128, where two or three short-lived CTAs per SM overlap
+// each other's prologue/epilogue better than one persistent CTA).
+// Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.  K blocks: block -1 is the bias
+// block (only the [n_tile x 16] shift tile travels, into the stage's W slot), blocks 0..num_kb-1 the filter.
+// ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kConvThreads)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                  const ConvArgs a) {
+                  const __grid_constant__ CUtensorMap tm_bias, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-B alignment
@@ -94,12 +135,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const uint32_t stage_tx = a_bytes + b_bytes;                       // bytes TMA delivers per stage
   const uint32_t stage_bytes = (stage_tx + 1023u) & ~1023u;          // stage pitch keeps every tile on a swizzle period
   const uint32_t ring_bytes = a.stages * stage_bytes < kOutStageBytes ? kOutStageBytes : a.stages * stage_bytes;
-  const uint32_t bar_base = base + ring_bytes;
+  const uint32_t ones_base = base + ring_bytes;
+  const uint32_t bar_base = ones_base + kOnesBytes;
   const uint32_t tmem_full_bar = bar_base + 16u * a.stages;
   const uint32_t tmem_slot = tmem_full_bar + 8u;
-  float* s_scale = reinterpret_cast<float*>(gbase + ring_bytes + 256);
-  float* s_shift = s_scale + 256;
-  float* s_floor = s_shift + 256;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
 
@@ -110,6 +149,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
+    ptx::prefetch_tmap(&tm_bias);
     for (int s = 0; s < a.stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
@@ -120,6 +160,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, a.tmem_cols);
     ptx::tmem_relinquish();
+  }
+  if (warp >= 2) {
+    write_ones_row(gbase + (ones_base - base), static_cast<int>(threadIdx.x) - 64, a.fmt);
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -138,25 +182,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       bh = (t % a.oh) * a.stride - a.pad_h;
       bn = t / a.oh;
     }
-    int tap = 0, cb = 0, tr = 0, ts = 0;
+    int cb = 0, tr = 0, ts = 0;
     int s = 0;
     uint32_t ph = 0;                       // stage index / phase kept incrementally: no division in the loop
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = -1; kb < num_kb; ++kb) {
       ptx::mbar_wait(empty_bar(s), ph ^ 1u);
       if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(full_bar(s), stage_tx);
         const uint32_t sa = base + s * stage_bytes;
-        if (a.im2col) {
-          ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
-                                  static_cast<uint16_t>(tr));
+        if (kb < 0) {                        // bias block: only the shift tile travels
+          ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
+          ptx::tma_load_2d(sa + a_bytes, &tm_bias, full_bar(s), 0, n_base);
         } else {
-          ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
+          ptx::mbar_expect_tx(full_bar(s), stage_tx);
+          if (a.im2col) {
+            ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
+                                    static_cast<uint16_t>(tr));
+          } else {
+            ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
+          }
+          ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
         }
-        ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
       }
       __syncwarp();
-      if (++cb == a.cblocks) {
-        cb = 0; ++tap;
+      if (kb >= 0 && ++cb == a.cblocks) {
+        cb = 0;
         if (++ts == a.kw) { ts = 0; ++tr; }
       }
       if (++s == a.stages) { s = 0; ph ^= 1u; }
@@ -167,19 +216,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int ksteps = a.row_bytes / 32;
     int s = 0;
     uint32_t ph = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = -1; kb < num_kb; ++kb) {
       ptx::mbar_wait(full_bar(s), ph);
       ptx::tc_fence_after();
       const uint32_t sa = base + s * stage_bytes;
-      const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
-      const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
       if (ptx::elect_one()) {
-        // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
-        if (ksteps == 4) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+        if (kb < 0) {
+          // accumulator := shift (hi + lo halves) broadcast down the 128 rows
+          ptx::umma_f16(tmem_base, ptx::make_smem_desc_rows(ones_base, 32), ptx::make_smem_desc_rows(sa + a_bytes, 32),
+                        idesc, 0u);
         } else {
-          for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+          const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
+          const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
+          // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
+          } else {
+            for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
+          }
         }
         ptx::umma_commit(empty_bar(s));      // smem slot free once these MMAs retire
         if (kb == num_kb - 1) ptx::umma_commit(tmem_full_bar);       // accumulator complete
@@ -189,15 +244,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else {
     // ---------------- epilogue (warps 2..5) ----------------
-    // TMEM -> registers -> BN/ReLU -> 16-bit -> shared staging (a 128 x 64-column chunk; it aliases pipeline stage
-    // 0, idle once tmem_full has fired because this CTA owns a single tile) -> global with 8 consecutive lanes per
-    // pixel, so each warp store covers whole 128-byte lines instead of 32 different ones.
     const int et = threadIdx.x - 64;         // 0..127
-    for (int i = et; i < a.n_tile; i += 128) {
-      s_scale[i] = __ldg(a.scale + n_base + i);
-      s_shift[i] = __ldg(a.shift + n_base + i);
-      s_floor[i] = a.floor ? __ldg(a.floor + n_base + i) : (a.relu ? 0.f : -INFINITY);
-    }
     const int quarter = warp & 3;            // TMEM lanes this warp may touch: [32q, 32q+32)
     const int row = quarter * 32 + lane;
     ptx::mbar_wait(tmem_full_bar, 0);
@@ -206,7 +253,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (!a.epi_staged) {
       // Row-per-thread stores straight from registers: no barriers, lowest latency for this one-tile-per-CTA kernel
       // (MEASURED on conv3, 73x73 1x1 64->80: 0.031 ms against 0.050 ms for the staged variant below).
-      asm volatile("bar.sync 1, 128;" ::: "memory");                   // scale/shift visible
       const int m = m0 + row;
       uint16_t* orow = reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(m) * a.ldo + a.coff + n_base;
       uint16_t* orow2 = reinterpret_cast<uint16_t*>(a.out2) + static_cast<size_t>(m) * a.ldo2 + a.coff2 + n_base - a.n_split;
@@ -221,23 +267,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {
           if (hh < cp) {
-            const int cc = c0 + hh * 16;
+            const int col = n_base + c0 + hh * 16;
             uint32_t q[8];
-            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cc);
-            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cc);
-            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + cc);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 sc = sc4[i], sh = sh4[i], fl = fl4[i];
-              const float x0 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i]), sc.x, sh.x), fl.x);
-              const float x1 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 1]), sc.y, sh.y), fl.y);
-              const float x2 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 2]), sc.z, sh.z), fl.z);
-              const float x3 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 3]), sc.w, sh.w), fl.w);
-              q[2 * i] = pack2(x0, x1, a.fmt);
-              q[2 * i + 1] = pack2(x2, x3, a.fmt);
-            }
+            convert16(v[hh], q, col >= a.relu_lo && col < a.relu_hi, a.fmt);
             if (valid) {
-              uint4* dst = reinterpret_cast<uint4*>((n_base + cc < a.n_split ? orow : orow2) + cc);
+              uint4* dst = reinterpret_cast<uint4*>((col < a.n_split ? orow : orow2) + c0 + hh * 16);
               dst[0] = make_uint4(q[0], q[1], q[2], q[3]);
               dst[1] = make_uint4(q[4], q[5], q[6], q[7]);
             }
@@ -245,40 +279,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
       }
     } else {
+      // TMEM -> registers -> ReLU -> 16-bit -> shared staging (a 128 x 64-column chunk; it aliases the pipeline
+      // ring, idle once tmem_full has fired because this CTA owns a single tile) -> global with 8 consecutive lanes
+      // per pixel, so each warp store covers whole 128-byte lines instead of 32 different ones.
       uint8_t* stage_g = gbase;                // start of the (now idle) ring, at least kOutStageBytes long
       const int cl = et & 7;                   // chunk lane of the copy-out: 8 lanes cover one pixel's 128 bytes
       for (int c0 = 0; c0 < a.n_tile; c0 += 64) {
-        const int cw = (a.n_tile - c0 < 64) ? (a.n_tile - c0) : 64;     // multiple of 16
-        asm volatile("bar.sync 1, 128;" ::: "memory");                 // scale/shift visible; staging free
+        const int cp = (a.n_tile - c0 >= 64) ? 4 : (a.n_tile - c0) / 16;
+        asm volatile("bar.sync 1, 128;" ::: "memory");                 // staging free
         uint32_t v[4][16];
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh)
-          if (hh * 16 < cw) ptx::tmem_ld_32x32b_x16(taddr + c0 + hh * 16, v[hh]);
+          if (hh < cp) ptx::tmem_ld_32x32b_x16(taddr + c0 + hh * 16, v[hh]);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {
-          if (hh * 16 < cw) {
+          if (hh < cp) {
+            const int col = n_base + c0 + hh * 16;
             uint32_t q[8];
-            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + c0 + hh * 16);
-            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + c0 + hh * 16);
-            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + c0 + hh * 16);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 sc = sc4[i], sh = sh4[i], fl = fl4[i];
-              const float x0 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i]), sc.x, sh.x), fl.x);
-              const float x1 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 1]), sc.y, sh.y), fl.y);
-              const float x2 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 2]), sc.z, sh.z), fl.z);
-              const float x3 = fmaxf(fmaf(__uint_as_float(v[hh][4 * i + 3]), sc.w, sh.w), fl.w);
-              q[2 * i] = pack2(x0, x1, a.fmt);
-              q[2 * i + 1] = pack2(x2, x3, a.fmt);
-            }
+            convert16(v[hh], q, col >= a.relu_lo && col < a.relu_hi, a.fmt);
             const int ch = hh * 2;
             *reinterpret_cast<uint4*>(stage_g + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(q[0], q[1], q[2], q[3]);
             *reinterpret_cast<uint4*>(stage_g + row * 128 + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(q[4], q[5], q[6], q[7]);
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (cl * 8 < cw) {
+        if (cl < 2 * cp) {
           const int col = n_base + c0 + cl * 8;
           uint16_t* dst_base = (col < a.n_split)
                                    ? reinterpret_cast<uint16_t*>(a.out) + a.coff + col
@@ -310,31 +336,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Persistent, cross-tile pipelined version (the one the tower uses).
+// Persistent, cross-tile pipelined version (the one the tower uses for n_tile >= 128).
 //
 // One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (t -> m_tile = t / n_tiles,
-// n_tile index = t % n_tiles, so CTAs running side by side share A and W tiles in L2).  The three roles
-// run their own tile loops and meet only through mbarriers, so
-//   * the TMA producer runs ahead across tile boundaries through the smem ring (loads for tile i+1 are in
+// n_tile index = t % n_tiles, so CTAs running side by side share A and W tiles in L2).  The roles run their
+// own tile loops and meet only through mbarriers, so
+//   * the TMA producers run ahead across tile boundaries through the smem ring (loads for tile i+1 are in
 //     flight while tile i is still multiplying) — this is what hides HBM/L2 latency for the short-K layers,
 //   * the accumulator is double-buffered in TMEM (2 x tmem_cols columns): the epilogue of tile i
-//     (tcgen05.ld -> BN/ReLU -> stores) overlaps the MMAs of tile i+1,
+//     (tcgen05.ld -> ReLU/convert -> TMA stores) overlaps the MMAs of tile i+1,
 //   * barrier init, TMEM allocation and descriptor prefetch are paid once per SM, not once per tile.
+// Warp roles: 0 = A producer, 6 = W producer, 1 = TMEM owner + MMA issuer, 2..5 and 7..10 = epilogue.
+// Every tile's K blocks: block -1 is the bias block (only the [n_tile x 16] shift tile travels, into the stage's
+// W slot; the A producer just arrives), blocks 0..num_kb-1 the filter taps x channel blocks.
 // ---------------------------------------------------------------------------------------------------
-template <bool kPair>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                             const __grid_constant__ CUtensorMap tm_bias,
                              const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                              const __grid_constant__ CUtensorMap tm_o64, const __grid_constant__ CUtensorMap tm_o64_2,
                              const ConvArgs a, const int m_tiles, const int n_tiles) {
-  constexpr int csize = kPair ? 2 : 1;
-  // csize == 2: launched as 2-CTA clusters = CTA pairs (cta_group::2).  The pair owns two consecutive M tiles
-  // (M = 256) of one N tile: each CTA loads its own 128 A rows and HALF of the weight tile (tm_b's box is
-  // n_tile/2 rows), the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 over both CTAs' shared memory,
-  // and the accumulator's two halves land in the two CTAs' TMEM.  Weight bytes through each SM's L2 port halve
-  // (the measured ceiling of this kernel), tile shape per SM is unchanged.  All loads complete on the leader's
-  // full barrier; stage release and accumulator-ready are tcgen05.commit multicasts to both CTAs; both CTAs'
-  // epilogue threads arrive on the leader's tmem_empty barrier.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -345,35 +366,27 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
   const int ck = a.row_bytes / 2;
   const uint32_t a_bytes = static_cast<uint32_t>(kBM) * rb;
-  // weight rows held per CTA: the whole N tile, or half of it in a CTA pair
-  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile / csize) * rb;
+  const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;
   const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u; // stage pitch keeps every tile on a swizzle period
-  const uint32_t out_stage = base + a.stages * stage_bytes;    // 16 KiB epilogue staging: 4 x [128 rows x 32 B]
-  const uint32_t bar_base = out_stage + kOutStageBytes;
+  const uint32_t out_stage = base + a.stages * stage_bytes;    // 16 KiB epilogue staging
+  const uint32_t ones_base = out_stage + kOutStageBytes;       // 4 KiB constant A tile of the bias MMA
+  const uint32_t bar_base = ones_base + kOnesBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
   const uint32_t acc_bar = bar_base + 16u * a.stages;          // tmem_full[2], tmem_empty[2]
   auto tmem_full = [&](int i) { return acc_bar + 8u * i; };
   auto tmem_empty = [&](int i) { return acc_bar + 16u + 8u * i; };
   const uint32_t tmem_slot = acc_bar + 32u;
-  float* s_scale = reinterpret_cast<float*>(gbase + a.stages * stage_bytes + kOutStageBytes + 256);
-  float* s_shift = s_scale + 256;
-  float* s_floor = s_shift + 256;
 
-  // work items: (M-tile group of csize tiles, N tile); this CTA owns M tile group*csize + rank
-  const int m_groups = (m_tiles + csize - 1) / csize;
-  const int total_tiles = m_groups * n_tiles;
+  const int total_tiles = m_tiles * n_tiles;
   const int num_kb = a.taps * a.cblocks;
-  uint32_t crank = 0u;
-  if constexpr (kPair) crank = ptx::cluster_ctarank();
-  const int first = static_cast<int>(blockIdx.x) / csize;
-  const int step = static_cast<int>(gridDim.x) / csize;
-  constexpr bool pair = kPair;
-  const bool leader = crank == 0;
+  const int first = static_cast<int>(blockIdx.x);
+  const int step = static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
+    ptx::prefetch_tmap(&tm_bias);
     ptx::prefetch_tmap(&tm_o);
     ptx::prefetch_tmap(&tm_o2);
     ptx::prefetch_tmap(&tm_o64);
@@ -384,172 +397,152 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
-      ptx::mbar_init(tmem_empty(i), pair ? 2 * kEpiThreads : kEpiThreads);   // every epilogue thread (of both CTAs) arrives
+      ptx::mbar_init(tmem_empty(i), kEpiThreads);   // every epilogue thread arrives
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    if constexpr (kPair) {
-      ptx::tmem_alloc_2sm(tmem_slot, 2 * a.tmem_cols);
-      ptx::tmem_relinquish_2sm();
-    } else {
-      ptx::tmem_alloc(tmem_slot, 2 * a.tmem_cols);
-      ptx::tmem_relinquish();
-    }
+    ptx::tmem_alloc(tmem_slot, 2 * a.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (warp >= 2 && warp <= 5) {
+    write_ones_row(gbase + (ones_base - base), static_cast<int>(threadIdx.x) - 64, a.fmt);
+    ptx::fence_proxy_async_smem();
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (kPair) ptx::cluster_sync();    // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
   if (warp == 0) {
-    {
-      // ---------------- TMA producer (warp-converged; one elected lane issues) ----------------
-      uint32_t it = 0;
-      int s = 0;
-      uint32_t ph = 0;                       // ring position kept incrementally: no division in the K loop
-      for (int t = first; t < total_tiles; t += step) {
-        const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
-        int bw = 0, bh = 0, bn = 0;
-        if (a.im2col) {
-          const int q = m0 % a.ow;
-          const int r = m0 / a.ow;
-          bw = q * a.stride - a.pad_w;
-          bh = (r % a.oh) * a.stride - a.pad_h;
-          bn = r / a.oh;
-        }
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+    // ---------------- TMA producer #1: A tiles (warp-converged; one elected lane issues) ----------------
+    uint32_t it = 0;
+    int s = 0;
+    uint32_t ph = 0;                       // ring position kept incrementally: no division in the K loop
+    for (int t = first; t < total_tiles; t += step) {
+      const int m0 = (t / n_tiles) * kBM;
+      int bw = 0, bh = 0, bn = 0;
+      if (a.im2col) {
+        const int q = m0 % a.ow;
+        const int r = m0 / a.ow;
+        bw = q * a.stride - a.pad_w;
+        bh = (r % a.oh) * a.stride - a.pad_h;
+        bn = r / a.oh;
+      }
+      int cb = 0, tr = 0, ts = 0;
+      for (int kb = -1; kb < num_kb; ++kb) {
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        if (kb >= 0) {
           if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[0 * 512 + it] = clock64();
-          const uint32_t sa = base + s * stage_bytes;
-          if (ptx::elect_one()) {
-            if constexpr (kPair) {
-              if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * a_bytes);
-              if (a.im2col) {
-                const int r = tap / a.kw;
-                ptx::tma_load_im2col_4d_2sm(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
-                                            static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
-              } else {
-                ptx::tma_load_2d_2sm(sa, &tm_a, full_bar(s), cb * ck, m0);
-              }
+          ++it;
+        }
+        const uint32_t sa = base + s * stage_bytes;
+        if (ptx::elect_one()) {
+          if (kb < 0) {
+            ptx::mbar_arrive(full_bar(s));             // bias block: the ones tile is resident
+          } else {
+            ptx::mbar_expect_tx(full_bar(s), a_bytes);
+            if (a.im2col) {
+              ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
+                                      static_cast<uint16_t>(tr));
             } else {
-              ptx::mbar_expect_tx(full_bar(s), a_bytes);
-              if (a.im2col) {
-                const int r = tap / a.kw;
-                ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn,
-                                        static_cast<uint16_t>(tap - r * a.kw), static_cast<uint16_t>(r));
-              } else {
-                ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
-              }
+              ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
             }
           }
-          __syncwarp();
-          if (++cb == a.cblocks) { cb = 0; ++tap; }
-          if (++s == a.stages) { s = 0; ph ^= 1u; }
         }
+        __syncwarp();
+        if (kb >= 0 && ++cb == a.cblocks) {
+          cb = 0;
+          if (++ts == a.kw) { ts = 0; ++tr; }
+        }
+        if (++s == a.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 6) {
-    {
-      // ---------------- TMA producer #2: weight tiles ----------------
-      // Issuing a TMA costs the issuing thread several hundred cycles; with one producer thread the A and W
-      // loads of a stage serialise, so the two operands get one issuing warp each.
-      uint32_t it = 0;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = first; t < total_tiles; t += step) {
-        const int n_base = (t % n_tiles) * a.n_tile;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+    // ---------------- TMA producer #2: weight tiles ----------------
+    // Issuing a TMA costs the issuing thread several hundred cycles; with one producer thread the A and W
+    // loads of a stage serialise, so the two operands get one issuing warp each.
+    uint32_t it = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = first; t < total_tiles; t += step) {
+      const int n_base = (t % n_tiles) * a.n_tile;
+      for (int kb = -1; kb < num_kb; ++kb) {
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        if (kb >= 0) {
           if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[1 * 512 + it] = clock64();
-          const uint32_t sb = base + s * stage_bytes + a_bytes;
-          if (ptx::elect_one()) {
-            if constexpr (kPair) {
-              if (leader) ptx::mbar_expect_tx(full_bar(s), 2u * b_bytes);
-              ptx::tma_load_2d_2sm(sb, &tm_b, full_bar(s), kb * ck, n_base + static_cast<int>(crank) * (a.n_tile / 2));
-            } else {
-              ptx::mbar_expect_tx(full_bar(s), b_bytes);
-              ptx::tma_load_2d(sb, &tm_b, full_bar(s), kb * ck, n_base);
-            }
-          }
-          __syncwarp();
-          if (++s == a.stages) { s = 0; ph ^= 1u; }
+          ++it;
         }
+        const uint32_t sb = base + s * stage_bytes + a_bytes;
+        if (ptx::elect_one()) {
+          if (kb < 0) {
+            ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
+            ptx::tma_load_2d(sb, &tm_bias, full_bar(s), 0, n_base);
+          } else {
+            ptx::mbar_expect_tx(full_bar(s), b_bytes);
+            ptx::tma_load_2d(sb, &tm_b, full_bar(s), kb * ck, n_base);
+          }
+        }
+        __syncwarp();
+        if (++s == a.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (leader || !pair) {
-      // ---------------- MMA issuer: warp-converged loop, one elected lane issues (pair: leader CTA only) ----------------
-      const uint32_t idesc = ptx::make_idesc_f16(a.fmt, pair ? 2 * kBM : kBM, a.n_tile);
-      const int ksteps = a.row_bytes / 32;
-      uint32_t it = 0, lt = 0;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = first; t < total_tiles; t += step, ++lt) {
-        const uint32_t as = lt & 1u;
-        ptx::mbar_wait(tmem_empty(as), ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+    // ---------------- MMA issuer: warp-converged loop, one elected lane issues ----------------
+    const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
+    const int ksteps = a.row_bytes / 32;
+    const uint64_t d_ones = ptx::make_smem_desc_rows(ones_base, 32);
+    uint32_t it = 0, lt = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = first; t < total_tiles; t += step, ++lt) {
+      const uint32_t as = lt & 1u;
+      ptx::mbar_wait(tmem_empty(as), ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t tacc = tmem_base + as * a.tmem_cols;
+      for (int kb = -1; kb < num_kb; ++kb) {
+        ptx::mbar_wait(full_bar(s), ph);
         ptx::tc_fence_after();
-        const uint32_t tacc = tmem_base + as * a.tmem_cols;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          ptx::mbar_wait(full_bar(s), ph);
-          ptx::tc_fence_after();
-          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[2 * 512 + it] = clock64();
-          const uint32_t sa = base + s * stage_bytes;
-          const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
-          const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
-          if (ptx::elect_one()) {
-            if constexpr (kPair) {
-              for (int k = 0; k < ksteps; ++k) ptx::umma_f16_2sm(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-              ptx::umma_commit_2sm(empty_bar(s), 3);       // frees stage s in both CTAs
-            } else {
-              if (ksteps == 4) {
+        if (kb >= 0 && a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[2 * 512 + it] = clock64();
+        const uint32_t sa = base + s * stage_bytes;
+        if (ptx::elect_one()) {
+          if (kb < 0) {
+            // accumulator := shift (hi + lo halves) broadcast down the 128 rows
+            ptx::umma_f16(tacc, d_ones, ptx::make_smem_desc_rows(sa + a_bytes, 32), idesc, 0u);
+          } else {
+            const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
+            const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
+            if (ksteps == 4) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-              } else {
-                for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-              }
-              ptx::umma_commit(empty_bar(s));
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
+            } else {
+              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
             }
           }
-          __syncwarp();
-          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[3 * 512 + it] = clock64();
-          if (++s == a.stages) { s = 0; ph ^= 1u; }
-        }
-        if (ptx::elect_one()) {
-          if constexpr (kPair) ptx::umma_commit_2sm(tmem_full(as), 3);  // both CTAs' epilogues
-          else ptx::umma_commit(tmem_full(as));
+          ptx::umma_commit(empty_bar(s));
         }
         __syncwarp();
+        if (kb >= 0) {
+          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[3 * 512 + it] = clock64();
+          ++it;
+        }
+        if (++s == a.stages) { s = 0; ph ^= 1u; }
       }
+      if (ptx::elect_one()) ptx::umma_commit(tmem_full(as));
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue (warps 2..5 and 7..10) ----------------
-    // MEASURED (timeline, profiles/r01_epilogue.md): with four epilogue warps a 128 x 64 chunk cost ~1600 cycles —
-    // 512 of TMEM read (tcgen05.ld moves 64 B/cycle/SM) followed, serially, by ~900 cycles of convert/pack code
-    // issued by ONE warp per scheduler — so every short-K layer (35x35 1x1s, the stem) was epilogue-bound.  Now each
-    // TMEM lane quarter has two warps (w and w+5 share w & 3), each owning 32 of the chunk's 64 columns, and the
-    // loads of chunk i+1 are issued before the arithmetic of chunk i, so the chunk time approaches the TMEM floor.
+    // Each TMEM lane quarter has two warps (w and w+5 share w & 3), each owning half of the 16-column pieces of a
+    // 64-column chunk; the next chunk's TMEM loads are in flight while this one is converted and staged.
     const int grp = warp >= 7 ? 1 : 0;                 // column half of each 64-column chunk
     const int et = grp ? static_cast<int>(threadIdx.x) - 224 + 128 : static_cast<int>(threadIdx.x) - 64;   // 0..255
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint32_t lt = 0;
-    int loaded_n_base = -1;
     for (int t = first; t < total_tiles; t += step, ++lt) {
-      const int m0 = ((t / n_tiles) * csize + static_cast<int>(crank)) * kBM;
+      const int m0 = (t / n_tiles) * kBM;
       const int n_base = (t % n_tiles) * a.n_tile;
-      if (n_base != loaded_n_base) {               // uniform across the epilogue threads
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = et; i < a.n_tile; i += kEpiThreads) {
-          s_scale[i] = __ldg(a.scale + n_base + i);
-          s_shift[i] = __ldg(a.shift + n_base + i);
-          s_floor[i] = a.floor ? __ldg(a.floor + n_base + i) : (a.relu ? 0.f : -INFINITY);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        loaded_n_base = n_base;
-      }
       const uint32_t as = lt & 1u;
       if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[6 * 512 + lt] = clock64();
       ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
@@ -557,50 +550,41 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[4 * 512 + lt] = clock64();
       const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
 
-      // 16-column pieces of the chunk at c0 owned by this thread: [first, first + np) of the chunk's cp (<= 4) pieces
-      auto geom = [&](int c0, int& cp, int& first, int& np) {
+      // 16-column pieces of the chunk at c0 owned by this thread: [fp, fp + np) of the chunk's cp (<= 4) pieces
+      auto geom = [&](int c0, int& cp, int& fp, int& np) {
         cp = (a.n_tile - c0) >> 4;
         if (cp > 4) cp = 4;
         const int h0 = (cp + 1) >> 1;
-        first = grp ? h0 : 0;
+        fp = grp ? h0 : 0;
         np = grp ? cp - h0 : h0;
       };
       auto issue = [&](uint32_t (&v)[32], int c0) {
-        int cp, first, np;
-        geom(c0, cp, first, np);
-        if (np > 0) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * first, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        if (np > 1) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * first + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        int cp, fp, np;
+        geom(c0, cp, fp, np);
+        if (np > 0) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * fp, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        if (np > 1) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * fp + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
       };
-      // The accumulator leaves through shared memory and TMA stores: each thread converts its 32 columns of one
+      // The accumulator leaves through shared memory and TMA stores: each thread converts its <=32 columns of one
       // output pixel (TMEM lane), writes them into the 16 KiB staging buffer, and one thread stores the chunk into
       // the destination slice(s).  Rows past the last valid pixel land in the unused tail of the buffer or are
       // clipped by the tensor map.
-      auto process = [&](uint32_t (&v)[32], int c0) {
-        int chunk_pieces, first, np;
-        geom(c0, chunk_pieces, first, np);
+      auto process = [&](uint32_t (&v)[32], uint32_t (&vn)[32], int c0) {
+        int chunk_pieces, fp, np;
+        geom(c0, chunk_pieces, fp, np);
+        if (c0 + 64 < a.n_tile) issue(vn, c0 + 64);
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (j < np) {
-            const int cc = c0 + 16 * (first + j);
-            const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cc);
-            const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cc);
-            const float4* fl4 = reinterpret_cast<const float4*>(s_floor + cc);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 sc = sc4[q], sh = sh4[q], fl = fl4[q];
-              const float x0 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 0]), sc.x, sh.x), fl.x);
-              const float x1 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 1]), sc.y, sh.y), fl.y);
-              const float x2 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 2]), sc.z, sh.z), fl.z);
-              const float x3 = fmaxf(fmaf(__uint_as_float(v[16 * j + 4 * q + 3]), sc.w, sh.w), fl.w);
-              pk[8 * j + 2 * q] = pack2(x0, x1, a.fmt);
-              pk[8 * j + 2 * q + 1] = pack2(x2, x3, a.fmt);
-            }
+            const int col = n_base + c0 + 16 * (fp + j);
+            convert16(&v[16 * j], &pk[8 * j], col >= a.relu_lo && col < a.relu_hi, a.fmt);
           }
         }
         // staging buffer is free once the previous chunk's stores have read it
+        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[7 * 512 + lt * 4 + (c0 >> 6)] = clock64();
         if (et == 0) ptx::tma_store_wait_read();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[8 * 512 + lt * 4 + (c0 >> 6)] = clock64();
         // A full 64-column chunk that lies in one destination goes out as ONE [128 rows x 128 B] box (128-byte
         // swizzled staging: conflict-free 16-byte writes, and a quarter of the box rows the TMA unit has to walk
         // compared with four 32-byte-row boxes); tails and chunks straddling n_split use 16-column boxes.
@@ -618,7 +602,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (j < np) {
-              const uint32_t dst = out_stage + (first + j) * 4096u + static_cast<uint32_t>(row) * 32u;
+              const uint32_t dst = out_stage + (fp + j) * 4096u + static_cast<uint32_t>(row) * 32u;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[8 * j]), "r"(pk[8 * j + 1]),
                            "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]) : "memory");
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[8 * j + 4]),
@@ -640,12 +624,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             }
           }
           ptx::tma_store_commit();
+          if (a.dbg && blockIdx.x == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[9 * 512 + lt * 4 + (c0 >> 6)] = clock64();
         }
       };
       auto release = [&]() {                       // last TMEM read of this tile has landed: hand the accumulator back
         ptx::tc_fence_before();
-        if constexpr (kPair) ptx::mbar_arrive_leader(tmem_empty(as));
-        else ptx::mbar_arrive(tmem_empty(as));
+        ptx::mbar_arrive(tmem_empty(as));
       };
 
       uint32_t va[32], vb[32];
@@ -653,13 +637,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       issue(va, 0);
       while (true) {
         ptx::tmem_ld_wait();
-        if (c0 + 64 < a.n_tile) issue(vb, c0 + 64); else release();
-        process(va, c0);
+        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[13 * 512 + lt * 4 + (c0 >> 6)] = clock64();
+        if (c0 + 64 >= a.n_tile) release();
+        process(va, vb, c0);
         c0 += 64;
         if (c0 >= a.n_tile) break;
         ptx::tmem_ld_wait();
-        if (c0 + 64 < a.n_tile) issue(va, c0 + 64); else release();
-        process(vb, c0);
+        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[13 * 512 + lt * 4 + (c0 >> 6)] = clock64();
+        if (c0 + 64 >= a.n_tile) release();
+        process(vb, va, c0);
         c0 += 64;
         if (c0 >= a.n_tile) break;
       }
@@ -670,12 +656,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (kPair) ptx::cluster_sync();    // no CTA leaves while its peer can still touch its smem / barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     __syncwarp();
-    if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, 2 * a.tmem_cols);
-    else ptx::tmem_dealloc(tmem_base, 2 * a.tmem_cols);
+    ptx::tmem_dealloc(tmem_base, 2 * a.tmem_cols);
   }
 }
 
@@ -685,7 +669,7 @@ inline size_t conv_stage_bytes(int n_tile, int row_bytes) {
 inline size_t conv_smem_bytes(int stages, int n_tile, int row_bytes, bool persistent = false) {
   size_t ring = static_cast<size_t>(stages) * conv_stage_bytes(n_tile, row_bytes);
   if (!persistent && ring < kOutStageBytes) ring = kOutStageBytes;   // the one-tile kernel stages its epilogue in the ring
-  return 1024 + ring + (persistent ? kOutStageBytes : 0) + 256 + 3072;
+  return 1024 + ring + (persistent ? kOutStageBytes : 0) + kOnesBytes + 256 + 1024;
 }
 
 }  // namespace icp

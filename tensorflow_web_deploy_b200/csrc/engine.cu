@@ -259,6 +259,7 @@ struct Act {   // NHWC 16-bit activation for max_batch images
 struct ConvLayer {
   std::string name;
   CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_bias;       // [cout][16] (hi, lo) halves of the BatchNorm shift: B operand of the bias MMA
   CUtensorMap tm_o, tm_o2;   // destination slices (persistent kernel's TMA-store epilogue): 16-column boxes
   CUtensorMap tm_o64, tm_o64_2;   // same, 64-column (128-byte, swizzled) boxes
   ConvArgs args{};
@@ -269,7 +270,6 @@ struct ConvLayer {
   long long macs_per_image = 0;
   long long in_elems_per_image = 0;
   bool persistent = true;  // conv_igemm_persistent_kernel (one CTA per SM walks the tiles)
-  int csize = 1;           // thread-block cluster size sharing (multicasting) each weight tile
   bool halo = false;       // conv_halo_kernel instead of conv_igemm_kernel
   HaloArgs hargs{};
 };
@@ -290,7 +290,9 @@ static bool g_conv_attr_set = false;
 
 // Packs HWIO fp32 weights into the K-major [cout][taps][cblocks*64] 16-bit matrix the B-operand TMA
 // reads, zero-filling the channel tail of every tap.
-static std::vector<uint16_t> pack_weights(const float* w, int kh, int kw, int cin, int cout, int ck, int fmt) {
+// `scale` (nullable): per-output-channel BatchNorm scale multiplied in before rounding to 16 bits.
+static std::vector<uint16_t> pack_weights(const float* w, int kh, int kw, int cin, int cout, int ck, int fmt,
+                                          const float* scale = nullptr) {
   const int cb = (cin + ck - 1) / ck;
   const size_t kp = static_cast<size_t>(kh) * kw * cb * ck;
   std::vector<uint16_t> out(static_cast<size_t>(cout) * kp, 0);
@@ -299,13 +301,38 @@ static std::vector<uint16_t> pack_weights(const float* w, int kh, int kw, int ci
       for (int ci = 0; ci < cin; ++ci) {
         const float* src = w + ((static_cast<size_t>(r) * kw + s) * cin + ci) * cout;
         const size_t kidx = (static_cast<size_t>(r) * kw + s) * cb * ck + ci;
-        for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(src[co], fmt);
+        for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(scale ? src[co] * scale[co] : src[co], fmt);
       }
   return out;
 }
 
+static float host_h2f(uint16_t h, int fmt) {
+  if (fmt) {
+    const uint32_t u = static_cast<uint32_t>(h) << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  }
+  __half hh;
+  memcpy(&hh, &h, 2);
+  return __half2float(hh);
+}
+
+// B operand of the bias MMA: [cout][16] 16-bit, K columns 0/1 = shift split into hi + lo halves (the A operand's
+// first two K columns are 1), so the accumulator starts at shift with ~2^-17 relative error.
+static std::vector<uint16_t> pack_bias(const float* shift, int cout, int fmt) {
+  std::vector<uint16_t> out(static_cast<size_t>(cout) * 16, 0);
+  for (int co = 0; co < cout; ++co) {
+    const uint16_t hi = host_f2h(shift[co], fmt);
+    out[co * 16] = hi;
+    out[co * 16 + 1] = host_f2h(shift[co] - host_h2f(hi, fmt), fmt);
+  }
+  return out;
+}
+
 // Halo kernel's B operand: K index = ((chunk * taps + tap) * ck + j), channel = chunk*ck + j.
-static std::vector<uint16_t> pack_weights_halo(const float* w, int kh, int kw, int cin, int cout, int ck, int fmt) {
+static std::vector<uint16_t> pack_weights_halo(const float* w, int kh, int kw, int cin, int cout, int ck, int fmt,
+                                               const float* scale = nullptr) {
   const int chunks = (cin + ck - 1) / ck, taps = kh * kw;
   const size_t kp = static_cast<size_t>(chunks) * taps * ck;
   std::vector<uint16_t> out(static_cast<size_t>(cout) * kp, 0);
@@ -313,7 +340,7 @@ static std::vector<uint16_t> pack_weights_halo(const float* w, int kh, int kw, i
     for (int ci = 0; ci < cin; ++ci) {
       const float* src = w + (static_cast<size_t>(t) * cin + ci) * cout;
       const size_t kidx = (static_cast<size_t>(ci / ck) * taps + t) * ck + (ci % ck);
-      for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(src[co], fmt);
+      for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(scale ? src[co] * scale[co] : src[co], fmt);
     }
   return out;
 }
@@ -361,7 +388,6 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.n_tiles = cout / n_tile;
   const int num_kb = kh * kw * cb;
   const size_t stage_bytes = conv_stage_bytes(n_tile, rb);
-  int pair_stage_n = 0;
   static const bool conv_v1 = getenv("ICP_CONV_V1") != nullptr;     // one tile per CTA (bring-up version)
   const size_t budget = conv_v1 ? ((n_tile <= 128) ? 100 * 1024 : 200 * 1024) : 204 * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
@@ -379,19 +405,6 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     if (stages < 1) stages = 1;
   }
   L.persistent = persistent;
-  // CTA pairs (cta_group::2): two SMs share one M=256 tile and each loads (and stores in smem) half of the
-  // weight tile, which also buys a deeper ring from the same shared memory.  Implemented, parity-green, and
-  // MEASURED SLOWER than one CTA per SM on this tower (4.08 vs 3.74 ms/step; conv4 0.345 vs 0.278 ms), so it is
-  // opt-in (ICP_PAIR=1) — see profiles/r01_halo_vs_im2col.md.
-  static const bool use_pair = getenv("ICP_PAIR") && atoi(getenv("ICP_PAIR")) != 0;
-  int csize = 1;
-  if (persistent && use_pair && n_tile % 16 == 0) {
-    csize = 2;
-    const size_t sb2 = conv_stage_bytes(n_tile / 2, rb);
-    stages = static_cast<int>(204 * 1024 / sb2);
-    if (stages > kMaxStages) stages = kMaxStages;
-    pair_stage_n = n_tile / 2;
-  }
   static const bool force_im2col = getenv("ICP_FORCE_IM2COL") != nullptr;
   const bool im2col = force_im2col || !(kh == 1 && kw == 1 && stride == 1);
   // Stride-1 convs with a real filter footprint: halo-resident kernel (conv_halo.cuh).  Per-image bands need a
@@ -441,13 +454,13 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       acc_sets = (2 * T * n_tile <= 512) ? 2 : 1;
       while (nstrips < 4 && halo_smem_bytes(strip_bytes, nstrips + 1, w_bytes) <= 225 * 1024) ++nstrips;
       const size_t smem = halo_smem_bytes(strip_bytes, nstrips, w_bytes);
-      std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt);
+      std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt, scale);
       void* d_w = pool.alloc(wp_host.size() * 2);
       CK(cudaMemcpy(d_w, wp_host.data(), wp_host.size() * 2, cudaMemcpyHostToDevice));
-      float* d_scale = static_cast<float*>(pool.alloc(cout * 4));
-      float* d_shift = static_cast<float*>(pool.alloc(cout * 4));
-      CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
+      std::vector<uint16_t> bp = pack_bias(shift, cout, fmt);
+      void* d_bias = pool.alloc(bp.size() * 2);
+      CK(cudaMemcpy(d_bias, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice));
+      L.tm_bias = make_tm_2d_rows(d_bias, cout, 16, n_tile, 32, fmt);
       const uint64_t kp = static_cast<uint64_t>(chunks) * taps * ck;
       L.halo = true;
       L.tm_b = make_tm_2d_rows(d_w, cout, kp, n_tile, rb, fmt);
@@ -467,7 +480,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       h.acc_cols = T * n_tile; h.acc_sets = acc_sets; h.tmem_cols = pow2_cols(acc_sets * T * n_tile);
       h.w_resident = resident ? 1 : 0; h.w_bytes = w_bytes; h.b_stages = b_stages;
       h.fmt = fmt; h.relu = relu ? 1 : 0;
-      h.out = out.p; h.ldo = out.c; h.coff = out_coff; h.scale = d_scale; h.shift = d_shift;
+      h.out = out.p; h.ldo = out.c; h.coff = out_coff; 
       L.smem = smem;
       if (!g_halo_attr_set) {
         CK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -481,18 +494,17 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   }
   if (transpose_out) fail(ICP_E_INVALID, "%s: transposed output needs the halo kernel in tall mode", name.c_str());
 
-  // weights + BN vectors to the device
-  std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, ck, fmt);
+  // weights (BatchNorm scale folded in) and the shift tile of the bias MMA
+  std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, ck, fmt, scale);
   void* d_w = pool.alloc(wp.size() * 2);
   CK(cudaMemcpy(d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
-  float* d_scale = static_cast<float*>(pool.alloc(cout * 4));
-  float* d_shift = static_cast<float*>(pool.alloc(cout * 4));
-  CK(cudaMemcpy(d_scale, scale, cout * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_shift, shift, cout * 4, cudaMemcpyHostToDevice));
+  std::vector<uint16_t> bp = pack_bias(shift, cout, fmt);
+  void* d_bias = pool.alloc(bp.size() * 2);
+  CK(cudaMemcpy(d_bias, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice));
+  L.tm_bias = make_tm_2d_rows(d_bias, cout, 16, n_tile, 32, fmt);
 
   const uint64_t kp = static_cast<uint64_t>(num_kb) * ck;
-  L.csize = csize;
-  L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile / csize, fmt, rb);
+  L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile, fmt, rb);
   const uint16_t* a_ptr = in.p + in_coff;
   if (im2col)
     L.tm_a = make_tm_im2col(a_ptr, max_n, in.h, in.w, cin, in.c, kh, kw, stride, pad_h, pad_w, fmt, rb);
@@ -515,28 +527,28 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.stages = stages;
   a.im2col = im2col ? 1 : 0;
   a.fmt = fmt;
-  a.relu = relu ? 1 : 0;
   a.out = out.p;
   a.ldo = out.c;
   a.coff = out_coff;
-  a.scale = d_scale;
-  a.shift = d_shift;
   static const bool v1_staged = getenv("ICP_V1_STAGED") != nullptr;
   a.epi_staged = v1_staged ? 1 : 0;
   a.dbg = nullptr;
-  a.w_gmem = d_w;
-  a.w_kp = static_cast<int>(kp);
-  a.floor = nullptr;
+  // ReLU column range: everything, nothing, or (fused siblings) the leading run of channels whose floor is 0
+  a.relu_lo = 0;
+  a.relu_hi = relu ? cout : 0;
   if (floor) {
-    float* d_floor = static_cast<float*>(pool.alloc(cout * 4));
-    CK(cudaMemcpy(d_floor, floor, cout * 4, cudaMemcpyHostToDevice));
-    a.floor = d_floor;
+    int hi = 0;
+    while (hi < cout && floor[hi] == 0.0f) ++hi;
+    for (int i = hi; i < cout; ++i)
+      if (floor[i] == 0.0f) fail(ICP_E_INVALID, "%s: ReLU channels must form one leading run", name.c_str());
+    if (hi % 16) fail(ICP_E_INVALID, "%s: ReLU boundary %d is not a multiple of 16", name.c_str(), hi);
+    a.relu_hi = hi;
   }
   a.out2 = out2 ? out2->p : nullptr;
   a.ldo2 = out2 ? out2->c : 0;
   a.coff2 = out2_coff;
   a.n_split = out2 ? n_split : (1 << 30);
-  L.smem = conv_smem_bytes(stages, pair_stage_n ? pair_stage_n : n_tile, rb, persistent);
+  L.smem = conv_smem_bytes(stages, n_tile, rb, persistent);
   {
     const uint64_t out_rows = static_cast<uint64_t>(max_n) * oh * ow;
     L.tm_o = make_tm_out(out.p, out_rows, out.c, fmt);
@@ -546,8 +558,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   }
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -562,7 +573,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     h.n_images = n;
     const int bands = h.tall ? (n * h.oh * h.wp + kBM * h.T - 1) / (kBM * h.T) : h.bands_per_image * n;
     const int items = bands * h.n_tiles;
-    conv_halo_kernel<<<items < g_num_sms ? items : g_num_sms, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, h);
+    conv_halo_kernel<<<items < g_num_sms ? items : g_num_sms, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
     CK(cudaGetLastError());
     return;
   }
@@ -570,31 +581,12 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
   a.m_total = n * L.pix_per_image;
   const int m_tiles = (a.m_total + kBM - 1) / kBM;
   if (L.persistent) {
-    const int cs = L.csize;
-    const int total = ((m_tiles + cs - 1) / cs) * L.n_tiles;          // (M-tile group, N tile) work items
-    const int max_clusters = g_num_sms / cs;
-    const int clusters = total < max_clusters ? total : max_clusters;
-    if (cs == 1) {
-      conv_igemm_persistent_kernel<false><<<clusters, kPersistThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
-      CK(cudaGetLastError());
-      return;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(clusters * cs);
-    cfg.blockDim = dim3(kPersistThreads);
-    cfg.dynamicSmemBytes = L.smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true>, L.tm_a, L.tm_b, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles));
+    const int total = m_tiles * L.n_tiles;
+    conv_igemm_persistent_kernel<<<total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st>>>(
+        L.tm_a, L.tm_b, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
   } else {
     dim3 grid(m_tiles, L.n_tiles);
-    conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, a);
+    conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, a);
   }
   CK(cudaGetLastError());
 }
@@ -1622,14 +1614,14 @@ int icp_conv2d_bn_relu(int device, int precision, const float* x, int n, int h, 
     const char* tl_path = getenv("ICP_TIMELINE");
     long long* d_dbg = nullptr;
     if (tl_path && (L.persistent || L.halo)) {
-      d_dbg = static_cast<long long*>(pool.alloc(10 * 512 * 8));
-      CK(cudaMemsetAsync(d_dbg, 0, 10 * 512 * 8, st));
+      d_dbg = static_cast<long long*>(pool.alloc(14 * 512 * 8));
+      CK(cudaMemsetAsync(d_dbg, 0, 14 * 512 * 8, st));
       L.args.dbg = d_dbg;
       L.hargs.dbg = d_dbg;
     }
     launch_conv(L, n, st);
     if (d_dbg) {
-      std::vector<long long> hd(10 * 512);
+      std::vector<long long> hd(14 * 512);
       CK(cudaMemcpyAsync(hd.data(), d_dbg, hd.size() * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       if (FILE* f = fopen(tl_path, "wb")) { fwrite(hd.data(), 8, hd.size(), f); fclose(f); }

@@ -29,12 +29,13 @@ def round16(a, precision):
 
 
 def ref_conv(x, w, scale, shift, stride, same, precision):
-    xq, wq = round16(x, precision), round16(w, precision)
+    # the engine folds the BatchNorm scale into the 16-bit weights (and adds shift inside the accumulator)
+    xq, wq = round16(x, precision), round16(w * scale.reshape(1, 1, 1, -1), precision)
     kh, kw = w.shape[:2]
     pad = ((kh - 1) // 2, (kw - 1) // 2) if same else (0, 0)
     y = F.conv2d(torch.from_numpy(xq.transpose(0, 3, 1, 2).copy()), torch.from_numpy(wq.transpose(3, 2, 0, 1).copy()),
                  None, stride, pad)
-    y = torch.relu(y * torch.from_numpy(scale).view(1, -1, 1, 1) + torch.from_numpy(shift).view(1, -1, 1, 1))
+    y = torch.relu(y + torch.from_numpy(shift).view(1, -1, 1, 1))
     return round16(y.numpy().transpose(0, 2, 3, 1), precision)
 
 

@@ -31,12 +31,13 @@ def round16(a, precision):
 def ref_conv(x, w, scale, shift, stride, same, relu, precision):
     import torch
     import torch.nn.functional as F
-    xq, wq = round16(x, precision), round16(w, precision)
+    # the engine folds the BatchNorm scale into the 16-bit weights (and adds shift inside the accumulator)
+    xq, wq = round16(x, precision), round16(w * scale.reshape(1, 1, 1, -1), precision)
     kh, kw = w.shape[:2]
     pad = ((kh - 1) // 2, (kw - 1) // 2) if same else (0, 0)
     y = F.conv2d(torch.from_numpy(xq.transpose(0, 3, 1, 2).copy()), torch.from_numpy(wq.transpose(3, 2, 0, 1).copy()),
                  None, stride, pad)
-    y = y * torch.from_numpy(scale).view(1, -1, 1, 1) + torch.from_numpy(shift).view(1, -1, 1, 1)
+    y = y + torch.from_numpy(shift).view(1, -1, 1, 1)
     if relu:
         y = torch.relu(y)
     return round16(y.numpy().transpose(0, 2, 3, 1), precision)
@@ -263,6 +264,7 @@ LAYERS = {
     "c17_1x1_768_704": (17, 17, 768, 1, 1, 704, 1, True),
     "c35_3x3_96": (35, 35, 96, 3, 3, 96, 1, True),
     "c8_3x3_448": (8, 8, 448, 3, 3, 384, 1, True),
+    "c35_1x1_288_256": (35, 35, 288, 1, 1, 256, 1, True),
     "conv1": (149, 149, 32, 3, 3, 32, 1, False),
     "conv2": (147, 147, 32, 3, 3, 64, 1, True),
     "conv3": (73, 73, 64, 1, 1, 80, 1, False),

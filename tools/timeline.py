@@ -24,6 +24,15 @@ for t in range(min(nt, 12)):
 
 if r.shape[0] >= 10 and (r[7] >= 0).any():
     ns = int((r[7] >= 0).sum())
-    print("halo epilogue sub-tiles (rows 7/8/9: TMEM read done, staging written+barrier, copy-out issued):")
+    print("epilogue units (rows 7/8/9) — halo: TMEM read done, staging written+barrier, copy-out issued;")
+    print("                                persistent: arithmetic done, staging free (wait_read+barrier), TMA store issued:")
     for q in range(min(ns, 24)):
         print("  sub %3d: tmem %8d  staged %8d (+%d)  stored %8d (+%d)" % (q, r[7, q], r[8, q], r[8, q] - r[7, q], r[9, q], r[9, q] - r[8, q]))
+
+if r.shape[0] >= 14 and (r[13] >= 0).any():
+    print("persistent epilogue chunk phases: ldwait-done | +convert (7) | +free (8) | +STS (10) | +fence (11) || store warp: issued (9) - fence | read done (12) - issued")
+    ns = int((r[13] >= 0).sum())
+    for q in range(min(ns, 24)):
+        t = r[13, q]
+        print("  chunk %3d: t=%8d  %5d %5d %5d %5d || %5d %5d" % (q, t, r[7, q] - t, r[8, q] - r[7, q], r[10, q] - r[8, q],
+                                                      r[11, q] - r[10, q], r[9, q] - r[11, q], r[12, q] - r[9, q]))
