@@ -147,7 +147,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int h_first = p0 / a.wp;
       for (int c = 0; c < a.chunks; ++c) {
         ptx::mbar_wait(strip_empty(s), ph ^ 1u);
-        if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[0 * 512 + it] = clock64();
+        ICP_STAMP(a.dbg, 0, it, lane == 0);
         ++it;
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(strip_full(s), strip_tx);
@@ -238,7 +238,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int c = 0; c < a.chunks; ++c) {
         ptx::mbar_wait(strip_full(s), ph);
         ptx::tc_fence_after();
-        if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[2 * 512 + it] = clock64();
+        ICP_STAMP(a.dbg, 2, it, lane == 0);
         const uint32_t a_units0 = ((strip0 + s * a.strip_bytes) >> 4) + local_units;
         if (a.w_resident) {
           if (ptx::elect_one()) {
@@ -287,7 +287,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (++sb == static_cast<uint32_t>(a.b_stages)) { sb = 0; phb ^= 1u; }
           }
         }
-        if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[3 * 512 + it] = clock64();
+        ICP_STAMP(a.dbg, 3, it, lane == 0);
         ++it;
         if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
       }
@@ -318,10 +318,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int p0 = (band - img * bands_per_image) * kBM * a.T;
       int nsub = (positions - p0 + kBM - 1) / kBM;
       if (nsub > a.T) nsub = a.T;
-      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[6 * 512 + lt] = clock64();
+      ICP_STAMP(a.dbg, 6, lt, et == 0);
       ptx::mbar_wait(tmem_full(as), pha);
       ptx::tc_fence_after();
-      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[4 * 512 + lt] = clock64();
+      ICP_STAMP(a.dbg, 4, lt, et == 0);
       const uint32_t tbase = tmem_base + as * a.acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
 
       // 16-column pieces of the chunk at c0 owned by this thread: [first, first + np)
@@ -370,7 +370,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * a.T + j < 512) a.dbg[8 * 512 + lt * a.T + j] = clock64();
+        ICP_STAMP(a.dbg, 8, lt * a.T + j, et == 0);
         if (cl < 2 * cp) {                         // lane's 8 columns exist in this chunk
           int px[4];
           uint4 val[4];
@@ -386,7 +386,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           for (int i = 0; i < 4; ++i)
             if (px[i] >= 0) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(px[i]) * a.ldo) = val[i];
         }
-        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * a.T + j < 512) a.dbg[9 * 512 + lt * a.T + j] = clock64();
+        ICP_STAMP(a.dbg, 9, lt * a.T + j, et == 0);
       };
       auto release = [&]() {                       // accumulator fully read: hand it back to the MMA issuer
         ptx::tc_fence_before();
@@ -400,7 +400,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int nj = j, nc = c0 + 64;
         if (nc >= a.n_tile) { nc = 0; ++nj; }
         ptx::tmem_ld_wait();
-        if (a.dbg && blockIdx.x == 0 && et == 0 && c0 == 0 && lt * a.T + j < 512) a.dbg[7 * 512 + lt * a.T + j] = clock64();
+        ICP_STAMP(a.dbg, 7, lt * a.T + j, et == 0 && c0 == 0);
         if (nj >= nsub) release();
         process(va, vb, j, c0, nj < nsub, nj, nc);
         if (nj >= nsub) break;
@@ -408,13 +408,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         nc = c0 + 64;
         if (nc >= a.n_tile) { nc = 0; ++nj; }
         ptx::tmem_ld_wait();
-        if (a.dbg && blockIdx.x == 0 && et == 0 && c0 == 0 && lt * a.T + j < 512) a.dbg[7 * 512 + lt * a.T + j] = clock64();
+        ICP_STAMP(a.dbg, 7, lt * a.T + j, et == 0 && c0 == 0);
         if (nj >= nsub) release();
         process(vb, va, j, c0, nj < nsub, nj, nc);
         if (nj >= nsub) break;
         j = nj; c0 = nc;
       }
-      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[5 * 512 + lt] = clock64();
+      ICP_STAMP(a.dbg, 5, lt, et == 0);
       if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
     }
   }

@@ -41,6 +41,19 @@ constexpr uint32_t kOutStageBytes = 16384;  // epilogue staging
 constexpr uint32_t kOnesBytes = 4096;       // [128 x 16] 16-bit "ones" A tile of the bias MMA (32-byte rows, SWIZZLE_32B)
 constexpr int kMaxStages = 12;
 
+// Debug timeline (tools/timeline.py): clock64 stamps of CTA 0 into a [rows][512] buffer.  Compiled in only with
+// -DICP_TIMELINE_BUILD (tools/build_timeline.sh): the branches alone cost the MMA-issue loop ~1 % of a step.
+#ifdef ICP_TIMELINE_BUILD
+#define ICP_STAMP(buf, row, idx, pred)                                                        \
+  do {                                                                                        \
+    if ((buf) && blockIdx.x == 0 && (pred) && (idx) < 512) (buf)[(row) * 512 + (idx)] = clock64(); \
+  } while (0)
+#else
+#define ICP_STAMP(buf, row, idx, pred) \
+  do {                                 \
+  } while (0)
+#endif
+
 struct ConvArgs {
   int m_total;     // valid output pixels (n * oh * ow)
   int oh, ow;      // output spatial size
@@ -49,6 +62,10 @@ struct ConvArgs {
   int kw;          // filter width (S)
   int taps;        // R * S
   int cblocks;     // ceil(cin / ck), ck = row_bytes / 2 channels per K block
+  int tail_ksteps; // K=16 MMAs issued for the LAST channel block of a tap: ceil((cin - (cblocks-1)*ck) / 16); the
+                   // remaining slices of that block are zero padding on both operands
+  int tail_rb;     // operand row bytes of that last block: 32 / 64 when <= 16 / 32 channels remain (its tiles then
+                   // come through tm_a_tail / tm_b_tail with SWIZZLE_32B/64B boxes), else row_bytes
   int row_bytes;   // bytes per operand row in smem: 32 / 64 / 128 (SWIZZLE_32B/64B/128B)
   int n_tile;      // output channels per CTA, multiple of 16, <= 256
   int tmem_cols;   // power of two >= max(32, n_tile)
@@ -120,6 +137,7 @@ __device__ __forceinline__ void write_ones_row(uint8_t* ones, int r, int fmt) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kConvThreads)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const __grid_constant__ CUtensorMap tm_a_tail, const __grid_constant__ CUtensorMap tm_b_tail,
                   const __grid_constant__ CUtensorMap tm_bias, const ConvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -145,11 +163,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int m0 = blockIdx.x * kBM;
   const int n_base = blockIdx.y * a.n_tile;
   const int num_kb = a.taps * a.cblocks;
+  const bool narrow_tail = a.tail_rb != a.row_bytes;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
     ptx::prefetch_tmap(&tm_bias);
+    ptx::prefetch_tmap(&tm_a_tail);
+    ptx::prefetch_tmap(&tm_b_tail);
     for (int s = 0; s < a.stages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
@@ -193,14 +214,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
           ptx::tma_load_2d(sa + a_bytes, &tm_bias, full_bar(s), 0, n_base);
         } else {
-          ptx::mbar_expect_tx(full_bar(s), stage_tx);
+          const bool tail = narrow_tail && cb == a.cblocks - 1;
+          const CUtensorMap* ma = tail ? &tm_a_tail : &tm_a;
+          ptx::mbar_expect_tx(full_bar(s), tail ? static_cast<uint32_t>(kBM + a.n_tile) * a.tail_rb : stage_tx);
           if (a.im2col) {
-            ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
+            ptx::tma_load_im2col_4d(sa, ma, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
                                     static_cast<uint16_t>(tr));
           } else {
-            ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
+            ptx::tma_load_2d(sa, ma, full_bar(s), cb * ck, m0);
           }
-          ptx::tma_load_2d(sa + a_bytes, &tm_b, full_bar(s), kb * ck, n_base);
+          ptx::tma_load_2d(sa + a_bytes, tail ? &tm_b_tail : &tm_b, full_bar(s), kb * ck, n_base);
         }
       }
       __syncwarp();
@@ -214,7 +237,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
     const int ksteps = a.row_bytes / 32;
-    int s = 0;
+    int s = 0, cb = 0;
     uint32_t ph = 0;
     for (int kb = -1; kb < num_kb; ++kb) {
       ptx::mbar_wait(full_bar(s), ph);
@@ -226,20 +249,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           ptx::umma_f16(tmem_base, ptx::make_smem_desc_rows(ones_base, 32), ptx::make_smem_desc_rows(sa + a_bytes, 32),
                         idesc, 0u);
         } else {
-          const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
-          const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
+          const bool last_cb = cb == a.cblocks - 1;
+          const uint32_t rbk = last_cb ? static_cast<uint32_t>(a.tail_rb) : rb;
+          const uint64_t da = ptx::make_smem_desc_rows(sa, rbk);
+          const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rbk);
           // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
-          if (ksteps == 4) {
+          const int ks = last_cb ? a.tail_ksteps : ksteps;
+          if (ks == 4) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
           } else {
-            for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
+            for (int k = 0; k < ks; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
           }
         }
         ptx::umma_commit(empty_bar(s));      // smem slot free once these MMAs retire
         if (kb == num_kb - 1) ptx::umma_commit(tmem_full_bar);       // accumulator complete
       }
       __syncwarp();
+      if (kb >= 0 && ++cb == a.cblocks) cb = 0;
       if (++s == a.stages) { s = 0; ph ^= 1u; }
     }
   } else {
@@ -352,6 +379,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                             const __grid_constant__ CUtensorMap tm_a_tail, const __grid_constant__ CUtensorMap tm_b_tail,
                              const __grid_constant__ CUtensorMap tm_bias,
                              const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                              const __grid_constant__ CUtensorMap tm_o64, const __grid_constant__ CUtensorMap tm_o64_2,
@@ -380,6 +408,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 
   const int total_tiles = m_tiles * n_tiles;
   const int num_kb = a.taps * a.cblocks;
+  const bool narrow_tail = a.tail_rb != a.row_bytes;
   const int first = static_cast<int>(blockIdx.x);
   const int step = static_cast<int>(gridDim.x);
 
@@ -387,6 +416,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
     ptx::prefetch_tmap(&tm_bias);
+    ptx::prefetch_tmap(&tm_a_tail);
+    ptx::prefetch_tmap(&tm_b_tail);
     ptx::prefetch_tmap(&tm_o);
     ptx::prefetch_tmap(&tm_o2);
     ptx::prefetch_tmap(&tm_o64);
@@ -419,6 +450,13 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     uint32_t it = 0;
     int s = 0;
     uint32_t ph = 0;                       // ring position kept incrementally: no division in the K loop
+    uint32_t sa = base;
+    const uint32_t a_tail_bytes = static_cast<uint32_t>(kBM) * a.tail_rb;
+    const int cb_last = a.cblocks - 1;
+    auto advance = [&]() {
+      sa += stage_bytes;
+      if (++s == a.stages) { s = 0; ph ^= 1u; sa = base; }
+    };
     for (int t = first; t < total_tiles; t += step) {
       const int m0 = (t / n_tiles) * kBM;
       int bw = 0, bh = 0, bn = 0;
@@ -429,33 +467,32 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         bh = (r % a.oh) * a.stride - a.pad_h;
         bn = r / a.oh;
       }
+      // bias block: the ones tile is resident, nothing to load
+      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+      if (ptx::elect_one()) ptx::mbar_arrive(full_bar(s));
+      __syncwarp();
+      advance();
       int cb = 0, tr = 0, ts = 0;
-      for (int kb = -1; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        if (kb >= 0) {
-          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[0 * 512 + it] = clock64();
-          ++it;
-        }
-        const uint32_t sa = base + s * stage_bytes;
+        ICP_STAMP(a.dbg, 0, it, lane == 0);
         if (ptx::elect_one()) {
-          if (kb < 0) {
-            ptx::mbar_arrive(full_bar(s));             // bias block: the ones tile is resident
+          const bool tail = narrow_tail && cb == cb_last;
+          const CUtensorMap* ma = tail ? &tm_a_tail : &tm_a;
+          ptx::mbar_expect_tx(full_bar(s), tail ? a_tail_bytes : a_bytes);
+          if (a.im2col) {
+            ptx::tma_load_im2col_4d(sa, ma, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
+                                    static_cast<uint16_t>(tr));
           } else {
-            ptx::mbar_expect_tx(full_bar(s), a_bytes);
-            if (a.im2col) {
-              ptx::tma_load_im2col_4d(sa, &tm_a, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
-                                      static_cast<uint16_t>(tr));
-            } else {
-              ptx::tma_load_2d(sa, &tm_a, full_bar(s), cb * ck, m0);
-            }
+            ptx::tma_load_2d(sa, ma, full_bar(s), cb * ck, m0);
           }
         }
         __syncwarp();
-        if (kb >= 0 && ++cb == a.cblocks) {
+        if (++cb == a.cblocks) {
           cb = 0;
           if (++ts == a.kw) { ts = 0; ++tr; }
         }
-        if (++s == a.stages) { s = 0; ph ^= 1u; }
+        advance();
       }
     }
   } else if (warp == 6) {
@@ -465,68 +502,99 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     uint32_t it = 0;
     int s = 0;
     uint32_t ph = 0;
+    uint32_t sb = base + a_bytes;
+    const uint32_t b_tail_bytes = static_cast<uint32_t>(a.n_tile) * a.tail_rb;
+    const int cb_last = a.cblocks - 1;
+    auto advance = [&]() {
+      sb += stage_bytes;
+      if (++s == a.stages) { s = 0; ph ^= 1u; sb = base + a_bytes; }
+    };
     for (int t = first; t < total_tiles; t += step) {
       const int n_base = (t % n_tiles) * a.n_tile;
-      for (int kb = -1; kb < num_kb; ++kb) {
+      // bias block: the [n_tile x 16] shift tile
+      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
+        ptx::tma_load_2d(sb, &tm_bias, full_bar(s), 0, n_base);
+      }
+      __syncwarp();
+      advance();
+      int cb = 0, kcol = 0;
+      for (int kb = 0; kb < num_kb; ++kb, ++it, kcol += ck) {
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        if (kb >= 0) {
-          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[1 * 512 + it] = clock64();
-          ++it;
-        }
-        const uint32_t sb = base + s * stage_bytes + a_bytes;
+        ICP_STAMP(a.dbg, 1, it, lane == 0);
         if (ptx::elect_one()) {
-          if (kb < 0) {
-            ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
-            ptx::tma_load_2d(sb, &tm_bias, full_bar(s), 0, n_base);
-          } else {
-            ptx::mbar_expect_tx(full_bar(s), b_bytes);
-            ptx::tma_load_2d(sb, &tm_b, full_bar(s), kb * ck, n_base);
-          }
+          const bool tail = narrow_tail && cb == cb_last;
+          ptx::mbar_expect_tx(full_bar(s), tail ? b_tail_bytes : b_bytes);
+          ptx::tma_load_2d(sb, tail ? &tm_b_tail : &tm_b, full_bar(s), kcol, n_base);
         }
         __syncwarp();
-        if (++s == a.stages) { s = 0; ph ^= 1u; }
+        if (++cb == a.cblocks) cb = 0;
+        advance();
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer: warp-converged loop, one elected lane issues ----------------
+    // The loop body is on the critical path of every K block (MEASURED: a dozen extra integer instructions here cost
+    // 1-2 % of a whole step), so descriptors are built from hoisted halves and the stage address is kept
+    // incrementally.
     const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
     const int ksteps = a.row_bytes / 32;
-    const uint64_t d_ones = ptx::make_smem_desc_rows(ones_base, 32);
+    const uint64_t hi_main = ptx::make_smem_desc_rows(0, rb);              // descriptor minus the address field
+    const uint64_t hi_tail = ptx::make_smem_desc_rows(0, a.tail_rb);
+    const uint64_t hi_32 = ptx::make_smem_desc_rows(0, 32);
+    const uint64_t d_ones = hi_32 | ((ones_base & 0x3FFFFu) >> 4);
+    const uint32_t a_units = a_bytes >> 4;
+    const uint32_t stage_units = stage_bytes >> 4;
+    const uint32_t base_units = (base & 0x3FFFFu) >> 4;
+    const int cb_last = a.cblocks - 1;
+    const bool uniform = (a.tail_ksteps == ksteps) && !narrow_tail;        // every block is a full one
     uint32_t it = 0, lt = 0;
     int s = 0;
     uint32_t ph = 0;
+    uint32_t su = base_units;                                              // stage start, 16-byte units
+    auto advance = [&]() {
+      su += stage_units;
+      if (++s == a.stages) { s = 0; ph ^= 1u; su = base_units; }
+    };
     for (int t = first; t < total_tiles; t += step, ++lt) {
       const uint32_t as = lt & 1u;
       ptx::mbar_wait(tmem_empty(as), ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + as * a.tmem_cols;
-      for (int kb = -1; kb < num_kb; ++kb) {
+      // bias block: accumulator := shift (hi + lo halves) broadcast down the 128 rows
+      ptx::mbar_wait(full_bar(s), ph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        ptx::umma_f16(tacc, d_ones, hi_32 | (su + a_units), idesc, 0u);
+        ptx::umma_commit(empty_bar(s));
+      }
+      __syncwarp();
+      advance();
+      int cb = 0;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
         ptx::mbar_wait(full_bar(s), ph);
         ptx::tc_fence_after();
-        if (kb >= 0 && a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[2 * 512 + it] = clock64();
-        const uint32_t sa = base + s * stage_bytes;
+        ICP_STAMP(a.dbg, 2, it, lane == 0);
         if (ptx::elect_one()) {
-          if (kb < 0) {
-            // accumulator := shift (hi + lo halves) broadcast down the 128 rows
-            ptx::umma_f16(tacc, d_ones, ptx::make_smem_desc_rows(sa + a_bytes, 32), idesc, 0u);
-          } else {
-            const uint64_t da = ptx::make_smem_desc_rows(sa, rb);
-            const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rb);
+          if (uniform || cb != cb_last) {
+            const uint64_t da = hi_main | su, db = hi_main | (su + a_units);
             if (ksteps == 4) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
             } else {
               for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
             }
+          } else {
+            const uint64_t da = hi_tail | su, db = hi_tail | (su + a_units);
+            for (int k = 0; k < a.tail_ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
           }
           ptx::umma_commit(empty_bar(s));
         }
         __syncwarp();
-        if (kb >= 0) {
-          if (a.dbg && blockIdx.x == 0 && lane == 0 && it < 512) a.dbg[3 * 512 + it] = clock64();
-          ++it;
-        }
-        if (++s == a.stages) { s = 0; ph ^= 1u; }
+        ICP_STAMP(a.dbg, 3, it, lane == 0);
+        if (++cb == a.cblocks) cb = 0;
+        advance();
       }
       if (ptx::elect_one()) ptx::umma_commit(tmem_full(as));
       __syncwarp();
@@ -544,10 +612,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       const int m0 = (t / n_tiles) * kBM;
       const int n_base = (t % n_tiles) * a.n_tile;
       const uint32_t as = lt & 1u;
-      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[6 * 512 + lt] = clock64();
+      ICP_STAMP(a.dbg, 6, lt, et == 0);
       ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
       ptx::tc_fence_after();
-      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[4 * 512 + lt] = clock64();
+      ICP_STAMP(a.dbg, 4, lt, et == 0);
       const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
 
       // 16-column pieces of the chunk at c0 owned by this thread: [fp, fp + np) of the chunk's cp (<= 4) pieces
@@ -581,10 +649,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           }
         }
         // staging buffer is free once the previous chunk's stores have read it
-        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[7 * 512 + lt * 4 + (c0 >> 6)] = clock64();
+        ICP_STAMP(a.dbg, 7, lt * 4 + (c0 >> 6), et == 0);
         if (et == 0) ptx::tma_store_wait_read();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[8 * 512 + lt * 4 + (c0 >> 6)] = clock64();
+        ICP_STAMP(a.dbg, 8, lt * 4 + (c0 >> 6), et == 0);
         // A full 64-column chunk that lies in one destination goes out as ONE [128 rows x 128 B] box (128-byte
         // swizzled staging: conflict-free 16-byte writes, and a quarter of the box rows the TMA unit has to walk
         // compared with four 32-byte-row boxes); tails and chunks straddling n_split use 16-column boxes.
@@ -624,7 +692,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             }
           }
           ptx::tma_store_commit();
-          if (a.dbg && blockIdx.x == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[9 * 512 + lt * 4 + (c0 >> 6)] = clock64();
+          ICP_STAMP(a.dbg, 9, lt * 4 + (c0 >> 6), true);
         }
       };
       auto release = [&]() {                       // last TMEM read of this tile has landed: hand the accumulator back
@@ -637,19 +705,19 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       issue(va, 0);
       while (true) {
         ptx::tmem_ld_wait();
-        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[13 * 512 + lt * 4 + (c0 >> 6)] = clock64();
+        ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
         if (c0 + 64 >= a.n_tile) release();
         process(va, vb, c0);
         c0 += 64;
         if (c0 >= a.n_tile) break;
         ptx::tmem_ld_wait();
-        if (a.dbg && blockIdx.x == 0 && et == 0 && lt * 4 + (c0 >> 6) < 512) a.dbg[13 * 512 + lt * 4 + (c0 >> 6)] = clock64();
+        ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
         if (c0 + 64 >= a.n_tile) release();
         process(vb, va, c0);
         c0 += 64;
         if (c0 >= a.n_tile) break;
       }
-      if (a.dbg && blockIdx.x == 0 && et == 0 && lt < 512) a.dbg[5 * 512 + lt] = clock64();
+      ICP_STAMP(a.dbg, 5, lt, et == 0);
     }
     if (et == 0) ptx::tma_store_wait_all();      // smem must outlive the last store's read
   }

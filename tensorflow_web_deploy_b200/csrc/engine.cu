@@ -259,6 +259,7 @@ struct Act {   // NHWC 16-bit activation for max_batch images
 struct ConvLayer {
   std::string name;
   CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a_tail, tm_b_tail;   // last channel block of a tap when <= 32 channels remain: 32/64-byte-row boxes
   CUtensorMap tm_bias;       // [cout][16] (hi, lo) halves of the BatchNorm shift: B operand of the bias MMA
   CUtensorMap tm_o, tm_o2;   // destination slices (persistent kernel's TMA-store epilogue): 16-column boxes
   CUtensorMap tm_o64, tm_o64_2;   // same, 64-column (128-byte, swizzled) boxes
@@ -511,6 +512,20 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   else
     L.tm_a = make_tm_2d(a_ptr, static_cast<uint64_t>(max_n) * in.h * in.w, cin, in.c, kBM, fmt, rb);
 
+  // last channel block of every tap: narrower boxes when only 16 / 32 channels remain (conv4: 80 = 64 + 16)
+  const int tail_c = cin - (cb - 1) * ck;
+  static const bool no_narrow_tail = getenv("ICP_NO_NARROW_TAIL") != nullptr;
+  const int tail_rb = (no_narrow_tail || rb != 128) ? rb : (tail_c <= 16 ? 32 : (tail_c <= 32 ? 64 : 128));
+  L.tm_a_tail = L.tm_a;
+  L.tm_b_tail = L.tm_b;
+  if (tail_rb != rb) {
+    L.tm_b_tail = make_tm_2d(d_w, cout, kp, kp, n_tile, fmt, tail_rb);
+    if (im2col)
+      L.tm_a_tail = make_tm_im2col(a_ptr, max_n, in.h, in.w, cin, in.c, kh, kw, stride, pad_h, pad_w, fmt, tail_rb);
+    else
+      L.tm_a_tail = make_tm_2d(a_ptr, static_cast<uint64_t>(max_n) * in.h * in.w, cin, in.c, kBM, fmt, tail_rb);
+  }
+
   ConvArgs& a = L.args;
   a.m_total = 0;
   a.oh = oh;
@@ -521,6 +536,8 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.kw = kw;
   a.taps = kh * kw;
   a.cblocks = cb;
+  a.tail_ksteps = (tail_c + 15) / 16;
+  a.tail_rb = tail_rb;
   a.row_bytes = rb;
   a.n_tile = n_tile;
   a.tmem_cols = pow2_cols(n_tile);
@@ -583,10 +600,10 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
   if (L.persistent) {
     const int total = m_tiles * L.n_tiles;
     conv_igemm_persistent_kernel<<<total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st>>>(
-        L.tm_a, L.tm_b, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
+        L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
   } else {
     dim3 grid(m_tiles, L.n_tiles);
-    conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, a);
+    conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_bias, a);
   }
   CK(cudaGetLastError());
 }

@@ -294,6 +294,9 @@ def cmd_layer(args):
 
 
 def main():
+    if os.environ.get("ICP_AB_LIB"):      # A/B timing on the same box against a saved build of an earlier commit
+        from tensorflow_web_deploy_b200 import engine as _e
+        _e.LIB_PATH = os.path.abspath(os.environ["ICP_AB_LIB"])
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
     p = sub.add_parser("conv"); p.add_argument("--only", default=None)
