@@ -203,71 +203,96 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       bh = (t % a.oh) * a.stride - a.pad_h;
       bn = t / a.oh;
     }
-    int cb = 0, tr = 0, ts = 0;
     int s = 0;
     uint32_t ph = 0;                       // stage index / phase kept incrementally: no division in the loop
-    for (int kb = -1; kb < num_kb; ++kb) {
+    uint32_t sa = base;
+    const uint32_t tail_tx = static_cast<uint32_t>(kBM + a.n_tile) * a.tail_rb;
+    const int cb_last = a.cblocks - 1;
+    auto advance = [&]() {
+      sa += stage_bytes;
+      if (++s == a.stages) { s = 0; ph ^= 1u; sa = base; }
+    };
+    // bias block: only the shift tile travels (the first pass over the ring never waits)
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(full_bar(0), static_cast<uint32_t>(a.n_tile) * 32u);
+      ptx::tma_load_2d(sa + a_bytes, &tm_bias, full_bar(0), 0, n_base);
+    }
+    __syncwarp();
+    advance();
+    int cb = 0, tr = 0, ts = 0, kcol = 0;
+    for (int kb = 0; kb < num_kb; ++kb, kcol += ck) {
       ptx::mbar_wait(empty_bar(s), ph ^ 1u);
       if (ptx::elect_one()) {
-        const uint32_t sa = base + s * stage_bytes;
-        if (kb < 0) {                        // bias block: only the shift tile travels
-          ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
-          ptx::tma_load_2d(sa + a_bytes, &tm_bias, full_bar(s), 0, n_base);
+        const bool tail = narrow_tail && cb == cb_last;
+        const CUtensorMap* ma = tail ? &tm_a_tail : &tm_a;
+        ptx::mbar_expect_tx(full_bar(s), tail ? tail_tx : stage_tx);
+        if (a.im2col) {
+          ptx::tma_load_im2col_4d(sa, ma, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
+                                  static_cast<uint16_t>(tr));
         } else {
-          const bool tail = narrow_tail && cb == a.cblocks - 1;
-          const CUtensorMap* ma = tail ? &tm_a_tail : &tm_a;
-          ptx::mbar_expect_tx(full_bar(s), tail ? static_cast<uint32_t>(kBM + a.n_tile) * a.tail_rb : stage_tx);
-          if (a.im2col) {
-            ptx::tma_load_im2col_4d(sa, ma, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
-                                    static_cast<uint16_t>(tr));
-          } else {
-            ptx::tma_load_2d(sa, ma, full_bar(s), cb * ck, m0);
-          }
-          ptx::tma_load_2d(sa + a_bytes, tail ? &tm_b_tail : &tm_b, full_bar(s), kb * ck, n_base);
+          ptx::tma_load_2d(sa, ma, full_bar(s), cb * ck, m0);
         }
+        ptx::tma_load_2d(sa + a_bytes, tail ? &tm_b_tail : &tm_b, full_bar(s), kcol, n_base);
       }
       __syncwarp();
-      if (kb >= 0 && ++cb == a.cblocks) {
+      if (++cb == a.cblocks) {
         cb = 0;
         if (++ts == a.kw) { ts = 0; ++tr; }
       }
-      if (++s == a.stages) { s = 0; ph ^= 1u; }
+      advance();
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = ptx::make_idesc_f16(a.fmt, kBM, a.n_tile);
     const int ksteps = a.row_bytes / 32;
-    int s = 0, cb = 0;
+    const uint64_t hi_main = ptx::make_smem_desc_rows(0, rb);              // descriptor minus the address field
+    const uint64_t hi_tail = ptx::make_smem_desc_rows(0, a.tail_rb);
+    const uint64_t hi_32 = ptx::make_smem_desc_rows(0, 32);
+    const uint32_t a_units = a_bytes >> 4;
+    const uint32_t stage_units = stage_bytes >> 4;
+    const uint32_t base_units = (base & 0x3FFFFu) >> 4;
+    const int cb_last = a.cblocks - 1;
+    const bool uniform = (a.tail_ksteps == ksteps) && !narrow_tail;        // every block is a full one
+    int s = 0;
     uint32_t ph = 0;
-    for (int kb = -1; kb < num_kb; ++kb) {
+    uint32_t su = base_units;                                              // stage start, 16-byte units
+    auto advance = [&]() {
+      su += stage_units;
+      if (++s == a.stages) { s = 0; ph ^= 1u; su = base_units; }
+    };
+    // bias block: accumulator := shift (hi + lo halves) broadcast down the 128 rows
+    ptx::mbar_wait(full_bar(0), 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      ptx::umma_f16(tmem_base, hi_32 | ((ones_base & 0x3FFFFu) >> 4), hi_32 | (su + a_units), idesc, 0u);
+      ptx::umma_commit(empty_bar(0));
+    }
+    __syncwarp();
+    advance();
+    int cb = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
       ptx::mbar_wait(full_bar(s), ph);
       ptx::tc_fence_after();
-      const uint32_t sa = base + s * stage_bytes;
       if (ptx::elect_one()) {
-        if (kb < 0) {
-          // accumulator := shift (hi + lo halves) broadcast down the 128 rows
-          ptx::umma_f16(tmem_base, ptx::make_smem_desc_rows(ones_base, 32), ptx::make_smem_desc_rows(sa + a_bytes, 32),
-                        idesc, 0u);
-        } else {
-          const bool last_cb = cb == a.cblocks - 1;
-          const uint32_t rbk = last_cb ? static_cast<uint32_t>(a.tail_rb) : rb;
-          const uint64_t da = ptx::make_smem_desc_rows(sa, rbk);
-          const uint64_t db = ptx::make_smem_desc_rows(sa + a_bytes, rbk);
-          // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
-          const int ks = last_cb ? a.tail_ksteps : ksteps;
-          if (ks == 4) {
+        // +32 B per K=16 slice inside the swizzled row: +2 in the (addr>>4) field
+        if (uniform || cb != cb_last) {
+          const uint64_t da = hi_main | su, db = hi_main | (su + a_units);
+          if (ksteps == 4) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
           } else {
-            for (int k = 0; k < ks; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
+            for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
           }
+        } else {
+          const uint64_t da = hi_tail | su, db = hi_tail | (su + a_units);
+          for (int k = 0; k < a.tail_ksteps; ++k) ptx::umma_f16(tmem_base, da + 2u * k, db + 2u * k, idesc, 1u);
         }
         ptx::umma_commit(empty_bar(s));      // smem slot free once these MMAs retire
         if (kb == num_kb - 1) ptx::umma_commit(tmem_full_bar);       // accumulator complete
       }
       __syncwarp();
-      if (kb >= 0 && ++cb == a.cblocks) cb = 0;
-      if (++s == a.stages) { s = 0; ph ^= 1u; }
+      if (++cb == a.cblocks) cb = 0;
+      advance();
     }
   } else {
     // ---------------- epilogue (warps 2..5) ----------------

@@ -395,14 +395,16 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   if (stages > kMaxStages) stages = kMaxStages;
   if (conv_v1 && stages > num_kb) stages = num_kb;
   if (stages < 1) stages = 1;
-  static const bool conv_v2_all = getenv("ICP_CONV_V2_ALL") != nullptr;
-  // narrow layers (n_tile < 128) keep several short-lived CTAs per SM: measured faster than one persistent CTA
-  const bool persistent = !conv_v1 && (conv_v2_all || n_tile >= 128);
+  // The persistent kernel is used for every layer: since its role loops and epilogue were tightened it also beats
+  // the one-tile-per-CTA kernel on the narrow layers (n_tile < 128: 2.517 vs 2.537 ms/step, conv3 0.066 vs 0.072,
+  // 35x35 3x3 64->96 0.035 vs 0.043).  ICP_CONV_V1=1 or ICP_CONV_V1_NARROW=1 select the one-tile kernel for A/B runs.
+  static const bool v1_narrow = getenv("ICP_CONV_V1_NARROW") != nullptr;
+  const bool persistent = !conv_v1 && !(v1_narrow && n_tile < 128);
   if (!persistent) {
     const size_t b1 = (n_tile <= 128) ? 100 * 1024 : 200 * 1024;
     stages = static_cast<int>(b1 / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages > num_kb) stages = num_kb;
+    if (stages > num_kb + 1) stages = num_kb + 1;    // + the bias block
     if (stages < 1) stages = 1;
   }
   L.persistent = persistent;
@@ -684,6 +686,8 @@ struct icp_engine {
   cudaStream_t lane_stream[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [0] unused (= caller's stream)
   cudaEvent_t fork_ev = nullptr;
   cudaEvent_t join_ev[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t stem_ops = 0;              // leading entries of `ops` that form the stem (conv1 .. pool2)
+  int stem_chunk = 0;               // images per pass of the stem (0 = whole batch at once), see enqueue_tower
   int lanes_max_batch = 1 << 30;    // measured faster at every batch size (0.86 -> 0.61 ms at 1, 3.37 -> 3.23 ms at 128)
   int launches = 0;
   long long conv_macs_per_image = 0;
@@ -1017,6 +1021,7 @@ struct Builder {
       x = p;
       tap("pool2", x);
     }
+    e.stem_ops = ops.size();
     x = block35(ops, "mixed_35x35x256a", x, 32);
     x = block35(ops, "mixed_35x35x288a", x, 64);
     x = block35(ops, "mixed_35x35x288b", x, 64);
@@ -1066,7 +1071,7 @@ struct Builder {
   }
 };
 
-static int run_op(const Op& op, int n, int fmt, cudaStream_t st) {
+static int run_op(const Op& op, int n, int fmt, cudaStream_t st, int out_image0 = 0) {
   switch (op.kind) {
     case Op::CONV:
       launch_conv(op.conv, n, st);
@@ -1074,14 +1079,17 @@ static int run_op(const Op& op, int n, int fmt, cudaStream_t st) {
     case Op::MAXPOOL: {
       const unsigned per_image = static_cast<unsigned>(op.out.h) * ((op.out.w + 1) / 2) * (op.c / 8);
       maxpool3s2_kernel<<<dim3((per_image + 255) / 256, n), 256, 0, st>>>(
-          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, 0, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff, fmt);
+          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, 0,
+          op.out.p + static_cast<size_t>(out_image0) * op.out.h * op.out.w * op.out.c, op.out.h, op.out.w, op.out.c,
+          op.out_coff, fmt);
       CK(cudaGetLastError());
       return 1;
     }
     case Op::AVGPOOL: {
       const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
       if (op.scale && op.k == 3 && op.stride == 1 && op.pad == 1)
-        avgpool3_bn_relu_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        avgpool3_bn_relu_kernel<<<static_cast<unsigned>((static_cast<long long>(n) * op.in.h * ((op.in.w + 3) / 4) *
+                                                         (op.c / 8) + 127) / 128), 128, 0, st>>>(
             op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.c, op.out_coff, op.scale, op.shift,
             fmt);
       else
@@ -1113,25 +1121,39 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
   int launches = 0;
   const int fmt = e.fmt;
   if (tm) tm->mark();
-  {
+  // Optional (ICP_STEM_CHUNK=<images>, default off): run the stem in passes over the SAME chunk-sized region of the
+  // intermediate buffers so that each producer->consumer pair (<= 88 MB at 32 images) stays in the 126 MB L2
+  // instead of making a round trip through HBM.  MEASURED at batch 128: 2.544 ms whole batch, 2.59 / 2.63 / 2.73 ms
+  // in passes of 64 / 32 / 16 — the stem kernels are not HBM-bound and the shorter launches quantise worse.
+  // Only the first op's input and the last op's output are indexed by the pass's first image (stem endpoints
+  // then hold the last pass only; per-op profiling always runs the whole batch).
+  const int chunk = (!tm && e.stem_chunk > 0 && n > e.stem_chunk) ? e.stem_chunk : n;
+  for (int i0 = 0; i0 < n; i0 += chunk) {
+    const int nc = n - i0 < chunk ? n - i0 : chunk;
     const Act& o = e.conv0_out;
-    const long long pix = static_cast<long long>(n) * o.h * o.w;
+    const long long pix = static_cast<long long>(nc) * o.h * o.w;
     const unsigned grid = static_cast<unsigned>((pix + 127) / 128);
+    const size_t in_off = static_cast<size_t>(i0) * e.S * e.S * 3;
     if (x_is_u8)
-      conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev), n, e.S, e.S, e.conv0, o.p, o.h,
-                                                  o.w, fmt);
+      conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0,
+                                                  o.p, o.h, o.w, fmt);
     else
-      conv0_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x_dev), n, e.S, e.S, e.conv0, o.p, o.h, o.w,
-                                                fmt);
+      conv0_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x_dev) + in_off, nc, e.S, e.S, e.conv0, o.p,
+                                                o.h, o.w, fmt);
     CK(cudaGetLastError());
     ++launches;
     if (tm) tm->mark();
+    for (size_t i = 0; i < e.stem_ops; ++i) {
+      launches += run_op(e.ops[i], nc, fmt, st, i + 1 == e.stem_ops ? i0 : 0);
+      if (tm) tm->mark();
+    }
   }
   // Independent branches of an inception block run on side streams between FORK and JOIN markers when one
   // layer cannot fill the GPU (small batches); captured into the same CUDA graph as parallel branches.
   const bool use_lanes = !tm && n <= e.lanes_max_batch;
   bool lane_live[icp_engine::kLanes] = {false, false, false, false, false};
-  for (const Op& op : e.ops) {
+  for (size_t oi = e.stem_ops; oi < e.ops.size(); ++oi) {
+    const Op& op = e.ops[oi];
     if (op.kind == Op::FORK) {
       if (use_lanes) CK(cudaEventRecord(e.fork_ev, st));
       continue;
@@ -1288,6 +1310,7 @@ int icp_create(const icp_config* cfg, icp_engine** out) {
     }
     CK(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
     if (const char* v = getenv("ICP_LANES_MAX_BATCH")) e->lanes_max_batch = atoi(v);
+    if (const char* v = getenv("ICP_STEM_CHUNK")) e->stem_chunk = atoi(v);
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&e->slot_h2d[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));

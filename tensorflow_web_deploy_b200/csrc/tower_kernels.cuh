@@ -233,53 +233,70 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, in
 }
 
 // 3x3 / stride 1 / SAME average pool (exclude-pad divisor) + the deferred BatchNorm + ReLU of the 1x1 projection
-// that ran before it (pool-after-projection, see engine.cu).  Fully unrolled: the nine 16-byte taps are issued
-// together (out-of-bounds taps read a clamped in-bounds address and are masked), one round trip per thread.
-__global__ void __launch_bounds__(256)
+// that ran before it (pool-after-projection, see engine.cu).  One thread = 8 channels x a run of 4 consecutive
+// output columns of one row: the 3-row column sums of the 6 input columns under the run are formed once and each
+// output is the sum of three of them (18 16-byte loads and 18 unpacks per 4 outputs instead of 36 / 36; the first
+// version was instruction-bound at 1.1 TB/s).  Out-of-range rows / columns contribute zero and the divisor is the
+// number of in-bounds taps, rows_in * cols_in.  All index arithmetic is 32-bit.
+__global__ void __launch_bounds__(128)
 avgpool3_bn_relu_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
                         uint16_t* __restrict__ out, int ldo, int coff, const float* __restrict__ scale,
                         const float* __restrict__ shift, int fmt) {
-  const int cg = C >> 3;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(N) * H * W * cg;
+  constexpr int kRun = 4;
+  const unsigned cg = static_cast<unsigned>(C) >> 3;
+  const unsigned runs = (static_cast<unsigned>(W) + kRun - 1) / kRun;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = static_cast<unsigned>(N) * H * runs * cg;
   if (idx >= total) return;
-  const int g = static_cast<int>(idx % cg);
-  const long long pix = idx / cg;
-  const int ox = static_cast<int>(pix % W);
-  const int oy = static_cast<int>((pix / W) % H);
-  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  const uint16_t* base = in + (static_cast<size_t>(n) * H * W) * ldi + cin_off + g * 8;
-  uint4 v[9];
-  bool ok[9];
+  const unsigned g = idx % cg;
+  const unsigned t = idx / cg;
+  const unsigned run = t % runs;
+  const unsigned rowi = t / runs;               // n * H + oy
+  const int oy = static_cast<int>(rowi % static_cast<unsigned>(H));
+  const int ox0 = static_cast<int>(run) * kRun;
+  const uint16_t* base = in + static_cast<size_t>(rowi - oy) * W * ldi + cin_off + g * 8;   // image start
+  float col[kRun + 2][8];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int iy = oy - 1 + r;
-    const bool oky = iy >= 0 && iy < H;
-    const int cy = min(max(iy, 0), H - 1);
+  for (int c = 0; c < kRun + 2; ++c) {
+    const int ix = ox0 - 1 + c;
+    float sum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ix >= 0 && ix < W) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int ix = ox - 1 + q;
-      ok[r * 3 + q] = oky && ix >= 0 && ix < W;
-      const int cx = min(max(ix, 0), W - 1);
-      v[r * 3 + q] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(cy) * W + cx) * ldi));
+      for (int r = 0; r < 3; ++r) {
+        const int iy = oy - 1 + r;
+        if (iy >= 0 && iy < H) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(iy) * W + ix) * ldi));
+          float f[8];
+          unpack8(v, f, fmt);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sum[j] += f[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) col[c][j] = sum[j];
+  }
+  const int rows_in = 3 - (oy == 0) - (oy == H - 1);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + g * 8 + j);
+    sh[j] = __ldg(shift + g * 8 + j);
+  }
+  uint16_t* orow = out + (static_cast<size_t>(rowi) * W + ox0) * ldo + coff + g * 8;
+#pragma unroll
+  for (int p = 0; p < kRun; ++p) {
+    const int ox = ox0 + p;
+    if (ox < W) {
+      const int cols_in = 3 - (ox == 0) - (ox == W - 1);
+      const float inv = 1.0f / static_cast<float>(rows_in * cols_in);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[j] = fmaxf(fmaf((col[p][j] + col[p + 1][j] + col[p + 2][j]) * inv, sc[j], sh[j]), 0.f);
+      *reinterpret_cast<uint4*>(orow + static_cast<size_t>(p) * ldo) = pack8(acc, fmt);
     }
   }
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int cnt = 0;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    float f[8];
-    unpack8(v[t], f, fmt);
-    const float m = ok[t] ? 1.f : 0.f;
-    cnt += ok[t] ? 1 : 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], m, acc[j]);
-  }
-  const float inv = 1.0f / static_cast<float>(cnt);
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    acc[j] = fmaxf(fmaf(acc[j] * inv, __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j)), 0.f);
-  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + coff + g * 8) = pack8(acc, fmt);
 }
 
 // ---------------------------------------------------------------------------------------------
