@@ -35,7 +35,7 @@ constexpr int kBM = 128;                    // output pixels per CTA tile (UMMA 
 constexpr int kBK = 64;                     // K elements per pipeline stage (one 128-B swizzle row)
 constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kConvThreads = 192;           // one-tile kernel: warps 0 TMA, 1 MMA, 2..5 epilogue
-constexpr int kPersistThreads = 352;        // warps 0/6 TMA producers, 1 MMA issuer, 2..5 and 7..10 epilogue
+constexpr int kPersistThreads = 416;        // warps 0,11 A producers; 6,12 W producers; 1 MMA issuer; 2..5, 7..10 epilogue
 constexpr int kEpiThreads = 256;            // two epilogue warps per TMEM lane quarter (one per half of a 64-column chunk)
 constexpr uint32_t kOutStageBytes = 16384;  // epilogue staging
 constexpr uint32_t kOnesBytes = 4096;       // [128 x 16] 16-bit "ones" A tile of the bias MMA (32-byte rows, SWIZZLE_32B)
@@ -398,7 +398,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 //   * the accumulator is double-buffered in TMEM (2 x tmem_cols columns): the epilogue of tile i
 //     (tcgen05.ld -> ReLU/convert -> TMA stores) overlaps the MMAs of tile i+1,
 //   * barrier init, TMEM allocation and descriptor prefetch are paid once per SM, not once per tile.
-// Warp roles: 0 = A producer, 6 = W producer, 1 = TMEM owner + MMA issuer, 2..5 and 7..10 = epilogue.
+// Warp roles: 0, 11 = A producers; 6, 12 = W producers; 1 = TMEM owner + MMA issuer; 2..5 and 7..10 = epilogue.
 // Every tile's K blocks: block -1 is the bias block (only the [n_tile x 16] shift tile travels, into the stage's
 // W slot; the A producer just arrives), blocks 0..num_kb-1 the filter taps x channel blocks.
 // ---------------------------------------------------------------------------------------------------
@@ -470,8 +470,13 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
-  if (warp == 0) {
-    // ---------------- TMA producer #1: A tiles (warp-converged; one elected lane issues) ----------------
+  if (warp == 0 || warp == 11) {
+    // ---------------- TMA producers #1: A tiles (warp-converged; one elected lane issues) ----------------
+    // MEASURED (timeline): one warp gets an im2col TMA out every ~476 cycles (a 2-D tiled one every ~353) however
+    // deep the ring is, and that cadence — not bytes, not the MMAs (128 cycles per K block at n_tile = 64) — set
+    // the ~518-cycle K-block period of every layer.  Two warps per operand take alternate K blocks.
+    const int mine = warp == 0 ? 0 : 1;          // parity of the ring passes this warp serves
+    int gpar = 0;                                // parity of the current block in the global block sequence
     uint32_t it = 0;
     int s = 0;
     uint32_t ph = 0;                       // ring position kept incrementally: no division in the K loop
@@ -493,26 +498,31 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         bn = r / a.oh;
       }
       // bias block: the ones tile is resident, nothing to load
-      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-      if (ptx::elect_one()) ptx::mbar_arrive(full_bar(s));
-      __syncwarp();
+      if (gpar == mine) {
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        if (ptx::elect_one()) ptx::mbar_arrive(full_bar(s));
+        __syncwarp();
+      }
+      gpar ^= 1;
       advance();
       int cb = 0, tr = 0, ts = 0;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        ICP_STAMP(a.dbg, 0, it, lane == 0);
-        if (ptx::elect_one()) {
-          const bool tail = narrow_tail && cb == cb_last;
-          const CUtensorMap* ma = tail ? &tm_a_tail : &tm_a;
-          ptx::mbar_expect_tx(full_bar(s), tail ? a_tail_bytes : a_bytes);
-          if (a.im2col) {
-            ptx::tma_load_im2col_4d(sa, ma, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
-                                    static_cast<uint16_t>(tr));
-          } else {
-            ptx::tma_load_2d(sa, ma, full_bar(s), cb * ck, m0);
+      for (int kb = 0; kb < num_kb; ++kb, ++it, gpar ^= 1) {
+        if (gpar == mine) {
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          ICP_STAMP(a.dbg, 0, it, lane == 0);
+          if (ptx::elect_one()) {
+            const bool tail = narrow_tail && cb == cb_last;
+            const CUtensorMap* ma = tail ? &tm_a_tail : &tm_a;
+            ptx::mbar_expect_tx(full_bar(s), tail ? a_tail_bytes : a_bytes);
+            if (a.im2col) {
+              ptx::tma_load_im2col_4d(sa, ma, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
+                                      static_cast<uint16_t>(tr));
+            } else {
+              ptx::tma_load_2d(sa, ma, full_bar(s), cb * ck, m0);
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
         if (++cb == a.cblocks) {
           cb = 0;
           if (++ts == a.kw) { ts = 0; ++tr; }
@@ -520,10 +530,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         advance();
       }
     }
-  } else if (warp == 6) {
-    // ---------------- TMA producer #2: weight tiles ----------------
-    // Issuing a TMA costs the issuing thread several hundred cycles; with one producer thread the A and W
-    // loads of a stage serialise, so the two operands get one issuing warp each.
+  } else if (warp == 6 || warp == 12) {
+    // ---------------- TMA producers #2: weight tiles (alternate K blocks, like the A producers) ----------------
+    const int mine = warp == 6 ? 0 : 1;
+    int gpar = 0;
     uint32_t it = 0;
     int s = 0;
     uint32_t ph = 0;
@@ -537,23 +547,28 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     for (int t = first; t < total_tiles; t += step) {
       const int n_base = (t % n_tiles) * a.n_tile;
       // bias block: the [n_tile x 16] shift tile
-      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-      if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
-        ptx::tma_load_2d(sb, &tm_bias, full_bar(s), 0, n_base);
-      }
-      __syncwarp();
-      advance();
-      int cb = 0, kcol = 0;
-      for (int kb = 0; kb < num_kb; ++kb, ++it, kcol += ck) {
+      if (gpar == mine) {
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        ICP_STAMP(a.dbg, 1, it, lane == 0);
         if (ptx::elect_one()) {
-          const bool tail = narrow_tail && cb == cb_last;
-          ptx::mbar_expect_tx(full_bar(s), tail ? b_tail_bytes : b_bytes);
-          ptx::tma_load_2d(sb, tail ? &tm_b_tail : &tm_b, full_bar(s), kcol, n_base);
+          ptx::mbar_expect_tx(full_bar(s), static_cast<uint32_t>(a.n_tile) * 32u);
+          ptx::tma_load_2d(sb, &tm_bias, full_bar(s), 0, n_base);
         }
         __syncwarp();
+      }
+      gpar ^= 1;
+      advance();
+      int cb = 0, kcol = 0;
+      for (int kb = 0; kb < num_kb; ++kb, ++it, kcol += ck, gpar ^= 1) {
+        if (gpar == mine) {
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          ICP_STAMP(a.dbg, 1, it, lane == 0);
+          if (ptx::elect_one()) {
+            const bool tail = narrow_tail && cb == cb_last;
+            ptx::mbar_expect_tx(full_bar(s), tail ? b_tail_bytes : b_bytes);
+            ptx::tma_load_2d(sb, tail ? &tm_b_tail : &tm_b, full_bar(s), kcol, n_base);
+          }
+          __syncwarp();
+        }
         if (++cb == a.cblocks) cb = 0;
         advance();
       }
@@ -597,23 +612,48 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       __syncwarp();
       advance();
       int cb = 0;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      auto issue_block = [&](uint32_t su_, int cb_) {       // the K=16 MMAs of one K block (elected lane only)
+        if (uniform || cb_ != cb_last) {
+          const uint64_t da = hi_main | su_, db = hi_main | (su_ + a_units);
+          if (ksteps == 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
+          } else {
+            for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
+          }
+        } else {
+          const uint64_t da = hi_tail | su_, db = hi_tail | (su_ + a_units);
+          for (int k = 0; k < a.tail_ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
+        }
+      };
+      int kb = 0;
+      // two K blocks per trip of the issue loop: one elect / branch round for 8 MMAs and 2 commits (MEASURED: +10 % on
+      // the n_tile = 64 layers, whose K-block period is set by this loop rather than by the MMAs; neutral for wider tiles)
+      for (; kb + 1 < num_kb; kb += 2, it += 2) {
+        const int s0 = s;
+        const uint32_t su0 = su, ph0 = ph;
+        const int cb0 = cb;
+        if (++cb == a.cblocks) cb = 0;
+        advance();
+        ptx::mbar_wait(full_bar(s0), ph0);
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_block(su0, cb0);
+          ptx::umma_commit(empty_bar(s0));
+          issue_block(su, cb);
+          ptx::umma_commit(empty_bar(s));
+        }
+        __syncwarp();
+        if (++cb == a.cblocks) cb = 0;
+        advance();
+      }
+      for (; kb < num_kb; ++kb, ++it) {
         ptx::mbar_wait(full_bar(s), ph);
         ptx::tc_fence_after();
         ICP_STAMP(a.dbg, 2, it, lane == 0);
         if (ptx::elect_one()) {
-          if (uniform || cb != cb_last) {
-            const uint64_t da = hi_main | su, db = hi_main | (su + a_units);
-            if (ksteps == 4) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
-            } else {
-              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
-            }
-          } else {
-            const uint64_t da = hi_tail | su, db = hi_tail | (su + a_units);
-            for (int k = 0; k < a.tail_ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
-          }
+          issue_block(su, cb);
           ptx::umma_commit(empty_bar(s));
         }
         __syncwarp();
