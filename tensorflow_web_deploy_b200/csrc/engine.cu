@@ -20,6 +20,7 @@
 #include "../../include/inception_b200.h"
 #include "conv_igemm.cuh"
 #include "conv_halo.cuh"
+#include "conv0_tc.cuh"
 #include "tower_kernels.cuh"
 
 namespace icp {
@@ -668,7 +669,9 @@ struct icp_engine {
   int graph_k = 5;
   uint8_t* d_rgb = nullptr;         // staging for icp_classify_rgb8
   size_t d_rgb_cap = 0;
-  Conv0Params conv0{};              // weights + folded BN of the Cin=3 stem conv, passed by value
+  Conv0Params conv0{};              // weights + folded BN of the Cin=3 stem conv, passed by value (FP32-pipe kernel)
+  Conv0TcParams conv0_tc_f{}, conv0_tc_u8{};   // tensor-core conv0: 16-bit weights (+ 2/255 for uint8 input), shift
+  bool conv0_tc = true;
   Act conv0_out;
   std::vector<Op> ops;              // everything after conv0 up to the last block (incl. FORK/JOIN markers)
   std::vector<int> launch_ops;      // indices into `ops` of the entries that launch a kernel
@@ -995,6 +998,27 @@ struct Builder {
       memcpy(e.conv0.w, w.data.data(), sizeof e.conv0.w);
       memcpy(e.conv0.scale, scale.data(), sizeof e.conv0.scale);
       memcpy(e.conv0.shift, shift.data(), sizeof e.conv0.shift);
+      // tensor-core version (conv0_tc.cuh): [cout][32] 16-bit weights with the BN scale folded in; for uint8 input
+      // also the 2/255 of the normalisation, whose "- 1" goes into the shift as -127.5 * sum of the ROUNDED weights,
+      // so the kernel computes exactly  sum W'(u - 127.5) + shift  on integer inputs
+      for (int variant = 0; variant < 2; ++variant) {
+        Conv0TcParams& tp = variant ? e.conv0_tc_u8 : e.conv0_tc_f;
+        const float in_scale = variant ? 2.0f / 255.0f : 1.0f;
+        for (int co = 0; co < 32; ++co) {
+          double wsum = 0.0;
+          for (int k = 0; k < 32; ++k) {
+            const uint16_t h = k < 27 ? host_f2h(w.data[static_cast<size_t>(k) * 32 + co] * scale[co] * in_scale, fmt) : 0;
+            tp.w[co * 32 + k] = h;
+            wsum += host_h2f(h, fmt);
+          }
+          tp.shift[co] = variant ? static_cast<float>(shift[co] - 127.5 * wsum) : shift[co];
+        }
+      }
+      e.conv0_tc = getenv("ICP_CONV0_FMA") == nullptr;
+      CK(cudaFuncSetAttribute(conv0_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(conv0_tc_smem_bytes())));
+      CK(cudaFuncSetAttribute(conv0_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(conv0_tc_smem_bytes())));
       const int o = (S - 3) / 2 + 1;
       e.conv0_out = alloc_act(o, o, 32);
       e.conv_macs_per_image += static_cast<long long>(o) * o * 32 * 27;
@@ -1134,7 +1158,15 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
     const long long pix = static_cast<long long>(nc) * o.h * o.w;
     const unsigned grid = static_cast<unsigned>((pix + 127) / 128);
     const size_t in_off = static_cast<size_t>(i0) * e.S * e.S * 3;
-    if (x_is_u8)
+    if (e.conv0_tc) {
+      const unsigned tgrid = grid < static_cast<unsigned>(g_num_sms) ? grid : static_cast<unsigned>(g_num_sms);
+      if (x_is_u8)
+        conv0_tc_kernel<uint8_t><<<tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st>>>(
+            static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_u8, o.p, o.h, o.w, fmt);
+      else
+        conv0_tc_kernel<float><<<tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st>>>(
+            static_cast<const float*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_f, o.p, o.h, o.w, fmt);
+    } else if (x_is_u8)
       conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0,
                                                   o.p, o.h, o.w, fmt);
     else
