@@ -177,6 +177,37 @@ def test_tower_matches_oracle_and_golden(eng_mod, synth6, oracle_run, precision)
     eng.close()
 
 
+OPT_IN_ENVS = [
+    pytest.param({"ICP_CONV0_FMA": "1"}, id="conv0_fp32_pipe"),
+    pytest.param({"ICP_HALO_MIN_W": "30", "ICP_HALO_TALL": "1"}, id="halo_kernel_everywhere"),
+    pytest.param({"ICP_CONV_V1_NARROW": "1"}, id="one_tile_kernel_for_narrow_layers"),
+    pytest.param({"ICP_STEM_CHUNK": "1"}, id="stem_in_passes"),
+    pytest.param({"ICP_NO_NARROW_TAIL": "1"}, id="full_width_channel_tails"),
+]
+
+
+@pytest.mark.parametrize("env", OPT_IN_ENVS)
+def test_opt_in_kernel_paths_stay_parity_green(synth6, oracle_run, built_lib, tmp_path, env):
+    """The A/B switches of csrc/engine.cu select other kernels for the same layers (read once per process, hence
+    the subprocess); every one of them has to meet the same bar against the oracle."""
+    import subprocess
+    import sys
+    x, _, pred = oracle_run
+    np.save(tmp_path / "x.npy", x)
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from tensorflow_web_deploy_b200 import engine; "
+            "e = engine.Engine(%r, 6, max_batch=2, precision='fp16'); "
+            "np.save(%r, e.forward(np.load(%r))); e.close()"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), synth6[0], str(tmp_path / "p.npy"),
+               str(tmp_path / "x.npy")))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    probs = np.load(tmp_path / "p.npy")
+    assert np.abs(probs - pred).max() <= PROB_TOL["fp16"]
+    np.testing.assert_array_equal(np.argsort(-probs, axis=1, kind="stable")[:, :5],
+                                  np.argsort(-pred, axis=1, kind="stable")[:, :5])
+
+
 def test_ragged_batches_and_batch_invariance(eng_mod, synth6):
     """Each image's result is independent of the batch it rides in (inference BN, ops.py:122-125):
     bit-exact across batch sizes, positions, CUDA-graph replay and input dtype path."""
