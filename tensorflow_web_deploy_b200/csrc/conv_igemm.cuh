@@ -68,6 +68,7 @@ struct ConvArgs {
                    // come through tm_a_tail / tm_b_tail with SWIZZLE_32B/64B boxes), else row_bytes
   int row_bytes;   // bytes per operand row in smem: 32 / 64 / 128 (SWIZZLE_32B/64B/128B)
   int n_tile;      // output channels per CTA, multiple of 16, <= 256
+  int cout;        // output channels of the layer: the last N tile may be narrower than n_tile (704 = 256 + 256 + 192)
   int tmem_cols;   // power of two >= max(32, n_tile)
   int stages;
   int im2col;      // 1: A via im2col TMA, 0: A via 2-D tiled TMA
@@ -676,6 +677,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     for (int t = first; t < total_tiles; t += step, ++lt) {
       const int m0 = (t / n_tiles) * kBM;
       const int n_base = (t % n_tiles) * a.n_tile;
+      // columns of this tile that exist: the weight / shift boxes of a narrower last tile are zero-filled past Cout
+      // (the MMAs run at full width), the epilogue simply stops at `cols`
+      const int cols = a.cout - n_base < a.n_tile ? a.cout - n_base : a.n_tile;
       const uint32_t as = lt & 1u;
       ICP_STAMP(a.dbg, 6, lt, et == 0);
       ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
@@ -685,7 +689,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 
       // 16-column pieces of the chunk at c0 owned by this thread: [fp, fp + np) of the chunk's cp (<= 4) pieces
       auto geom = [&](int c0, int& cp, int& fp, int& np) {
-        cp = (a.n_tile - c0) >> 4;
+        cp = (cols - c0) >> 4;
         if (cp > 4) cp = 4;
         const int h0 = (cp + 1) >> 1;
         fp = grp ? h0 : 0;
@@ -704,7 +708,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       auto process = [&](uint32_t (&v)[32], uint32_t (&vn)[32], int c0) {
         int chunk_pieces, fp, np;
         geom(c0, chunk_pieces, fp, np);
-        if (c0 + 64 < a.n_tile) issue(vn, c0 + 64);
+        if (c0 + 64 < cols) issue(vn, c0 + 64);
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -771,16 +775,16 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       while (true) {
         ptx::tmem_ld_wait();
         ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
-        if (c0 + 64 >= a.n_tile) release();
+        if (c0 + 64 >= cols) release();
         process(va, vb, c0);
         c0 += 64;
-        if (c0 >= a.n_tile) break;
+        if (c0 >= cols) break;
         ptx::tmem_ld_wait();
         ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
-        if (c0 + 64 >= a.n_tile) release();
+        if (c0 + 64 >= cols) release();
         process(vb, va, c0);
         c0 += 64;
-        if (c0 >= a.n_tile) break;
+        if (c0 >= cols) break;
       }
       ICP_STAMP(a.dbg, 5, lt, et == 0);
     }

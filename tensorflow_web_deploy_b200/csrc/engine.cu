@@ -386,8 +386,17 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     }
   const int ck = rb / 2;
   const int cb = (cin + ck - 1) / ck;
-  const int n_tile = pick_n_tile(cout);
+  int n_tile = pick_n_tile(cout);
   L.n_tiles = cout / n_tile;
+  // Experiment (ICP_UNEVEN_N=1): full 256-column tiles plus a narrower last one when that needs FEWER tiles than the
+  // even split (640 = 256 + 256 + 128 instead of 4 x 160, 704 = 256 + 256 + 192 instead of 4 x 176).  MEASURED: no
+  // gain (2.461 vs 2.461 ms/step; 17x17 1x1 768->704 0.0246 vs 0.0232 ms) — at 256 columns the K block is MMA-bound
+  // and the ring is one stage shorter.
+  static const bool no_uneven = getenv("ICP_UNEVEN_N") == nullptr;
+  if (!no_uneven && getenv("ICP_CONV_V1") == nullptr && kh * kw == 1 && (cout + 255) / 256 < L.n_tiles) {
+    n_tile = 256;
+    L.n_tiles = (cout + 255) / 256;
+  }
   const int num_kb = kh * kw * cb;
   const size_t stage_bytes = conv_stage_bytes(n_tile, rb);
   static const bool conv_v1 = getenv("ICP_CONV_V1") != nullptr;     // one tile per CTA (bring-up version)
@@ -543,6 +552,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.tail_rb = tail_rb;
   a.row_bytes = rb;
   a.n_tile = n_tile;
+  a.cout = cout;
   a.tmem_cols = pow2_cols(n_tile);
   a.stages = stages;
   a.im2col = im2col ? 1 : 0;
