@@ -21,7 +21,7 @@ def rows(path):
         units[x["Metric Name"]] = x["Metric Unit"]
     rs = [out[k] for k in sorted(out, key=int)]
     # keep the LAST forward only: a forward starts at its conv0 launch and ends at the main head_kernel
-    starts = [i for i, x in enumerate(rs) if "conv0_kernel" in x["Kernel Name"]]
+    starts = [i for i, x in enumerate(rs) if "conv0" in x["Kernel Name"]]
     if starts:
         rs = rs[starts[-1]:]
     return rs, units
