@@ -284,8 +284,8 @@ def main():
         conv_fl = sum(fl for (nm, kind, fl, by) in table if kind == 1) * B
         n_conv = sum(1 for t in table if t[1] == 1)
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_persistent_kernel / conv_igemm_kernel / conv_halo_kernel "
-                                                 "(tcgen05 implicit-GEMM family, all conv launches but conv0)",
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_persistent_kernel (63 launches) / conv_halo_kernel (2): the "
+                                                 "tcgen05 implicit-GEMM family, all conv launches but conv0",
                     "achieved": achieved,
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                     "peak_source": peaks["source"] + " burst bf16 (MEASURED_PEAKS.json)",
