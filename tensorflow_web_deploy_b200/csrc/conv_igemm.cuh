@@ -403,9 +403,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // Every tile's K blocks: block -1 is the bias block (only the [n_tile x 16] shift tile travels, into the stage's
 // W slot; the A producer just arrives), blocks 0..num_kb-1 the filter taps x channel blocks.
 // ---------------------------------------------------------------------------------------------------
+// kCluster: launched as 2-CTA clusters.  The two CTAs own the two M tiles of a pair (same N tile, same K blocks); each
+// loads HALF of every weight tile and multicasts it into both CTAs' shared memory, so the weight bytes crossing
+// L2->SM — the larger half of the traffic of the tap-heavy layers, which are bound by exactly that (profiles/
+// r01_epilogue.md) — halve.  A stage is free only when BOTH CTAs' MMAs have released it (tcgen05.commit multicast onto
+// both empty barriers), because the peer writes into it.
+template <bool kCluster>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                              const __grid_constant__ CUtensorMap tm_a_tail, const __grid_constant__ CUtensorMap tm_b_tail,
+                             const __grid_constant__ CUtensorMap tm_b_half, const __grid_constant__ CUtensorMap tm_b_tail_half,
                              const __grid_constant__ CUtensorMap tm_bias,
                              const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                              const __grid_constant__ CUtensorMap tm_o64, const __grid_constant__ CUtensorMap tm_o64_2,
@@ -432,11 +439,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   auto tmem_empty = [&](int i) { return acc_bar + 16u + 8u * i; };
   const uint32_t tmem_slot = acc_bar + 32u;
 
-  const int total_tiles = m_tiles * n_tiles;
+  // work item t -> (M tile or, in a cluster, pair of M tiles; N tile).  tile_of(t) = this CTA's M tile.
+  uint32_t crank = 0;
+  if constexpr (kCluster) crank = ptx::cluster_ctarank();
+  const int total_tiles = (kCluster ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
   const int num_kb = a.taps * a.cblocks;
   const bool narrow_tail = a.tail_rb != a.row_bytes;
-  const int first = static_cast<int>(blockIdx.x);
-  const int step = static_cast<int>(gridDim.x);
+  const int first = static_cast<int>(blockIdx.x) / (kCluster ? 2 : 1);
+  const int step = static_cast<int>(gridDim.x) / (kCluster ? 2 : 1);
+  auto tile_m0 = [&](int t) { return ((t / n_tiles) * (kCluster ? 2 : 1) + static_cast<int>(crank)) * kBM; };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
@@ -444,13 +455,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     ptx::prefetch_tmap(&tm_bias);
     ptx::prefetch_tmap(&tm_a_tail);
     ptx::prefetch_tmap(&tm_b_tail);
+    ptx::prefetch_tmap(&tm_b_half);
+    ptx::prefetch_tmap(&tm_b_tail_half);
     ptx::prefetch_tmap(&tm_o);
     ptx::prefetch_tmap(&tm_o2);
     ptx::prefetch_tmap(&tm_o64);
     ptx::prefetch_tmap(&tm_o64_2);
     for (int s = 0; s < a.stages; ++s) {
       ptx::mbar_init(full_bar(s), 2);          // arrivals per stage: the A producer and the W producer
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), kCluster ? 2 : 1);   // cluster: both CTAs' MMA issuers release a stage
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
@@ -468,6 +481,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster) ptx::cluster_sync();   // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
 
@@ -489,7 +503,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       if (++s == a.stages) { s = 0; ph ^= 1u; sa = base; }
     };
     for (int t = first; t < total_tiles; t += step) {
-      const int m0 = (t / n_tiles) * kBM;
+      const int m0 = tile_m0(t);
       int bw = 0, bh = 0, bn = 0;
       if (a.im2col) {
         const int q = m0 % a.ow;
@@ -566,7 +580,15 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           if (ptx::elect_one()) {
             const bool tail = narrow_tail && cb == cb_last;
             ptx::mbar_expect_tx(full_bar(s), tail ? b_tail_bytes : b_bytes);
-            ptx::tma_load_2d(sb, tail ? &tm_b_tail : &tm_b, full_bar(s), kcol, n_base);
+            if constexpr (kCluster) {
+              // this CTA's half of the weight rows, delivered to both CTAs (each barrier receives both halves' bytes)
+              const uint32_t half_rows = static_cast<uint32_t>(a.n_tile) >> 1;
+              ptx::tma_load_2d_mcast(sb + crank * half_rows * (tail ? static_cast<uint32_t>(a.tail_rb) : rb),
+                                     tail ? &tm_b_tail_half : &tm_b_half, full_bar(s), kcol,
+                                     n_base + static_cast<int>(crank * half_rows), static_cast<uint16_t>(3));
+            } else {
+              ptx::tma_load_2d(sb, tail ? &tm_b_tail : &tm_b, full_bar(s), kcol, n_base);
+            }
           }
           __syncwarp();
         }
@@ -594,6 +616,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     int s = 0;
     uint32_t ph = 0;
     uint32_t su = base_units;                                              // stage start, 16-byte units
+    auto commit_empty = [&](int s_) {
+      if constexpr (kCluster) ptx::umma_commit_mcast(empty_bar(s_), static_cast<uint16_t>(3));
+      else ptx::umma_commit(empty_bar(s_));
+    };
     auto advance = [&]() {
       su += stage_units;
       if (++s == a.stages) { s = 0; ph ^= 1u; su = base_units; }
@@ -608,7 +634,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         ptx::umma_f16(tacc, d_ones, hi_32 | (su + a_units), idesc, 0u);
-        ptx::umma_commit(empty_bar(s));
+        commit_empty(s);
       }
       __syncwarp();
       advance();
@@ -641,9 +667,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           issue_block(su0, cb0);
-          ptx::umma_commit(empty_bar(s0));
+          commit_empty(s0);
           issue_block(su, cb);
-          ptx::umma_commit(empty_bar(s));
+          commit_empty(s);
         }
         __syncwarp();
         if (++cb == a.cblocks) cb = 0;
@@ -655,7 +681,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         ICP_STAMP(a.dbg, 2, it, lane == 0);
         if (ptx::elect_one()) {
           issue_block(su, cb);
-          ptx::umma_commit(empty_bar(s));
+          commit_empty(s);
         }
         __syncwarp();
         ICP_STAMP(a.dbg, 3, it, lane == 0);
@@ -675,7 +701,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     const int row = quarter * 32 + lane;
     uint32_t lt = 0;
     for (int t = first; t < total_tiles; t += step, ++lt) {
-      const int m0 = (t / n_tiles) * kBM;
+      const int m0 = tile_m0(t);
       const int n_base = (t % n_tiles) * a.n_tile;
       // columns of this tile that exist: the weight / shift boxes of a narrower last tile are zero-filled past Cout
       // (the MMAs run at full width), the epilogue simply stops at `cols`
@@ -793,6 +819,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster) ptx::cluster_sync();   // no CTA leaves while its peer can still write its smem / barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     __syncwarp();

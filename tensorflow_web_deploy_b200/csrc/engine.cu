@@ -261,6 +261,9 @@ struct ConvLayer {
   std::string name;
   CUtensorMap tm_a, tm_b;
   CUtensorMap tm_a_tail, tm_b_tail;   // last channel block of a tap when <= 32 channels remain: 32/64-byte-row boxes
+  CUtensorMap tm_b_half, tm_b_tail_half;   // cluster mode: half of the weight tile's rows per box (multicast by each CTA)
+  bool cluster = false;    // 2-CTA clusters sharing every weight tile by multicast (maps built; used for big launches)
+  int cluster_min_tiles = 16;   // ... i.e. when m_tiles >= cluster_min_tiles * SMs
   CUtensorMap tm_bias;       // [cout][16] (hi, lo) halves of the BatchNorm shift: B operand of the bias MMA
   CUtensorMap tm_o, tm_o2;   // destination slices (persistent kernel's TMA-store epilogue): 16-column boxes
   CUtensorMap tm_o64, tm_o64_2;   // same, 64-column (128-byte, swizzled) boxes
@@ -538,6 +541,23 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       L.tm_a_tail = make_tm_2d(a_ptr, static_cast<uint64_t>(max_n) * in.h * in.w, cin, in.c, kBM, fmt, tail_rb);
   }
 
+  // 2-CTA clusters (weight tiles multicast, each CTA fetching half the rows).  MEASURED at batch 128: conv4 0.1984 ->
+  // 0.1895 ms and the K=1024 N=256 GEMM 0.2666 -> 0.2616, but the 35x35 5x5 0.0638 -> 0.0704 and every launch with
+  // only a few tiles per SM slower (2.548 vs 2.480 ms/step when used everywhere): the lock-step of the two CTAs and
+  // the coarser work items cost more than the weight bytes save unless the weight tile is most of the traffic and
+  // there are many waves.  So: wide tiles only, and only when a launch has >= 16 tiles per SM (decided per launch).
+  // ICP_NO_CLUSTER=1 / ICP_CLUSTER_ALL=1 for A/B runs.
+  static const bool no_cluster = getenv("ICP_NO_CLUSTER") != nullptr;
+  static const bool cluster_all = getenv("ICP_CLUSTER_ALL") != nullptr;
+  L.cluster = persistent && !no_cluster && num_kb >= 2 && (cluster_all || n_tile >= 160);
+  L.cluster_min_tiles = cluster_all ? 0 : 16;
+  L.tm_b_half = L.tm_b;
+  L.tm_b_tail_half = L.tm_b_tail;
+  if (L.cluster) {
+    L.tm_b_half = make_tm_2d(d_w, cout, kp, kp, n_tile / 2, fmt, rb);
+    L.tm_b_tail_half = tail_rb != rb ? make_tm_2d(d_w, cout, kp, kp, n_tile / 2, fmt, tail_rb) : L.tm_b_half;
+  }
+
   ConvArgs& a = L.args;
   a.m_total = 0;
   a.oh = oh;
@@ -588,7 +608,8 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   }
   if (!g_conv_attr_set) {
     CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -611,9 +632,29 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
   a.m_total = n * L.pix_per_image;
   const int m_tiles = (a.m_total + kBM - 1) / kBM;
   if (L.persistent) {
+    if (L.cluster && m_tiles >= L.cluster_min_tiles * g_num_sms) {
+      const int items = ((m_tiles + 1) / 2) * L.n_tiles;
+      const int max_clusters = g_num_sms / 2;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * (items < max_clusters ? items : max_clusters));
+      cfg.blockDim = dim3(kPersistThreads);
+      cfg.dynamicSmemBytes = L.smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true>, L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half,
+                            L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles));
+      return;
+    }
     const int total = m_tiles * L.n_tiles;
-    conv_igemm_persistent_kernel<<<total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st>>>(
-        L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
+    conv_igemm_persistent_kernel<false><<<total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st>>>(
+        L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64,
+        L.tm_o64_2, a, m_tiles, L.n_tiles);
   } else {
     dim3 grid(m_tiles, L.n_tiles);
     conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_bias, a);

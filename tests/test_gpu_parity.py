@@ -184,6 +184,7 @@ OPT_IN_ENVS = [
     pytest.param({"ICP_STEM_CHUNK": "1"}, id="stem_in_passes"),
     pytest.param({"ICP_NO_NARROW_TAIL": "1"}, id="full_width_channel_tails"),
     pytest.param({"ICP_UNEVEN_N": "1"}, id="uneven_n_tiles"),
+    pytest.param({"ICP_CLUSTER_ALL": "1"}, id="two_cta_clusters_everywhere"),
 ]
 
 
