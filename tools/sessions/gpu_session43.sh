@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+D=tensorflow_web_deploy_b200/_ab
+for i in 1 2; do
+  timeout 300 python tools/gpu_bringup.py speed --precision bf16 --n 128 --graph | grep SPEED | sed "s/^/CUR /"
+  for v in GROUP2 NOSW G2NOSW; do
+    ICP_AB_LIB=$D/lib_$v.so timeout 300 python tools/gpu_bringup.py speed --precision bf16 --n 128 --graph | grep SPEED | sed "s/^/$v /"
+  done
+done
+for L in c35_5x5_48_64 c17_1x7_192 gemm_k1024_n256; do
+  timeout 300 python tools/gpu_bringup.py layer --name $L --reps 10 --n 64 | grep LAYER | sed 's/^/CUR /'
+  for v in GROUP2 NOSW G2NOSW; do
+    ICP_AB_LIB=$D/lib_$v.so timeout 300 python tools/gpu_bringup.py layer --name $L --reps 10 --n 64 | grep LAYER | sed "s/^/$v /"
+  done
+done
+ICP_AB_LIB=$D/lib_G2NOSW.so timeout 300 python tools/gpu_bringup.py conv > gpurun_out/conv_cases.log 2>&1; echo "conv rc=$?"; grep -E "BAD|EXC" gpurun_out/conv_cases.log | head

@@ -1,0 +1,18 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+run() { local name=$1; shift; local t=$1; shift
+  echo "=== $name" | tee -a gpurun_out/session5.log
+  timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
+  echo "=== $name rc=$?" | tee -a gpurun_out/session5.log
+  tail -n 60 "gpurun_out/$name.log" >> gpurun_out/session5.log
+}
+run conv_cases 300 python tools/gpu_bringup.py conv
+run tower_fp16 300 python tools/gpu_bringup.py tower --precision fp16 --n 2
+run profile_b128 300 python tools/gpu_bringup.py profile --n 128 --precision bf16
+run v1_profile_b128 300 env ICP_CONV_V1=1 python tools/gpu_bringup.py profile --n 128 --precision bf16
+run speed_b128_graph 300 python tools/gpu_bringup.py speed --precision bf16 --n 128 --graph
+run speed_b1_graph 300 python tools/gpu_bringup.py speed --precision bf16 --n 1 --graph --iters 50
+run pytest_gpu 900 python -m pytest tests -x -q -m gpu
+run bench1 600 python bench.py --gpus 1 --steps 20 --warmup 3
+grep -E "^===|CASE.*(BAD|EXC)|max \|dprob|PROFILE|SPEED|passed|failed|^\{" gpurun_out/session5.log | cut -c1-1500 | tail -60
