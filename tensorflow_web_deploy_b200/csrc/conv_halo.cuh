@@ -58,6 +58,7 @@ struct HaloArgs {
   int relu;
   void* out;
   int ldo, coff;
+  int epi_direct;       // 1: epilogue threads store their 32 columns straight from registers (no staging, no barriers)
   long long* dbg;       // optional timeline buffer (CTA 0 only), same rows as the persistent kernel (tools/timeline.py)
 };
 
@@ -343,6 +344,35 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int cp, first, np;
         geom(c0, cp, first, np);
         if (more) issue(vn, nj, nc);
+        if (a.epi_direct) {
+          // Barrier-free variant: every thread maps its own row, converts its <= 32 columns and writes them with
+          // 16-byte stores (64 contiguous bytes per thread).  MEASURED on conv1 / conv2 against the staged variant
+          // below: see profiles/r01_epilogue.md.
+          const int p = p0 + j * kBM + row;
+          int oy = p / a.wp;
+          const int ox = p - oy * a.wp;
+          int im = img;
+          if (a.tall) { im = oy / a.oh; oy -= im * a.oh; }
+          const bool valid = (im < a.n_images) && (oy < a.oh) && (ox < a.ow);
+          const int pixd = a.transpose_out ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
+          uint32_t q[16];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+            if (jj < np) convert16(&v[16 * jj], &q[8 * jj], a.relu != 0, a.fmt);
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(pixd) * a.ldo +
+                                                  a.coff + n_base + c0 + 16 * first);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              if (jj < np) {
+                dst[2 * jj] = make_uint4(q[8 * jj], q[8 * jj + 1], q[8 * jj + 2], q[8 * jj + 3]);
+                dst[2 * jj + 1] = make_uint4(q[8 * jj + 4], q[8 * jj + 5], q[8 * jj + 6], q[8 * jj + 7]);
+              }
+            }
+          }
+          ICP_STAMP(a.dbg, 9, lt * a.T + j, et == 0);
+          return;
+        }
         int pix = -1;
         if (c0 == 0 && grp == 0) {               // one thread per row maps the sub-tile's positions to output pixels
           const int p = p0 + j * kBM + row;

@@ -496,6 +496,9 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       h.acc_cols = T * n_tile; h.acc_sets = acc_sets; h.tmem_cols = pow2_cols(acc_sets * T * n_tile);
       h.w_resident = resident ? 1 : 0; h.w_bytes = w_bytes; h.b_stages = b_stages;
       h.fmt = fmt; h.relu = relu ? 1 : 0;
+      // narrow tiles store straight from registers (conv1, 32 channels: 0.147 -> 0.117 ms); at 64 channels the 16-byte
+      // stores of one warp touch 32 lines per instruction and the staged copy-out is as fast (conv2 0.165 vs 0.169 ms)
+      h.epi_direct = getenv("ICP_HALO_DIRECT") ? atoi(getenv("ICP_HALO_DIRECT")) : (n_tile <= 32 ? 1 : 0);
       h.out = out.p; h.ldo = out.c; h.coff = out_coff; 
       L.smem = smem;
       if (!g_halo_attr_set) {

@@ -185,6 +185,8 @@ OPT_IN_ENVS = [
     pytest.param({"ICP_NO_NARROW_TAIL": "1"}, id="full_width_channel_tails"),
     pytest.param({"ICP_UNEVEN_N": "1"}, id="uneven_n_tiles"),
     pytest.param({"ICP_CLUSTER_ALL": "1"}, id="two_cta_clusters_everywhere"),
+    pytest.param({"ICP_HALO_DIRECT": "1", "ICP_HALO_MIN_W": "30"}, id="halo_direct_stores"),
+    pytest.param({"ICP_HALO_DIRECT": "0"}, id="halo_staged_stores"),
 ]
 
 
