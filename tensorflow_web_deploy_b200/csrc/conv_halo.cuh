@@ -62,6 +62,9 @@ struct HaloArgs {
   long long* dbg;       // optional timeline buffer (CTA 0 only), same rows as the persistent kernel (tools/timeline.py)
 };
 
+// kDirect: the epilogue variant is a compile-time choice — carrying both in one kernel cost the direct path 20 %
+// (conv1 0.120 -> 0.147 ms when a third variant was added experimentally).
+template <bool kDirect>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_bias, const HaloArgs a) {
@@ -344,7 +347,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int cp, first, np;
         geom(c0, cp, first, np);
         if (more) issue(vn, nj, nc);
-        if (a.epi_direct) {
+        if constexpr (kDirect) {
           // Barrier-free variant: every thread maps its own row, converts its <= 32 columns and writes them with
           // 16-byte stores (64 contiguous bytes per thread).  MEASURED on conv1 / conv2 against the staged variant
           // below: see profiles/r01_epilogue.md.
@@ -371,8 +374,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
           }
           ICP_STAMP(a.dbg, 9, lt * a.T + j, et == 0);
-          return;
-        }
+        } else {
         int pix = -1;
         if (c0 == 0 && grp == 0) {               // one thread per row maps the sub-tile's positions to output pixels
           const int p = p0 + j * kBM + row;
@@ -417,6 +419,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (px[i] >= 0) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(px[i]) * a.ldo) = val[i];
         }
         ICP_STAMP(a.dbg, 9, lt * a.T + j, et == 0);
+        }
       };
       auto release = [&]() {                       // accumulator fully read: hand it back to the MMA issuer
         ptx::tc_fence_before();
