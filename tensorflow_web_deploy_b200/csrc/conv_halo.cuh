@@ -64,7 +64,9 @@ struct HaloArgs {
 
 // kDirect: the epilogue variant is a compile-time choice — carrying both in one kernel cost the direct path 20 %
 // (conv1 0.120 -> 0.147 ms when a third variant was added experimentally).
-template <bool kDirect>
+// kStem: the configuration of the two stem layers that use this kernel by default — weights resident, per-image bands,
+// no transposed store — as compile-time constants (the streamed / tall / transposed paths are the opt-in ones).
+template <bool kDirect, bool kStem>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_bias, const HaloArgs a) {
@@ -75,6 +77,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool f_resident = kStem ? true : a.w_resident != 0;
+  const bool f_tall = kStem ? false : a.tall != 0;
+  const bool f_transpose = kStem ? false : a.transpose_out != 0;
   const uint32_t rb = static_cast<uint32_t>(a.row_bytes);
   const uint32_t strip0 = base;
   const uint32_t wbase = base + static_cast<uint32_t>(a.nstrips) * a.strip_bytes;   // resident weights or ring
@@ -99,9 +104,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const uint32_t tap_bytes = static_cast<uint32_t>(a.n_tile) * rb;
   const uint32_t b_stride = (tap_bytes + 1023u) & ~1023u;
   // padded-grid positions that hold outputs: per image, or over the whole batch in tall mode
-  const int positions = a.tall ? a.n_images * a.oh * a.wp : a.oh * a.wp;
-  const int bands_per_image = a.tall ? (positions + kBM * a.T - 1) / (kBM * a.T) : a.bands_per_image;
-  const int total_bands = a.tall ? bands_per_image : bands_per_image * a.n_images;
+  const int positions = f_tall ? a.n_images * a.oh * a.wp : a.oh * a.wp;
+  const int bands_per_image = f_tall ? (positions + kBM * a.T - 1) / (kBM * a.T) : a.bands_per_image;
+  const int total_bands = f_tall ? bands_per_image : bands_per_image * a.n_images;
   const int total_items = total_bands * a.n_tiles;          // work item = (band, N tile), N fastest
 
   if (warp == 0 && lane == 0) {
@@ -146,7 +151,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int band = item / a.n_tiles;
-      const int img = a.tall ? 0 : band / bands_per_image;
+      const int img = f_tall ? 0 : band / bands_per_image;
       const int p0 = (band - img * bands_per_image) * kBM * a.T;
       const int h_first = p0 / a.wp;
       for (int c = 0; c < a.chunks; ++c) {
@@ -163,7 +168,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 6) {
     // ---------------- weight producer ----------------
-    if (a.w_resident) {
+    if (f_resident) {
       if (ptx::elect_one()) {
         ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes + static_cast<uint32_t>(a.n_tile) * 32u);
         ptx::tma_load_2d(bias_base, &tm_bias, w_full, 0, 0);
@@ -209,12 +214,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     __syncwarp();
     const uint32_t tap_units = tap_bytes >> 4;
     const uint32_t sub_units = (static_cast<uint32_t>(kBM) * rb) >> 4;
-    if (a.w_resident) ptx::mbar_wait(w_full, 0);
+    if (f_resident) ptx::mbar_wait(w_full, 0);
     uint32_t s = 0, ph = 0, sb = 0, phb = 0, as = 0, pha = 0;
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int band = item / a.n_tiles;
-      const int img = a.tall ? 0 : band / bands_per_image;
+      const int img = f_tall ? 0 : band / bands_per_image;
       const int p0 = (band - img * bands_per_image) * kBM * a.T;
       const int h_first = p0 / a.wp;
       const uint32_t local_units = (static_cast<uint32_t>(p0 - h_first * a.wp) * rb) >> 4;
@@ -224,7 +229,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t tacc0 = tmem_base + as * a.acc_cols;
       // every sub-tile's accumulator starts at the BatchNorm shift: ones tile x (hi, lo) shift tile, K = 16
-      if (a.w_resident) {
+      if (f_resident) {
         if (ptx::elect_one())
           for (int j = 0; j < nsub; ++j) ptx::umma_f16(tacc0 + j * a.n_tile, d_ones, desc32 | (bias_base >> 4), idesc, 0u);
         __syncwarp();
@@ -244,7 +249,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ptx::tc_fence_after();
         ICP_STAMP(a.dbg, 2, it, lane == 0);
         const uint32_t a_units0 = ((strip0 + s * a.strip_bytes) >> 4) + local_units;
-        if (a.w_resident) {
+        if (f_resident) {
           if (ptx::elect_one()) {
             uint32_t b_units = (wbase >> 4) + static_cast<uint32_t>(c * taps) * tap_units;
             for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
@@ -318,7 +323,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lt) {
       const int band = item / a.n_tiles;
       const int n_base = (item - band * a.n_tiles) * a.n_tile;
-      const int img = a.tall ? 0 : band / bands_per_image;
+      const int img = f_tall ? 0 : band / bands_per_image;
       const int p0 = (band - img * bands_per_image) * kBM * a.T;
       int nsub = (positions - p0 + kBM - 1) / kBM;
       if (nsub > a.T) nsub = a.T;
@@ -355,9 +360,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           int oy = p / a.wp;
           const int ox = p - oy * a.wp;
           int im = img;
-          if (a.tall) { im = oy / a.oh; oy -= im * a.oh; }
+          if (f_tall) { im = oy / a.oh; oy -= im * a.oh; }
           const bool valid = (im < a.n_images) && (oy < a.oh) && (ox < a.ow);
-          const int pixd = a.transpose_out ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
+          const int pixd = f_transpose ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
           uint32_t q[16];
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj)
@@ -381,9 +386,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           int oy = p / a.wp;                     // tall mode: row over all images
           const int ox = p - oy * a.wp;
           int im = img;
-          if (a.tall) { im = oy / a.oh; oy -= im * a.oh; }
+          if (f_tall) { im = oy / a.oh; oy -= im * a.oh; }
           if ((im < a.n_images) && (oy < a.oh) && (ox < a.ow))
-            pix = a.transpose_out ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
+            pix = f_transpose ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
         }
         uint32_t q[16];
 #pragma unroll

@@ -502,8 +502,10 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       h.out = out.p; h.ldo = out.c; h.coff = out_coff; 
       L.smem = smem;
       if (!g_halo_attr_set) {
-        CK(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CK(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CK(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int dev = 0;
         CK(cudaGetDevice(&dev));
         CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -628,10 +630,15 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     h.n_images = n;
     const int bands = h.tall ? (n * h.oh * h.wp + kBM * h.T - 1) / (kBM * h.T) : h.bands_per_image * n;
     const int items = bands * h.n_tiles;
-    if (h.epi_direct)
-      conv_halo_kernel<true><<<items < g_num_sms ? items : g_num_sms, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
-    else
-      conv_halo_kernel<false><<<items < g_num_sms ? items : g_num_sms, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
+    const unsigned grid = static_cast<unsigned>(items < g_num_sms ? items : g_num_sms);
+    const bool stem = h.w_resident && !h.tall && !h.transpose_out;
+    if (h.epi_direct) {
+      if (stem) conv_halo_kernel<true, true><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
+      else conv_halo_kernel<true, false><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
+    } else {
+      if (stem) conv_halo_kernel<false, true><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
+      else conv_halo_kernel<false, false><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
+    }
     CK(cudaGetLastError());
     return;
   }
