@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: images/sec of the Inception-v3 classify path on synthetic 299x299x3.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision bf16|fp16]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision fp16|bf16] [--strong]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one batch of 128 images per GPU (BASELINE.json configs[2]/[3]: batch=128 bf16 per B200,
-1024 over 8) through the whole tower: conv0 + 93 tcgen05 implicit-GEMM convs + pools + softmax/top-5.
-Multi-GPU = pure data parallel, weights replicated, one NCCL all-gather of the [128,C] probabilities
-per step.  Prints ONE JSON line on rank 0.
+One "step" = one batch of 128 images per GPU (BASELINE.json configs[2]/[3]: batch=128 per B200, 1024 over 8)
+through the whole tower: conv0 + 93 tcgen05 implicit-GEMM convs + pools + softmax/top-5.  Multi-GPU = pure data
+parallel through the repo's sharding API (sharding.ShardedTower.step_device): weights replicated, one NCCL all-gather
+of the [128,C] probabilities per step on a side stream; --strong fixes the global batch at 1024
+ instead of 128 per GPU.  Prints ONE JSON line on rank 0.
+
+Default storage type is fp16: it is the mode that meets the north_star's 1e-3 score bar (the `parity` object of the
+line is measured in-run, on images of the timed batch, against the CPU oracle); --precision bf16 (the dtype
+BASELINE configs[2] names) runs the same kernels at the same speed with ~2e-3 score error.
 
 value     images/s, whole job, inputs resident in HBM, CUDA events on the launching stream, max over ranks
 e2e       images/s through Engine.forward_u8 (public API): pinned-host uint8 batch -> H2D -> tower -> D2H probs
@@ -48,12 +53,18 @@ def measured_peaks():
 
 
 def conv_traffic_per_launch(batch, precision):
-    """DRAM bytes per conv launch from the committed ncu capture (only valid for the configuration it was taken at)."""
-    p = os.path.join(ROOT, "profiles", "r01_conv_traffic_final.json")
-    if batch != 128 or not os.path.exists(p):
+    """(DRAM bytes per conv launch, note) from the newest committed ncu capture; only valid for the configuration
+    it was taken at (batch 128; DRAM traffic is the same for fp16 and bf16 storage)."""
+    if batch != 128:
         return None
-    d = json.load(open(p))
-    return d["dram_bytes_total"] / d["conv_launches_per_step"]
+    for name in ("r02_conv_traffic_final.json", "r01_conv_traffic_final.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            return (d["dram_bytes_total"] / d["conv_launches_per_step"],
+                    "dram__bytes_read+write per launch, mean over the %d conv launches of one step, from the committed ncu "
+                    "capture profiles/%s (batch 128)" % (d["conv_launches_per_step"], name))
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -160,15 +171,37 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def parity_in_run(gpu_probs, x_images, precision, threads):
+    """max |dprob| and top-5 identity of the TIMED configuration against the CPU oracle, on images of the timed batch."""
+    import torch
+    from oracle import inception_oracle as O
+    from tensorflow_web_deploy_b200 import weights
+    global _ORACLE_W
+    torch.set_num_threads(threads)
+    if _ORACLE_W is None:
+        _ORACLE_W = weights.synthetic_weights(NUM_CLASSES)
+    ref = O.Tower(_ORACLE_W).forward(x_images, NUM_CLASSES, with_aux=False)[1]
+    err = float(np.abs(gpu_probs - ref).max())
+    top_eq = bool((np.argsort(-gpu_probs, axis=1, kind="stable")[:, :5] == O.top_k(ref, 5)[1]).all())
+    tol = 1e-3
+    return {"images": int(x_images.shape[0]), "max_abs_dprob": err, "top5_equal": top_eq, "tolerance": tol,
+            "pass": bool(err <= tol and top_eq), "dtype": precision,
+            "against": "CPU oracle (torch fp32 restatement, pinned to the reference's own graph: tests/test_oracle_pin.py)",
+            "what": "probabilities of the first %d images of the timed batch, read back after the last timed step" % x_images.shape[0]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--precision", default="fp16", choices=["bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--strong", action="store_true", help="fixed global batch of 1024 (BASELINE configs[3]) split over the GPUs")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra sustained run (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,24 +224,28 @@ def main():
         g.build()
     if world > 1:
         dist.barrier()
-    from tensorflow_web_deploy_b200 import engine, weights
+    from tensorflow_web_deploy_b200 import engine, sharding, weights
 
-    B, C = args.batch, NUM_CLASSES
+    C = NUM_CLASSES
+    GLOBAL_STRONG = 1024
+    rows = GLOBAL_STRONG // world if args.strong else args.batch          # rows of a step this rank owns
+    B = min(rows, args.batch)                                             # images per tower launch (one GPU's sweet spot)
+    chunks = rows // B
     wpath = os.path.join(tempfile.gettempdir(), "icp_bench_c%d_rank%d.icpw" % (C, rank))
     weights.save_blob(wpath, weights.synthetic_weights(C))
     eng = engine.Engine(wpath, C, device=local_rank, max_batch=B, precision=args.precision, use_cuda_graph=True)
     dev = torch.device("cuda", local_rank)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     x_dev = torch.empty((B, 299, 299, 3), device=dev, dtype=torch.float32).uniform_(-1, 1, generator=gen)
-    probs = torch.empty((B, C), device=dev, dtype=torch.float32)
-    gathered = torch.empty((B * world, C), device=dev, dtype=torch.float32)
     stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: the engine enqueues on the handle we pass
     torch.cuda.set_stream(stream)
+    tower = sharding.ShardedTower(None, C, dist=dist if world > 1 else None, device=dev, engine=eng)
+
+    last = [None]
 
     def step():
-        eng.forward_device(x_dev.data_ptr(), B, probs.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, probs)      # the path's only collective: [B,C] probabilities
+        for _ in range(chunks):                     # strong scaling at small N: several sweet-spot batches per step
+            last[0] = tower.step_device(x_dev, stream)   # tower on `stream`, all-gather of [B,C] probs on the side stream
 
     def sync_all():
         torch.cuda.synchronize()
@@ -227,36 +264,88 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    last[0].wait(stream)                            # the timed region ends when the last all-gather has landed
     e1.record(stream)
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    launches = eng.launches_per_forward * args.steps
+    head_launches = eng.launches_per_forward
+    launches = head_launches * args.steps * chunks
+    timed_probs = last[0].probs[:B].cpu().numpy() if world == 1 else last[0].probs[rank * B:(rank + 1) * B].cpu().numpy()
+    burst_clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- sustained run: >= 2 s of back-to-back steps, clocks / power sampled throughout ----------------
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / (ms_total / args.steps)) + 1)
+        s2 = ClockSampler(local_rank)
+        sync_all()
+        if rank == 0:
+            s2.start()
+        e0.record(stream)
+        for _ in range(n_sus):
+            step()
+        last[0].wait(stream)
+        e1.record(stream)
+        sync_all()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            c2 = s2.stop()
+            pw = [float(x[2]) for x in s2.samples if x[2].replace(".", "").isdigit()]
+            sustained = {"steps": n_sus, "seconds": float(ms2.item()) * 1e-3, "ms_per_step": float(ms2.item()) / n_sus,
+                         "value": rows * world * n_sus / (float(ms2.item()) * 1e-3), "clocks": c2,
+                         "power_w_median": float(np.median(pw)) if pw else None, "power_w_max": max(pw) if pw else None}
 
     # ---------------- end-to-end through the public API: pinned host u8 -> H2D -> tower -> D2H ----------------
     # Two alternating pinned host batches through Engine.submit_u8 / collect (two slots): the PCIe copy of batch
     # i+1 overlaps the tower of batch i; every step's input crosses PCIe and its probabilities/top-5 come back.
+    # At N > 1 the probabilities stay on the device (submit_u8_device_out), are all-gathered on a side stream and
+    # the gathered [N*B, C] result is copied to pinned host memory — no host round trip before the collective.
+    sampler_e = ClockSampler(local_rank)
     x_hosts = [torch.randint(0, 256, (B, 299, 299, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     x_nps = [t.numpy() for t in x_hosts]
     outs = [(torch.empty((B, C), dtype=torch.float32).pin_memory().numpy(),
              torch.empty((B, 5), dtype=torch.float32).pin_memory().numpy(),
              torch.empty((B, 5), dtype=torch.int32).pin_memory().numpy()) for _ in range(2)]
+    if world > 1:
+        ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+        comm = torch.cuda.Stream(device=dev)
+        p_dev = [torch.empty((B, C), dtype=torch.float32, device=dev) for _ in range(2)]
+        g_dev = [torch.empty((B * world, C), dtype=torch.float32, device=dev) for _ in range(2)]
+        g_host = [torch.empty((B * world, C), dtype=torch.float32).pin_memory() for _ in range(2)]
+        g_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_submit(i):
+        s_ = i & 1
+        if world == 1:
+            eng.submit_u8(x_nps[s_], s_, 5, outs[s_])
+            return
+        eng.submit_u8_device_out(x_nps[s_], s_, p_dev[s_].data_ptr())
+        ev = torch.cuda.Event()
+        ev.record(ext)
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            dist.all_gather_into_tensor(g_dev[s_], p_dev[s_])
+            g_host[s_].copy_(g_dev[s_], non_blocking=True)
+            g_done[s_].record(comm)
+
+    def e2e_collect(i):
+        s_ = i & 1
+        eng.collect(s_)
+        if world > 1:
+            g_done[s_].synchronize()
 
     def e2e_loop(steps):
-        eng.submit_u8(x_nps[0], 0, 5, outs[0])
-        for i in range(1, steps):
-            eng.submit_u8(x_nps[i & 1], i & 1, 5, outs[i & 1])
-            p, v, ix = eng.collect((i - 1) & 1)
-            if world > 1:
-                probs.copy_(torch.from_numpy(p), non_blocking=False)
-                dist.all_gather_into_tensor(gathered, probs)
-        p, v, ix = eng.collect((steps - 1) & 1)
-        if world > 1:
-            probs.copy_(torch.from_numpy(p), non_blocking=False)
-            dist.all_gather_into_tensor(gathered, probs)
-            torch.cuda.synchronize()
+        total = steps * chunks
+        e2e_submit(0)
+        for i in range(1, total):
+            e2e_submit(i)
+            e2e_collect(i - 1)
+        e2e_collect(total - 1)
 
     e2e_loop(args.warmup)
     sync_all()
@@ -265,18 +354,19 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_ips = B * world * args.steps / float(e2e_s.item())
+    e2e_ips = rows * world * args.steps / float(e2e_s.item())
     # synchronous single-call variant (no overlap), for reference
     t0 = time.perf_counter()
     for _ in range(max(3, args.steps // 4)):
         eng.forward_u8(x_nps[0], 5)
     e2e_sync_ips = B * max(3, args.steps // 4) / (time.perf_counter() - t0)
-    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peaks = measured_peaks()
-        value = B * world * args.steps / (ms_total * 1e-3)
-        # ---------------- roofline of the dominant kernel (conv_igemm_kernel), live ----------------
+        value = rows * world * args.steps / (ms_total * 1e-3)
+        cores = min(host_cores(), 32)
+        parity = parity_in_run(timed_probs[:8], x_dev[:8].cpu().numpy(), args.precision, cores)
+        # ---------------- roofline of the dominant kernel family (tcgen05 implicit-GEMM convs), live ----------------
         eng.forward(x_dev[:B].cpu().numpy())                    # resident input for the profiled passes
         per_op = eng.profile_forward(B, reps=3)
         table = eng.op_table()
@@ -284,63 +374,104 @@ def main():
         conv_fl = sum(fl for (nm, kind, fl, by) in table if kind == 1) * B
         n_conv = sum(1 for t in table if t[1] == 1)
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_persistent_kernel (63 launches) / conv_halo_kernel (2): the "
-                                                 "tcgen05 implicit-GEMM family, all conv launches but conv0",
+        tr = conv_traffic_per_launch(B, args.precision)
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_persistent_kernel / conv_halo_kernel: the tcgen05 implicit-GEMM "
+                                                 "family, all conv launches but conv0",
                     "achieved": achieved,
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                    "peak_source": peaks["source"] + " burst bf16 (MEASURED_PEAKS.json)",
+                    "peak_source": peaks["source"] + " burst 16-bit dense (MEASURED_PEAKS.json; fp16 and bf16 share the pipe rate)",
                     "launches_per_step": n_conv, "avg_launch_us": 1e3 * conv_ms / n_conv,
-                    "share_of_step": conv_ms / float(per_op.sum()), "traffic": conv_traffic_per_launch(B, args.precision),
-                    "traffic_note": "dram__bytes_read+write per launch, mean over the 65 conv launches of one step, from "
-                                    "the committed ncu capture profiles/r01_conv_traffic_final.json (batch 128 bf16); "
-                                    "null for other configurations",
-                    "whole_tower_frac": value / world * FLOP_PER_IMAGE / 1e12 / peaks["bf16_tflops"]}
-        # ---------------- batch-1 latency (BASELINE configs[1]) ----------------
-        lat = engine.Engine(wpath, C, device=local_rank, max_batch=1, precision=args.precision, use_cuda_graph=True)
-        x1 = x_dev[:1].cpu().numpy()
-        dms = []
-        for i in range(203):
-            lat.forward(x1)
-            if i >= 3:
-                dms.append(lat.last_forward_ms)
-        rgb = np.random.default_rng(2).integers(0, 256, (375, 500, 3), dtype=np.uint8)
-        wall = []
-        for i in range(103):
-            t0 = time.perf_counter()
-            lat.classify_rgb8(rgb, 5)
-            if i >= 3:
-                wall.append(1e3 * (time.perf_counter() - t0))
-        latency = {"batch1_tower_device_ms_p50": float(np.median(dms)), "batch1_tower_device_ms_p99": float(np.percentile(dms, 99)),
-                   "classify_rgb8_wall_ms_p50": float(np.median(wall)), "classify_rgb8_wall_ms_p99": float(np.percentile(wall, 99))}
-        lat.close()
+                    "share_of_step": conv_ms / float(per_op.sum()), "traffic": tr[0] if tr else None,
+                    "traffic_note": (tr[1] if tr else "no committed ncu capture for this configuration"),
+                    "whole_tower_frac": value / world * FLOP_PER_IMAGE / 1e12 / peaks["bf16_tflops"],
+                    "whole_tower_frac_sustained_peak": (value / world * FLOP_PER_IMAGE / 1e12 / peaks["bf16_tflops_sustained"])
+                    if peaks.get("bf16_tflops_sustained") else None}
+        latency = None
+        if not args.no_latency:
+            latency = batch1_latency(engine, wpath, C, local_rank, args.precision, x_dev[:1].cpu().numpy())
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = min(host_cores(), 32)
             ips, secs = oracle_images_per_s(12, cores)
             cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "12 images, batch 1 each (as the reference serves), torch fp32 CPU oracle, %.1f s" % secs,
                    "p50_latency_s": secs / 12}
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": args.precision,
+                "data": "synthetic",
                 "config": {"workload": "batch=%d/GPU %s synthetic 299x299x3, full Inception-v3 tower + softmax + top-5 "
-                                       "(BASELINE configs[2]; configs[3] at 8 GPUs)" % (B, args.precision),
-                           "global_batch": B * world, "num_classes": C, "parallelism": "dp%d" % world,
-                           "collective": "all_gather probs [%d,%d] f32" % (B, C) if world > 1 else "none",
+                                       "(BASELINE configs[2]; configs[3] at 8 GPUs)%s" % (
+                                           rows, args.precision, "; fixed global batch 1024 (strong scaling)" if args.strong else ""),
+                           "global_batch": rows * world, "images_per_tower_launch": B, "num_classes": C,
+                           "parallelism": "dp%d" % world,
+                           "api": "sharding.ShardedTower.step_device (engine.forward_device + all_gather_into_tensor on a side stream)",
+                           "collective": "all_gather probs [%d,%d] f32, overlapped with the next step's tower" % (B, C) if world > 1 else "none",
                            "l2": "inputs larger than L2 (%.0f MB fp32 batch, activations ~8 GB)" % (B * 299 * 299 * 3 * 4 / 1e6),
                            "cuda_graph": True},
-                "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": B * 299 * 299 * 3,
-                        "d2h_bytes_per_step": B * C * 4 + B * 5 * 8,
-                        "api": "Engine.submit_u8/collect (icp_submit_u8, two slots: H2D of batch i+1 overlaps tower i)",
+                "e2e": {"value": e2e_ips, "unit": "images/s", "h2d_bytes_per_step": rows * 299 * 299 * 3,
+                        "d2h_bytes_per_step": (rows * C * 4 + rows * 5 * 8) if world == 1 else rows * world * C * 4,
+                        "api": "Engine.submit_u8/collect (icp_submit_u8, two slots: H2D of batch i+1 overlaps tower i)" if world == 1 else
+                               "Engine.submit_u8_device_out/collect + all_gather on a side stream + D2H of the gathered probabilities",
                         "sync_call_value": e2e_sync_ips},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-                "latency": latency,
+                "gpu_launches": launches, "parity": parity, "roofline": roofline, "cpu_baseline": cpu, "clocks": burst_clocks,
+                "sustained": sustained, "latency": latency,
                 "reference_published": {"classify_image_latency_s": 0.47, "source": "reference README.md:22, TF CPU, hardware unstated"}}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def batch1_latency(engine, wpath, C, device, precision, x1):
+    """BASELINE configs[1] and the metric's second half: batch-1 tower device time and the wall time of
+    ImagenetClassifier.classify_image(jpeg bytes) itself (decode + preprocess + tower + top-k, bytes in, tuple out)."""
+    import io
+    import tempfile
+    from PIL import Image
+    from tensorflow_web_deploy_b200 import PyClassification as P
+    lat = engine.Engine(wpath, C, device=device, max_batch=1, precision=precision, use_cuda_graph=True)
+    dms = []
+    for i in range(1003):
+        lat.forward(x1)
+        if i >= 3:
+            dms.append(lat.last_forward_ms)
+    rgb = np.random.default_rng(2).integers(0, 256, (375, 500, 3), dtype=np.uint8)
+    wall = []
+    for i in range(203):
+        t0 = time.perf_counter()
+        lat.classify_rgb8(rgb, 5)
+        if i >= 3:
+            wall.append(1e3 * (time.perf_counter() - t0))
+    lat.close()
+    out = {"batch1_tower_device_ms_p50": float(np.median(dms)), "batch1_tower_device_ms_p99": float(np.percentile(dms, 99)),
+           "classify_rgb8_wall_ms_p50": float(np.median(wall)), "classify_rgb8_wall_ms_p99": float(np.percentile(wall, 99))}
+    # classify_image(jpeg bytes): a 500x375 JPEG (the geometry of the reference's data/sample.jpg; the file itself when
+    # the committed fixture is present)
+    sample = os.path.join(ROOT, "tests", "golden", "reference_sample.jpg")
+    if os.path.exists(sample):
+        jpeg = open(sample, "rb").read()
+    else:
+        buf = io.BytesIO()
+        Image.fromarray(rgb).save(buf, "JPEG", quality=90)
+        jpeg = buf.getvalue()
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write("daisy\ndandelion\nroses\nsunflowers\ntulips\n")
+        labels = f.name
+    os.environ.setdefault("ICP_DEVICE", str(device))
+    clf = P.ImagenetClassifier(wpath, labels, device=device, precision=precision)
+    ci = []
+    for i in range(203):
+        t0 = time.perf_counter()
+        r = clf.classify_image(jpeg)
+        if i >= 3:
+            ci.append(1e3 * (time.perf_counter() - t0))
+        assert r is not None
+    out.update({"classify_image_ms_p50": float(np.median(ci)), "classify_image_ms_p99": float(np.percentile(ci, 99)),
+                "classify_image_input": "%d-byte JPEG, 500x375" % len(jpeg),
+                "classify_image_decode": getattr(clf, "decode_backend", "PIL (host libjpeg-turbo)")})
+    os.unlink(labels)
+    return out
 
 
 if __name__ == "__main__":

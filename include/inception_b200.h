@@ -77,6 +77,9 @@ int icp_forward_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* pr
 int icp_submit_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host,
                   float* topk_vals_host, int32_t* topk_idx_host, int slot);
 int icp_collect(icp_engine* e, int slot);
+/* Multi-GPU variant: the probabilities stay on the device (probs_dev float32 [n,C], caller-owned, on the engine's
+ * device) so that a collective can consume them without a host round trip; work is ordered on icp_stream(e). */
+int icp_submit_u8_device_out(icp_engine* e, const uint8_t* x_host, int n, float* probs_dev, int slot);
 
 /* Per-launch profile of the tower: op i of icp_num_ops() is one kernel launch.  icp_op_info gives its
  * reference scope name, kind (ICP_OP_*), algorithmic FLOPs and algorithmic HBM bytes per image;

@@ -19,6 +19,7 @@ from __future__ import annotations
 import io
 import logging
 import os
+import threading
 import time
 
 import numpy as np
@@ -62,6 +63,10 @@ class ImagenetClassifier(object):
         self.engine = _engine.Engine(model_def_file, num_classes=len(self.label_names), device=device, max_batch=1,
                                      precision=precision, use_cuda_graph=use_cuda_graph)
         self.top_k = min(NUM_TOP_CLASSES, len(self.label_names))
+        # The reference's tf.Session.run is thread-safe and Flask's development server / gthread workers are threaded;
+        # the engine keeps one set of staging buffers, so requests of one process are serialised here (the C ABI
+        # also locks per engine).  Cost: nothing next to the tower; throughput comes from the micro-batcher (serving/).
+        self._lock = threading.Lock()
 
     def eval_image(self, image, height, width, scope=None):
         """Compat shim for PyClassification.py:180-203: decoded uint8 HWC -> the float32 [S,S,3]
@@ -72,7 +77,8 @@ class ImagenetClassifier(object):
         try:
             start_time = time.time()
             rgb = decode_jpeg_rgb(image)
-            probs, labels = self.engine.classify_rgb8(rgb, self.top_k)
+            with self._lock:
+                probs, labels = self.engine.classify_rgb8(rgb, self.top_k)
             end_time = time.time()
             logger.info("classify_image cost %.2f secs", end_time - start_time)
             names = [self.label_names[labels[0]], self.label_names[labels[1]], self.label_names[labels[2]]]

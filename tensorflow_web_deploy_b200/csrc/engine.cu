@@ -13,6 +13,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -291,7 +292,6 @@ static int pow2_cols(int n) {
   while (c < n) c <<= 1;
   return c;
 }
-static bool g_conv_attr_set = false;
 
 // Packs HWIO fp32 weights into the K-major [cout][taps][cblocks*64] 16-bit matrix the B-operand TMA
 // reads, zero-filling the channel tail of every tap.
@@ -350,7 +350,6 @@ static std::vector<uint16_t> pack_weights_halo(const float* w, int kh, int kw, i
   return out;
 }
 
-static bool g_halo_attr_set = false;
 
 // in: NHWC buffer (pitch in.c) of which channels [in_coff, in_coff+cin) feed the conv.
 static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n, const Act& in, int in_coff, int cin,
@@ -501,16 +500,6 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       h.epi_direct = getenv("ICP_HALO_DIRECT") ? atoi(getenv("ICP_HALO_DIRECT")) : (n_tile <= 32 ? 1 : 0);
       h.out = out.p; h.ldo = out.c; h.coff = out_coff; 
       L.smem = smem;
-      if (!g_halo_attr_set) {
-        CK(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CK(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        g_halo_attr_set = true;
-      }
       return L;
     }
   }
@@ -612,15 +601,6 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     L.tm_o64 = make_tm_out(out.p, out_rows, out.c, fmt, 64);
     L.tm_o64_2 = out2 ? make_tm_out(out2->p, out_rows, out2->c, fmt, 64) : L.tm_o64;
   }
-  if (!g_conv_attr_set) {
-    CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    g_conv_attr_set = true;
-  }
   return L;
 }
 
@@ -684,8 +664,7 @@ struct Op {
   Act in, out;                    // pools
   int c = 0, in_coff = 0, out_coff = 0;   // pools: channels pooled, channel offsets in `in` / `out`
   int k = 3, stride = 1, pad = 0;
-  const float* scale = nullptr;   // AVGPOOL after a linear 1x1 projection: that layer's BN + ReLU
-  const float* shift = nullptr;
+  bool post_relu = false;         // AVGPOOL after the pool branch's 1x1 projection + BN: that layer's ReLU
   std::string name;
 };
 
@@ -719,6 +698,7 @@ struct icp_engine {
   int C = 0;
   int max_batch = 0;
   mutable std::string err;
+  mutable std::mutex mu;            // one call at a time per engine (the reference's tf.Session.run is thread-safe)
   DevicePool pool;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -743,11 +723,12 @@ struct icp_engine {
   Act final_act;                    // 8x8x2048
   float *d_fc_w = nullptr, *d_fc_b = nullptr;
   float *d_logits = nullptr, *d_probs = nullptr, *d_topk_val = nullptr;
+  float *d_feat = nullptr, *d_part = nullptr;       // head: pooled features [n][2048], partial logits [n][8][C<=32]
   int* d_topk_idx = nullptr;
   // aux head
   std::vector<Op> aux_ops;
   Act aux_feat;                     // 1x1x768
-  float *d_aux_w = nullptr, *d_aux_b = nullptr, *d_aux_logits = nullptr;
+  float *d_aux_w = nullptr, *d_aux_b = nullptr, *d_aux_logits = nullptr, *d_aux_feat = nullptr, *d_aux_part = nullptr;
   std::map<std::string, Endpoint> endpoints;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   static constexpr int kLanes = 5;
@@ -858,9 +839,9 @@ struct Builder {
   // All 1x1 convs of a block read the same input, so they run as ONE GEMM over the concatenated output
   // channels: [branch1x1 | branch temps ... | pool-branch projection].  branch1x1's columns land in the
   // block's concat buffer, the rest in a fused temp buffer whose channel slices feed the k>1 convs.
-  // The pool branch is projected FIRST (linear part only: scale 1, shift 0, no ReLU) and average-pooled
-  // afterwards, with its BatchNorm + ReLU applied on the pooled value: avg_pool and a 1x1 conv commute
-  // (both linear; inception_model.py:122-124 order is pool -> conv -> BN -> relu), and pooling 32..192
+  // The pool branch is projected FIRST (conv + BatchNorm affine, no ReLU) and average-pooled afterwards, with
+  // its ReLU applied on the pooled value: avg_pool (exclude-pad divisor) commutes with a 1x1 conv and with a
+  // per-channel affine (inception_model.py:122-124 order is pool -> conv -> BN -> relu), and pooling 32..192
   // projected channels instead of 192..2048 input channels removes ~80 % of the pool traffic.
   struct Sib {
     std::string scope;
@@ -870,7 +851,6 @@ struct Builder {
   struct Fused {
     Act temp;                      // fused temp buffer (channels after the first destination)
     std::vector<int> temp_off;     // channel offset of sibling i inside `temp` (-1 for the first-destination sibling)
-    std::vector<float> pool_scale, pool_shift;   // deferred BN of the pool-projection sibling
   };
   // sibs[0] goes to (out, out_coff) when `first_to_out`, everything else to the fused temp.
   Fused fused_1x1(std::vector<Op>& ops, const std::string& block, const Act& x, const std::vector<Sib>& sibs,
@@ -890,11 +870,15 @@ struct Builder {
       std::vector<float> sc, sh;
       bn_fold(sb.scope, sb.cout, sc, sh);
       for (int j = 0; j < sb.cout; ++j) {
-        scale[col + j] = sb.pool_proj ? 1.0f : sc[j];
-        shift[col + j] = sb.pool_proj ? 0.0f : sh[j];
+        // pool projection: the exclude-pad average of a constant is that constant, so the WHOLE BatchNorm affine
+        // commutes with the pool and is folded in here (scale into the 16-bit weights, shift into the fp32 accumulator
+        // through the bias MMA) exactly as for every other conv; only the ReLU waits for the pooled value.  (r01
+        // stored the un-normalised projection in 16 bits and applied the affine after the pool, which amplifies the
+        // storage rounding by |mean|/sigma on trained statistics — ADVICE r01.)
+        scale[col + j] = sc[j];
+        shift[col + j] = sh[j];
         floor[col + j] = sb.pool_proj ? -INFINITY : 0.0f;
       }
-      if (sb.pool_proj) { f.pool_scale = sc; f.pool_shift = sh; }
       if (i == 0 && first_to_out) {
         f.temp_off.push_back(-1);
       } else {
@@ -939,19 +923,15 @@ struct Builder {
     conv_slice(ops, scope, in, in_coff, cin, cout, kh, kw, 1, true, out, 0);
     return out;
   }
-  // 3x3/1 SAME average pool of the projected pool branch + its deferred BN + ReLU, into the concat slice
+  // 3x3/1 SAME average pool of the projected (conv + BN) pool branch + its deferred ReLU, into the concat slice
   void pool_after_projection(std::vector<Op>& ops, const std::string& scope, const Fused& f, int temp_off, int c,
                              const Act& out, int coff) {
     Op op;
     op.kind = Op::AVGPOOL;
-    op.name = scope + "[avg_pool after 1x1 + BN + ReLU]";
+    op.name = scope + "[avg_pool + ReLU after 1x1 + BN]";
     op.in = f.temp; op.in_coff = temp_off; op.out = out; op.out_coff = coff; op.c = c;
     op.k = 3; op.stride = 1; op.pad = 1;
-    float* d_sc = static_cast<float*>(e.pool.alloc(c * 4));
-    float* d_sh = static_cast<float*>(e.pool.alloc(c * 4));
-    CK(cudaMemcpy(d_sc, f.pool_scale.data(), c * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_sh, f.pool_shift.data(), c * 4, cudaMemcpyHostToDevice));
-    op.scale = d_sc; op.shift = d_sh;
+    op.post_relu = true;
     op.lane = lane;
     ops.push_back(std::move(op));
   }
@@ -1080,10 +1060,6 @@ struct Builder {
         }
       }
       e.conv0_tc = getenv("ICP_CONV0_FMA") == nullptr;
-      CK(cudaFuncSetAttribute(conv0_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              static_cast<int>(conv0_tc_smem_bytes())));
-      CK(cudaFuncSetAttribute(conv0_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              static_cast<int>(conv0_tc_smem_bytes())));
       const int o = (S - 3) / 2 + 1;
       e.conv0_out = alloc_act(o, o, 32);
       e.conv_macs_per_image += static_cast<long long>(o) * o * 32 * 27;
@@ -1132,6 +1108,8 @@ struct Builder {
       e.d_aux_w = static_cast<float*>(e.pool.alloc(w.data.size() * 4));
       e.d_aux_b = static_cast<float*>(e.pool.alloc(b.data.size() * 4));
       e.d_aux_logits = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * e.C * 4));
+      e.d_aux_feat = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * 768 * 4));
+      e.d_aux_part = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * (768 / kHeadSlice) * kHeadSmallC * 4));
       CK(cudaMemcpy(e.d_aux_w, w.data.data(), w.data.size() * 4, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(e.d_aux_b, b.data.data(), b.data.size() * 4, cudaMemcpyHostToDevice));
       Endpoint ep;
@@ -1152,6 +1130,8 @@ struct Builder {
     e.d_logits = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * e.C * 4));
     e.d_probs = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * e.C * 4));
     e.d_topk_val = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * 16 * 4));
+    e.d_feat = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * x.c * 4));
+    e.d_part = static_cast<float*>(e.pool.alloc(static_cast<size_t>(maxn) * (x.c / kHeadSlice) * kHeadSmallC * 4));
     e.d_topk_idx = static_cast<int*>(e.pool.alloc(static_cast<size_t>(maxn) * 16 * 4));
     Endpoint lg; lg.vec = e.d_logits; lg.c = e.C;
     Endpoint pr; pr.vec = e.d_probs; pr.c = e.C;
@@ -1176,20 +1156,48 @@ static int run_op(const Op& op, int n, int fmt, cudaStream_t st, int out_image0 
     }
     case Op::AVGPOOL: {
       const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
-      if (op.scale && op.k == 3 && op.stride == 1 && op.pad == 1)
-        avgpool3_bn_relu_kernel<<<static_cast<unsigned>((static_cast<long long>(n) * op.in.h * ((op.in.w + 3) / 4) *
-                                                         (op.c / 8) + 127) / 128), 128, 0, st>>>(
-            op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.c, op.out_coff, op.scale, op.shift,
-            fmt);
-      else
+      if (op.post_relu && op.k == 3 && op.stride == 1 && op.pad == 1) {
+        // band of rows per CTA: the staged tile fits 96 KiB and, when the batch is small, there are >= 2 CTAs per SM
+        const int per_row = (op.in.w + 2) * op.c * 2;
+        int max_rows = 98304 / per_row - 2;
+        if (max_rows < 1) fail(ICP_E_INVALID, "avg_pool tile of %d x %d channels does not fit shared memory", op.in.w, op.c);
+        int bands = (op.in.h + max_rows - 1) / max_rows;
+        while (n * bands < 2 * g_num_sms && (op.in.h + bands) / (bands + 1) >= 4) ++bands;
+        const int band_rows = (op.in.h + bands - 1) / bands;
+        bands = (op.in.h + band_rows - 1) / band_rows;
+        const size_t smem = static_cast<size_t>(band_rows + 2) * per_row;
+        avgpool3_relu_kernel<<<static_cast<unsigned>(n * bands), 256, smem, st>>>(
+            op.in.p, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.c, op.out_coff, band_rows, bands, 1, fmt);
+      } else {
         avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
             op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff,
-            op.k, op.stride, op.pad, op.scale, op.shift, 1, fmt);
+            op.k, op.stride, op.pad, nullptr, nullptr, 0, fmt);
+      }
       CK(cudaGetLastError());
       return 1;
     }
   }
   return 0;
+}
+
+// Head: pooled features -> (partial) logits -> softmax -> top-k (tower_kernels.cuh); returns the launches made.
+static int launch_head(icp_engine& e, const uint16_t* fmap, int hw, int F, int ld, const float* w, const float* b,
+                       float* logits, float* probs, float* feat, float* part, int n, int k, cudaStream_t st) {
+  if (F % kHeadSlice) fail(ICP_E_INVALID, "head: %d features is not a multiple of %d", F, kHeadSlice);
+  const int C = e.C, slices = F / kHeadSlice;
+  const bool small = C <= kHeadSmallC;
+  int launches = 2;
+  head_pool_kernel<<<dim3(n, slices), 256, 0, st>>>(fmap, hw, F, ld, feat, w, C, part, e.fmt);
+  CK(cudaGetLastError());
+  if (!small) {
+    head_fc_kernel<<<dim3((C + 63) / 64, (n + 15) / 16), 256, 0, st>>>(feat, n, F, w, b, C, logits);
+    CK(cudaGetLastError());
+    ++launches;
+  }
+  head_finish_kernel<<<n, 256, C * sizeof(float), st>>>(small ? part : nullptr, slices, b, C, logits, probs, e.d_topk_val,
+                                                       e.d_topk_idx, probs ? k : 0);
+  CK(cudaGetLastError());
+  return launches;
 }
 
 // Enqueue the whole tower for n images whose preprocessed fp32 input sits at x_dev.
@@ -1277,17 +1285,12 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
   }
   if (e.cfg.enable_aux && !tm) {
     for (const Op& op : e.aux_ops) launches += run_op(op, n, fmt, st);
-    head_kernel<<<n, 256, (768 + e.C) * sizeof(float), st>>>(e.aux_feat.p, 1, 768, e.aux_feat.c, e.d_aux_w, e.d_aux_b,
-                                                             e.C, e.d_aux_logits, nullptr, nullptr, nullptr, 0, fmt);
-    CK(cudaGetLastError());
-    ++launches;
+    launches += launch_head(e, e.aux_feat.p, 1, 768, e.aux_feat.c, e.d_aux_w, e.d_aux_b, e.d_aux_logits, nullptr,
+                            e.d_aux_feat, e.d_aux_part, n, 0, st);
   }
   const Act& f = e.final_act;
-  head_kernel<<<n, 256, (f.c + e.C) * sizeof(float), st>>>(f.p, f.h * f.w, f.c, f.c, e.d_fc_w, e.d_fc_b, e.C,
-                                                           e.d_logits, probs_dev ? probs_dev : e.d_probs, e.d_topk_val,
-                                                           e.d_topk_idx, k, fmt);
-  CK(cudaGetLastError());
-  ++launches;
+  launches += launch_head(e, f.p, f.h * f.w, f.c, f.c, e.d_fc_w, e.d_fc_b, e.d_logits, probs_dev ? probs_dev : e.d_probs,
+                          e.d_feat, e.d_part, n, k, st);
   if (tm) tm->mark();
   return launches;
 }
@@ -1332,6 +1335,8 @@ static void run_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, int
 
 template <class F>
 static int guard(const icp_engine* e, F&& f) {
+  std::unique_lock<std::mutex> lock;
+  if (e) lock = std::unique_lock<std::mutex>(e->mu);
   try {
     f();
     return ICP_OK;
@@ -1350,6 +1355,30 @@ static int guard(const icp_engine* e, F&& f) {
   }
 }
 
+// Function attributes (opt-in to > 48 KiB of dynamic shared memory) are per device/context, so they are set
+// every time a device is selected for building — not once per process (a second engine on another
+// device would otherwise launch without the opt-in).
+static void set_kernel_attrs(int device) {
+  const int big = 227 * 1024;
+  CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv0_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(conv0_tc_smem_bytes())));
+  CK(cudaFuncSetAttribute(conv0_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(conv0_tc_smem_bytes())));
+  CK(cudaFuncSetAttribute(avgpool3_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, device));
+  if (const char* v = getenv("ICP_MBAR_TIMEOUT_MS")) {
+    const long long cycles = atoll(v) * 1900000LL;     // ~1.9 GHz SM clock
+    CK(cudaMemcpyToSymbol(ptx::g_mbar_timeout_cycles, &cycles, sizeof cycles));
+  }
+}
+
 static void require_device(int device) {
   int count = 0;
   cudaError_t err = cudaGetDeviceCount(&count);
@@ -1363,6 +1392,7 @@ static void require_device(int device) {
     fail(ICP_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   CK(cudaSetDevice(device));
   load_driver_api();
+  set_kernel_attrs(device);
 }
 
 }  // namespace icp
@@ -1537,8 +1567,8 @@ int icp_forward_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* pr
   });
 }
 
-int icp_submit_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host, float* topk_vals_host,
-                  int32_t* topk_idx_host, int slot) {
+static int submit_u8_impl(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host,
+                          float* topk_vals_host, int32_t* topk_idx_host, float* probs_dev, int slot) {
   if (!e) return ICP_E_INVALID;
   return guard(e, [&] {
     if (!x_host) fail(ICP_E_INVALID, "null input");
@@ -1553,8 +1583,8 @@ int icp_submit_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* pro
     CK(cudaEventRecord(e->slot_h2d[slot], e->copy_stream));
     CK(cudaStreamWaitEvent(e->stream, e->slot_h2d[slot], 0));
     const int kk = k > 0 ? k : 0;
-    run_tower(*e, e->d_slot_u8[slot], true, n, kk ? kk : e->graph_k, nullptr, e->stream, false);
-    if (probs_out_host)
+    run_tower(*e, e->d_slot_u8[slot], true, n, kk ? kk : e->graph_k, probs_dev, e->stream, false);
+    if (probs_out_host && !probs_dev)
       CK(cudaMemcpyAsync(probs_out_host, e->d_probs, static_cast<size_t>(n) * e->C * 4, cudaMemcpyDeviceToHost,
                          e->stream));
     if (kk && topk_vals_host)
@@ -1566,6 +1596,16 @@ int icp_submit_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* pro
     CK(cudaEventRecord(e->slot_done[slot], e->stream));
     e->slot_busy[slot] = true;
   });
+}
+
+int icp_submit_u8(icp_engine* e, const uint8_t* x_host, int n, int k, float* probs_out_host, float* topk_vals_host,
+                  int32_t* topk_idx_host, int slot) {
+  return submit_u8_impl(e, x_host, n, k, probs_out_host, topk_vals_host, topk_idx_host, nullptr, slot);
+}
+
+int icp_submit_u8_device_out(icp_engine* e, const uint8_t* x_host, int n, float* probs_dev, int slot) {
+  if (!probs_dev) return ICP_E_INVALID;
+  return submit_u8_impl(e, x_host, n, 0, nullptr, nullptr, nullptr, probs_dev, slot);
 }
 
 int icp_collect(icp_engine* e, int slot) {

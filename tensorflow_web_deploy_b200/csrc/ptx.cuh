@@ -45,12 +45,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The default bound is far
+// above anything a healthy launch can see (~60 s of SM clocks: a time-sliced GPU, a sanitizer or a debugger may
+// stall a CTA for seconds, and a trap poisons the context, so it must not fire on mere slowness).  The engine
+// overwrites it from ICP_MBAR_TIMEOUT_MS (bring-up sessions use 2000; 0 = wait forever).
+__device__ long long g_mbar_timeout_cycles = 120000000000LL;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  const long long limit = *reinterpret_cast<volatile long long*>(&g_mbar_timeout_cycles);
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (limit > 0 && clock64() - t0 > limit) {
       printf("icp: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
              threadIdx.x, bar, parity);
       __trap();

@@ -232,116 +232,200 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, in
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(pix) * ldo + coff + g * 8) = pack8(acc, fmt);
 }
 
-// 3x3 / stride 1 / SAME average pool (exclude-pad divisor) + the deferred BatchNorm + ReLU of the 1x1 projection
-// that ran before it (pool-after-projection, see engine.cu).  One thread = 8 channels x a run of 4 consecutive
-// output columns of one row: the 3-row column sums of the 6 input columns under the run are formed once and each
-// output is the sum of three of them (18 16-byte loads and 18 unpacks per 4 outputs instead of 36 / 36; the first
-// version was instruction-bound at 1.1 TB/s).  Out-of-range rows / columns contribute zero and the divisor is the
-// number of in-bounds taps, rows_in * cols_in.  All index arithmetic is 32-bit.
-__global__ void __launch_bounds__(128)
-avgpool3_bn_relu_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
-                        uint16_t* __restrict__ out, int ldo, int coff, const float* __restrict__ scale,
-                        const float* __restrict__ shift, int fmt) {
-  constexpr int kRun = 4;
-  const unsigned cg = static_cast<unsigned>(C) >> 3;
-  const unsigned runs = (static_cast<unsigned>(W) + kRun - 1) / kRun;
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned total = static_cast<unsigned>(N) * H * runs * cg;
-  if (idx >= total) return;
-  const unsigned g = idx % cg;
-  const unsigned t = idx / cg;
-  const unsigned run = t % runs;
-  const unsigned rowi = t / runs;               // n * H + oy
-  const int oy = static_cast<int>(rowi % static_cast<unsigned>(H));
-  const int ox0 = static_cast<int>(run) * kRun;
-  const uint16_t* base = in + static_cast<size_t>(rowi - oy) * W * ldi + cin_off + g * 8;   // image start
-  float col[kRun + 2][8];
+// 3x3 / stride 1 / SAME average pool (exclude-pad divisor, tf.nn.avg_pool, ops.py:397-400) + ReLU of the pool
+// branch, run AFTER that branch's 1x1 projection (pool-after-projection, see engine.cu: the exclude-pad average of a
+// constant is that constant, so the whole BatchNorm affine commutes with the pool and is folded into the projection
+// GEMM like any other conv's; only the ReLU has to wait for the pooled value).
+//
+// One CTA = (image, band of output rows): the band's input rows (+1 halo row each side, +1 zero column each side) of
+// the channel slice are staged in shared memory by cp.async 16-byte copies — every input byte crosses L2->SM once,
+// all copies in flight at once — and each thread then forms outputs from 9 conflict-free LDS.128.  r01 kernel: 18
+// dependent predicated global loads per 4 outputs, ~1 TB/s on L2-resident data (215 us per step over 9 launches).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void acc8(float (&s)[8], const uint4& v, int fmt) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  if (fmt) {
 #pragma unroll
-  for (int c = 0; c < kRun + 2; ++c) {
-    const int ix = ox0 - 1 + c;
-    float sum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ix >= 0 && ix < W) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int iy = oy - 1 + r;
-        if (iy >= 0 && iy < H) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(iy) * W + ix) * ldi));
-          float f[8];
-          unpack8(v, f, fmt);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sum[j] += f[j];
-        }
-      }
+    for (int i = 0; i < 4; ++i) {
+      s[2 * i] += __uint_as_float(w[i] << 16);
+      s[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
     }
+  } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) col[c][j] = sum[j];
-  }
-  const int rows_in = 3 - (oy == 0) - (oy == H - 1);
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(scale + g * 8 + j);
-    sh[j] = __ldg(shift + g * 8 + j);
-  }
-  uint16_t* orow = out + (static_cast<size_t>(rowi) * W + ox0) * ldo + coff + g * 8;
-#pragma unroll
-  for (int p = 0; p < kRun; ++p) {
-    const int ox = ox0 + p;
-    if (ox < W) {
-      const int cols_in = 3 - (ox == 0) - (ox == W - 1);
-      const float inv = 1.0f / static_cast<float>(rows_in * cols_in);
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        acc[j] = fmaxf(fmaf((col[p][j] + col[p + 1][j] + col[p + 2][j]) * inv, sc[j], sh[j]), 0.f);
-      *reinterpret_cast<uint4*>(orow + static_cast<size_t>(p) * ldo) = pack8(acc, fmt);
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      s[2 * i] += f.x;
+      s[2 * i + 1] += f.y;
     }
+  }
+}
+__global__ void __launch_bounds__(256)
+avgpool3_relu_kernel(const uint16_t* __restrict__ in, int H, int W, int C, int ldi, int cin_off,
+                     uint16_t* __restrict__ out, int ldo, int coff, int band_rows, int bands, int relu, int fmt) {
+  extern __shared__ uint4 pool_tile[];          // [(band_rows + 2)][(W + 2)][C / 8] 16-byte vectors
+  const int n = blockIdx.x / bands;
+  const int y0 = (blockIdx.x - n * bands) * band_rows;
+  const int rows = min(band_rows, H - y0);
+  const int cg = C >> 3;
+  const int wp = W + 2;
+  const int tile_vecs = (rows + 2) * wp * cg;
+  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(pool_tile));
+  const uint16_t* img = in + static_cast<size_t>(n) * H * W * ldi + cin_off;
+  for (int v = threadIdx.x; v < tile_vecs; v += blockDim.x) {
+    const int g = v % cg;
+    const int t = v / cg;
+    const int tx = t % wp, ty = t / wp;
+    const int iy = y0 - 1 + ty, ix = tx - 1;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      cp_async16(tile_s + static_cast<uint32_t>(v) * 16u, img + (static_cast<size_t>(iy) * W + ix) * ldi + g * 8);
+    else
+      pool_tile[v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int out_vecs = rows * W * cg;
+  uint16_t* obase = out + static_cast<size_t>(n) * H * W * ldo + coff;
+  for (int v = threadIdx.x; v < out_vecs; v += blockDim.x) {
+    const int g = v % cg;
+    const int t = v / cg;
+    const int ox = t % W, ty = t / W;
+    const int oy = y0 + ty;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint4* c0 = pool_tile + (ty * wp + ox) * cg + g;      // top-left tap (padded coordinates)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) acc8(s, c0[(r * wp + q) * cg], fmt);
+    const int rows_in = 3 - (oy == 0) - (oy == H - 1);
+    const int cols_in = 3 - (ox == 0) - (ox == W - 1);
+    const float inv = 1.0f / static_cast<float>(rows_in * cols_in);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] *= inv;
+      if (relu) s[j] = fmaxf(s[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(oy) * W + ox) * ldo + g * 8) = pack8(s, fmt);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Head (inception_model.py:318-329 + PyClassification.py:163-164): global average pool over
-// HW -> flatten -> fc [F, C] + bias -> softmax -> top-k of the probabilities (descending, ties to
-// the lower index).  One CTA per image, 256 threads.  Generic over F (2048 main head, 768 aux
-// head with hw = 1) and C; `probs == nullptr` skips softmax/top-k (aux logits only).
+// Head (inception_model.py:318-329 + PyClassification.py:163-164): global average pool over HW -> flatten
+// -> fc [F, C] + bias -> softmax -> top-k of the probabilities (descending, ties to the lower index).
+//
+// r01 ran this as one CTA per image (grid 128 on 148 SMs, 33 us at batch 128, and an fc loop that re-read the whole
+// weight matrix per image with a class-strided access: unusable at C = 1001 / 4001).  Now three stages, every
+// reduction in a fixed order (results are bit-identical whatever batch an image rides in):
+//   head_pool_kernel      grid (n, F/256): mean over HW of 256 channels -> feat[n][F] fp32; for C <= kHeadSmallC also
+//                         the slice's partial logits -> part[n][F/256][C]
+//   head_fc_kernel        (C > kHeadSmallC only) logits[n][C] = feat[n][F] x W[F][C] + b: a tiled fp32 GEMM, weights read
+//                         once per 16 images, coalesced along C
+//   head_finish_kernel    grid n: (partials + bias ->) logits -> softmax -> top-k
+// Generic over F (2048 main head, 768 aux head with hw = 1); `probs == nullptr` stops after the logits (aux head).
 // ---------------------------------------------------------------------------------------------
+constexpr int kHeadSmallC = 32;
+constexpr int kHeadSlice = 256;      // channels per head_pool CTA
+
 __global__ void __launch_bounds__(256)
-head_kernel(const uint16_t* __restrict__ feat_map, int hw, int F, int ld, const float* __restrict__ fc_w /*[F][C]*/,
-            const float* __restrict__ fc_b, int C, float* __restrict__ logits, float* __restrict__ probs,
-            float* __restrict__ topk_val, int* __restrict__ topk_idx, int k, int fmt) {
-  extern __shared__ float sm[];
-  float* feat = sm;            // [F]
-  float* lg = sm + F;          // [C]
+head_pool_kernel(const uint16_t* __restrict__ feat_map, int hw, int F, int ld, float* __restrict__ feat,
+                 const float* __restrict__ fc_w /*[F][C]*/, int C, float* __restrict__ part /*[n][F/256][C]*/, int fmt) {
+  __shared__ float red[8][kHeadSlice];
+  __shared__ float fs[kHeadSlice];
+  const int n = blockIdx.x, sl = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int g = tid & 31;            // 8-channel group inside the slice
+  const int pp = tid >> 5;           // pixel part: pixels pp, pp + 8, ...
+  const uint16_t* src = feat_map + static_cast<size_t>(n) * hw * ld + sl * kHeadSlice + g * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = pp; p < hw; p += 8) acc8(acc, __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(p) * ld)), fmt);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[pp][g * 8 + j] = acc[j];
+  __syncthreads();
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][tid];
+    s *= 1.0f / static_cast<float>(hw);
+    fs[tid] = s;
+    feat[static_cast<size_t>(n) * F + sl * kHeadSlice + tid] = s;
+  }
+  if (C > kHeadSmallC) return;
+  __syncthreads();
+  // partial logits of this slice: one warp per class, lanes stride the slice's 256 features
+  const int lane = tid & 31, warp = tid >> 5;
+  const float* w0 = fc_w + static_cast<size_t>(sl) * kHeadSlice * C;
+  for (int c = warp; c < C; c += 8) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHeadSlice / 32; ++i) a = fmaf(fs[lane + 32 * i], __ldg(w0 + static_cast<size_t>(lane + 32 * i) * C + c), a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) part[(static_cast<size_t>(n) * gridDim.y + sl) * C + c] = a;
+  }
+}
+
+// logits[n][C] = feat[n][F] x W[F][C] + b.  CTA = 16 images x 64 classes, 256 threads = 64 classes x 4 K-phases;
+// K walked in chunks of 256 staged in shared memory; the 4 phases are summed in a fixed order.
+__global__ void __launch_bounds__(256)
+head_fc_kernel(const float* __restrict__ feat, int n, int F, const float* __restrict__ fc_w, const float* __restrict__ fc_b,
+               int C, float* __restrict__ logits) {
+  __shared__ float fs[16][256];
+  __shared__ float red[4][16][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int ph = threadIdx.x >> 6;
+  const int i0 = blockIdx.y * 16;
+  const int ni = min(16, n - i0);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < F; k0 += 256) {
+    __syncthreads();
+    for (int v = threadIdx.x; v < 16 * 256; v += 256) {
+      const int i = v >> 8, k = v & 255;
+      fs[i][k] = (i < ni && k0 + k < F) ? feat[static_cast<size_t>(i0 + i) * F + k0 + k] : 0.f;
+    }
+    __syncthreads();
+    if (c < C) {
+      const int kend = min(256, F - k0);
+      for (int k = ph; k < kend; k += 4) {
+        const float w = __ldg(fc_w + static_cast<size_t>(k0 + k) * C + c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(fs[i][k], w, acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) red[ph][i][threadIdx.x & 63] = acc[i];
+  __syncthreads();
+  for (int v = threadIdx.x; v < 16 * 64; v += 256) {
+    const int i = v >> 6, cc = v & 63;
+    const int col = blockIdx.x * 64 + cc;
+    if (i < ni && col < C)
+      logits[static_cast<size_t>(i0 + i) * C + col] = ((red[0][i][cc] + red[1][i][cc]) + (red[2][i][cc] + red[3][i][cc])) + fc_b[col];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+head_finish_kernel(const float* __restrict__ part, int slices, const float* __restrict__ fc_b, int C,
+                   float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ topk_val,
+                   int* __restrict__ topk_idx, int k) {
+  extern __shared__ float lg[];      // [C]
   __shared__ float red[32];
   __shared__ int redi[32];
   const int n = blockIdx.x;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const float inv = 1.0f / static_cast<float>(hw);
-  for (int g = tid; g < F / 8; g += blockDim.x) {
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = 0; p < hw; ++p) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(feat_map + (static_cast<size_t>(n) * hw + p) * ld + g * 8));
-      float f[8];
-      unpack8(v, f, fmt);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  if (part != nullptr) {             // small C: sum the slices' partial logits in order, add the bias
+    for (int c = tid; c < C; c += blockDim.x) {
+      float a = 0.f;
+      for (int s = 0; s < slices; ++s) a += part[(static_cast<size_t>(n) * slices + s) * C + c];
+      a += fc_b[c];
+      lg[c] = a;
+      logits[static_cast<size_t>(n) * C + c] = a;
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) feat[g * 8 + j] = acc[j] * inv;
-  }
-  __syncthreads();
-  // fc: one warp per class, lanes stride the feature dimension (fc_w is [F][C], class fastest)
-  for (int c = warp; c < C; c += 8) {
-    float acc = 0.f;
-    for (int f = lane; f < F; f += 32) acc = fmaf(feat[f], __ldg(fc_w + static_cast<size_t>(f) * C + c), acc);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      acc += fc_b[c];
-      lg[c] = acc;
-      logits[static_cast<size_t>(n) * C + c] = acc;
-    }
+  } else {
+    for (int c = tid; c < C; c += blockDim.x) lg[c] = logits[static_cast<size_t>(n) * C + c];
   }
   __syncthreads();
   if (probs == nullptr) return;

@@ -47,6 +47,7 @@ SIGNATURES = {
     "icp_forward_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p, _f32p, _i32p]),
     "icp_submit_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p, _f32p, _i32p, C.c_int]),
     "icp_collect": (C.c_int, [C.c_void_p, C.c_int]),
+    "icp_submit_u8_device_out": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_void_p, C.c_int]),
     "icp_num_ops": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "icp_op_info": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
                               C.POINTER(C.c_double)]),
@@ -175,6 +176,17 @@ class Engine:
         _check(self._lib.icp_collect(self._h, slot), self._h)
         x, out = self._inflight.pop(slot)
         return out
+
+    def submit_u8_device_out(self, x: np.ndarray, slot: int, probs_ptr: int) -> None:
+        """submit_u8 whose probabilities stay on the device (float32 [n,C] at `probs_ptr`), for callers that feed a
+        collective; ordered on Engine.stream; collect(slot) waits for the tower."""
+        if x.dtype != np.uint8 or not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("submit_u8_device_out needs a C-contiguous uint8 array")
+        _check(self._lib.icp_submit_u8_device_out(self._h, x.ctypes.data_as(_u8p), x.shape[0], C.c_void_p(probs_ptr), slot),
+               self._h)
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[slot] = (x, None)
 
     def op_table(self):
         """[(name, kind, flops_per_image, bytes_per_image)] for every launch of one forward pass."""

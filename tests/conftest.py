@@ -47,3 +47,33 @@ def synth6(tmp_path_factory):
     path = str(tmp_path_factory.mktemp("w") / "synthetic_c6.icpw")
     weights.save_blob(path, W)
     return path, W
+
+
+def calibrated_weights(num_classes, seed=4321, images=2):
+    """Synthetic weights with TRAINED-LIKE BatchNorm statistics (test helper; uses the oracle, so it lives in tests/).
+
+    The default synthetic blob draws moving_mean ~ N(0, 0.1) and variance in [0.5, 1.5] — tame.  A trained net's
+    statistics are whatever the conv outputs really are: a mean of several sigma and variances spread over orders
+    of magnitude.  Here every conv's output channels are rescaled by 10^U(-1,1) and moving_mean / moving_variance
+    are then SET to the measured per-channel statistics of the oracle's activations on a few random images, layer by
+    layer, so |mean| / sigma is O(1..5) and the BN fold has real work to do (the pool-branch reorder)."""
+    import numpy as np
+    import torch
+    from oracle import inception_oracle as O
+    from tensorflow_web_deploy_b200 import weights
+    rng = np.random.default_rng(seed)
+    W = weights.synthetic_weights(num_classes, seed=seed)
+    for name in list(W):
+        if name.endswith("/weights") and W[name].ndim == 4:
+            W[name] = W[name] * (10.0 ** rng.uniform(-1, 1, W[name].shape[3])).astype(np.float32)
+
+    class Calibrating(O.Tower):
+        def bn_relu(self, y, scope):
+            c = y.shape[1]
+            self.w[scope + "/BatchNorm/moving_mean"] = y.mean(dim=(0, 2, 3)).numpy().astype(np.float32)
+            self.w[scope + "/BatchNorm/moving_variance"] = y.var(dim=(0, 2, 3), unbiased=False).numpy().astype(np.float32) + np.float32(1e-4)
+            return super().bn_relu(y, scope)
+
+    x = rng.uniform(-1, 1, (images, 299, 299, 3)).astype(np.float32)
+    Calibrating(W).forward(x, num_classes, with_aux=True)
+    return W

@@ -332,3 +332,128 @@ def test_imagenet_classifier_drop_in(synth6, tmp_path, built_lib):
     assert acc == pytest.approx(float(np.sum(np.sort(np.float32(
         clf.engine.classify_rgb8(decoded, 5)[0])))), abs=1e-6)
     assert clf.classify_image(b"garbage") is None
+
+
+# ----------------------------------------------------------------------------------------------- round 2
+def test_reference_sample_jpg_through_classify_image(synth6, built_lib):
+    """BASELINE configs[0] on the reference's OWN fixtures: data/sample.jpg + data/synset.txt through
+    ImagenetClassifier.classify_image (PyClassification.py:205-226, incl. the warm-up call of setup_app), GPU vs oracle."""
+    from PIL import Image
+    from oracle import inception_oracle as O
+    from tensorflow_web_deploy_b200 import PyClassification as P
+    path, W = synth6
+    jpeg = open(os.path.join(GOLDEN, "reference_sample.jpg"), "rb").read()
+    clf = P.ImagenetClassifier(path, os.path.join(GOLDEN, "reference_synset.txt"))
+    assert clf.label_names == ["none", "daisy", "dandelion", "roses", "sunflowers", "tulips"]
+    out = clf.classify_image(jpeg)                 # the warm-up of PyClassification.py:223-226
+    assert out is not None
+    names, probs, secs, acc = out
+    decoded = np.asarray(Image.open(io.BytesIO(jpeg)).convert("RGB"))
+    assert decoded.shape == (375, 500, 3)
+    onames, oprobs, oacc = O.OracleClassifier(W, clf.label_names, 6).classify_decoded(decoded)
+    assert names == onames
+    assert np.abs(probs - oprobs).max() <= 1e-3 and abs(float(acc) - oacc) <= 2e-3
+    again = clf.classify_image(jpeg)
+    assert again[0] == names and np.array_equal(again[1], probs)       # replay of the captured graph is bit-identical
+
+
+@pytest.mark.parametrize("num_classes", [1001, 4001])
+def test_large_class_head(eng_mod, tmp_path, num_classes):
+    """the ImageNet-sized (1001) and the reference model.meta's 4001-class head
+    (inception_model.py:325-329) — the tiled fc GEMM path of the head instead of the fused small-C one."""
+    from oracle import inception_oracle as O
+    from tensorflow_web_deploy_b200 import weights
+    W = weights.synthetic_weights(num_classes)
+    rng = np.random.default_rng(21)
+    W["logits/logits/weights"] = (W["logits/logits/weights"] * 6).astype(np.float32)     # a peaked softmax over 1000s of classes
+    path = str(tmp_path / "w.icpw")
+    weights.save_blob(path, W)
+    x = rng.uniform(-1, 1, (3, 299, 299, 3)).astype(np.float32)
+    tw = O.Tower(W)
+    logits, pred = tw.forward(x, num_classes, with_aux=True)
+    eng = eng_mod.Engine(path, num_classes, max_batch=3, precision="fp16", enable_aux=True)
+    probs, vals, idx = eng.forward_topk(x, 5)
+    assert np.abs(probs - pred).max() <= 1e-3
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-4)
+    gl = eng.endpoint("logits")
+    assert np.abs(gl - logits).max() <= 2e-2 * max(1.0, float(np.abs(logits).max()))
+    assert np.abs(eng.endpoint("aux_logits") - tw.end_points["aux_logits"]).max() <= 2e-2 * max(1.0, float(np.abs(tw.end_points["aux_logits"]).max()))
+    ov, oi = O.top_k(pred, 5)
+    assert np.array_equal(idx[:, 0], oi[:, 0])
+    for r in range(3):                                  # top-5 identical wherever the oracle's gaps exceed the error bar
+        gaps = np.abs(np.diff(np.sort(pred[r])[::-1][:6]))
+        if gaps.min() > 2e-4:
+            np.testing.assert_array_equal(idx[r], oi[r])
+    np.testing.assert_array_equal(idx, np.argsort(-probs, axis=1, kind="stable")[:, :5])       # self-consistent, ties to lower index
+    np.testing.assert_array_equal(vals, np.take_along_axis(probs, idx, 1))
+    one = eng.forward(x[1:2])
+    np.testing.assert_array_equal(one, probs[1:2])                                              # batch-invariant, bit-exact
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_trained_like_batchnorm_statistics(eng_mod, tmp_path, precision):
+    """with trained statistics (|mean|/sigma of several units, variances over orders of magnitude) the BN
+    fold — and in particular the pool branch, whose affine is applied BEFORE the avg-pool now — must still meet the bar."""
+    from conftest import calibrated_weights
+    from oracle import inception_oracle as O
+    from tensorflow_web_deploy_b200 import weights
+    W = calibrated_weights(6)
+    W["logits/logits/weights"] = (W["logits/logits/weights"] * 4).astype(np.float32)
+    path = str(tmp_path / "cal.icpw")
+    weights.save_blob(path, W)
+    x = np.random.default_rng(5).uniform(-1, 1, (2, 299, 299, 3)).astype(np.float32)
+    tw = O.Tower(W)
+    _, pred = tw.forward(x, 6, with_aux=False)
+    eng = eng_mod.Engine(path, 6, max_batch=2, precision=precision)
+    probs = eng.forward(x)
+    assert np.abs(probs - pred).max() <= PROB_TOL[precision]
+    rel_lim = 2.5e-3 if precision == "fp16" else 2e-2
+    for k in ("mixed_35x35x256a", "mixed_17x17x768b", "mixed_17x17x768e", "mixed_8x8x2048b"):
+        got, ref = eng.endpoint(k), tw.end_points[k]
+        pool = slice(got.shape[3] - (32 if k.endswith("256a") else 192), got.shape[3])     # the branch_pool slice
+        for sl in (slice(None), pool):
+            rel = np.sqrt(((got[..., sl] - ref[..., sl]) ** 2).mean()) / (np.sqrt((ref[..., sl] ** 2).mean()) + 1e-12)
+            assert rel <= rel_lim, (k, sl, rel)
+    eng.close()
+
+
+def test_classify_image_is_thread_safe(synth6, built_lib):
+    """The reference's Session.run is thread-safe and threaded WSGI servers call classify_image concurrently."""
+    import threading
+    from tensorflow_web_deploy_b200 import PyClassification as P
+    from PIL import Image
+    path, _ = synth6
+    clf = P.ImagenetClassifier(path, os.path.join(GOLDEN, "reference_synset.txt"))
+    rng = np.random.default_rng(13)
+    jpegs = []
+    for i in range(4):
+        buf = io.BytesIO()
+        Image.fromarray(rng.integers(0, 256, (200 + 40 * i, 300 - 30 * i, 3), dtype=np.uint8)).save(buf, "JPEG", quality=90)
+        jpegs.append(buf.getvalue())
+    want = [clf.classify_image(j) for j in jpegs]
+    got = [[None] * 8 for _ in jpegs]
+
+    def work(t):
+        for rep in range(8):
+            got[t][rep] = clf.classify_image(jpegs[t])
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(len(jpegs))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for t in range(len(jpegs)):
+        for rep in range(8):
+            assert got[t][rep][0] == want[t][0]
+            np.testing.assert_array_equal(got[t][rep][1], want[t][1])
+
+
+def test_two_engines_in_one_process(eng_mod, synth6):
+    """Function attributes are per device: a second engine (second device when the box has one) works in-process."""
+    x = np.random.default_rng(3).uniform(-1, 1, (2, 299, 299, 3)).astype(np.float32)
+    a = eng_mod.Engine(synth6[0], 6, device=0, max_batch=2, precision="fp16")
+    dev_b = 1 if torch.cuda.device_count() > 1 else 0
+    b = eng_mod.Engine(synth6[0], 6, device=dev_b, max_batch=2, precision="fp16")
+    pa, pb = a.forward(x), b.forward(x)
+    np.testing.assert_array_equal(pa, pb)
+    np.testing.assert_array_equal(a.forward(x), pa)
+    a.close(); b.close()
