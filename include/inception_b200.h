@@ -106,6 +106,26 @@ int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_de
 int icp_classify_rgb8(icp_engine* e, const uint8_t* rgb, int h, int w, int k, float* topk_vals,
                       int32_t* topk_idx);
 
+/* One request exactly as the reference serves it — the JPEG string in, top-k out
+ * (PyClassification.py:150-151 tf.image.decode_jpeg(channels=3) ... :163-164 top_k; :205-215): nvJPEG decodes on
+ * the GPU into the buffer the crop/resize kernel reads, then tower, softmax, top-k.  Baseline and progressive
+ * JPEGs; grayscale is expanded to 3 channels.  ICP_E_INVALID for anything that is not a decodable JPEG. */
+int icp_classify_jpeg(icp_engine* e, const uint8_t* jpg, size_t len, int k, float* topk_vals, int32_t* topk_idx);
+
+/* Decode alone (parity tap against libjpeg): rgb_out_host (may be NULL to query the size) receives uint8 [h,w,3]. */
+int icp_decode_jpeg(icp_engine* e, const uint8_t* jpg, size_t len, uint8_t* rgb_out_host, size_t cap, int* h_out,
+                    int* w_out);
+/* nvjpegBackend_t value of the decoder in use (-1 before the first JPEG call). */
+int icp_jpeg_backend(icp_engine* e, int* backend);
+
+/* Micro-batched requests (serving front-end): n images of different sizes -> ONE tower launch at batch n.
+ * rgb8: decoded uint8 [hs[i], ws[i], 3] host buffers; jpeg: JPEG byte strings decoded on the GPU.
+ * topk_vals / topk_idx are [n, k].  n <= max_batch. */
+int icp_classify_batch_rgb8(icp_engine* e, const uint8_t* const* rgbs, const int* hs, const int* ws, int n, int k,
+                            float* topk_vals, int32_t* topk_idx);
+int icp_classify_batch_jpeg(icp_engine* e, const uint8_t* const* jpgs, const size_t* lens, int n, int k,
+                            float* topk_vals, int32_t* topk_idx);
+
 /* GPU preprocessing alone (parity tap): rgb uint8 [h,w,3] -> out float32 [S,S,3]. */
 int icp_preprocess_rgb8(icp_engine* e, const uint8_t* rgb, int h, int w, float* out_host);
 

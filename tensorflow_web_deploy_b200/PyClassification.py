@@ -63,6 +63,10 @@ class ImagenetClassifier(object):
         self.engine = _engine.Engine(model_def_file, num_classes=len(self.label_names), device=device, max_batch=1,
                                      precision=precision, use_cuda_graph=use_cuda_graph)
         self.top_k = min(NUM_TOP_CLASSES, len(self.label_names))
+        # JPEG decode: "nvjpeg" = on the GPU inside the engine (icp_classify_jpeg: the graph starts at the JPEG string,
+        # as the reference's does, PyClassification.py:150-151); "pil" = host libjpeg(-turbo), the decoder family TF's
+        # DecodeJpeg used, then icp_classify_rgb8.  Anything nvJPEG refuses (CMYK, arithmetic coding) falls back to PIL.
+        self.decode_backend = os.environ.get("ICP_JPEG", "nvjpeg").lower()
         # The reference's tf.Session.run is thread-safe and Flask's development server / gthread workers are threaded;
         # the engine keeps one set of staging buffers, so requests of one process are serialised here (the C ABI
         # also locks per engine).  Cost: nothing next to the tower; throughput comes from the micro-batcher (serving/).
@@ -76,9 +80,18 @@ class ImagenetClassifier(object):
     def classify_image(self, image):
         try:
             start_time = time.time()
-            rgb = decode_jpeg_rgb(image)
-            with self._lock:
-                probs, labels = self.engine.classify_rgb8(rgb, self.top_k)
+            probs = None
+            if self.decode_backend == "nvjpeg":
+                try:
+                    with self._lock:
+                        probs, labels = self.engine.classify_jpeg(image, self.top_k)
+                except _engine.EngineError as err:
+                    if err.code != -1:              # ICP_E_INVALID: nvJPEG could not take this stream; try libjpeg
+                        raise
+            if probs is None:
+                rgb = decode_jpeg_rgb(image)
+                with self._lock:
+                    probs, labels = self.engine.classify_rgb8(rgb, self.top_k)
             end_time = time.time()
             logger.info("classify_image cost %.2f secs", end_time - start_time)
             names = [self.label_names[labels[0]], self.label_names[labels[1]], self.label_names[labels[2]]]

@@ -5,6 +5,7 @@
 // block's NHWC output (no concat kernels), pools and the head are HBM-bound kernels.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvjpeg.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -678,6 +679,44 @@ struct Endpoint {
 
 using namespace icp;
 
+// ------------------------------------------------------------------------------------------ JPEG decode (nvJPEG)
+// The reference's graph starts at the JPEG string (tf.image.decode_jpeg, PyClassification.py:150-151).  nvJPEG
+// decodes on the GPU straight into the staging buffer the crop/resize kernel reads: no host-side pixel buffer,
+// no host->device copy of decoded pixels.  Backends are tried in the order hardware engine -> GPU-assisted
+// Huffman -> hybrid (CPU Huffman + GPU IDCT); ICP_NVJPEG_BACKEND=<n> pins one (nvjpegBackend_t value).
+struct JpegDecoder {
+  nvjpegHandle_t h = nullptr;
+  nvjpegJpegState_t st = nullptr;
+  int backend = -1;
+  std::vector<int> candidates;
+  void destroy() {
+    if (st) nvjpegJpegStateDestroy(st);
+    if (h) nvjpegDestroy(h);
+    st = nullptr; h = nullptr; backend = -1;
+  }
+  bool open_next() {      // false when no backend is left
+    destroy();
+    while (!candidates.empty()) {
+      const int b = candidates.front();
+      candidates.erase(candidates.begin());
+      static const bool interp = getenv("ICP_NVJPEG_NO_INTERP") == nullptr;   // chroma upsampling with interpolation ~ libjpeg "fancy upsampling"
+      if (nvjpegCreateEx(static_cast<nvjpegBackend_t>(b), nullptr, nullptr, interp ? NVJPEG_FLAGS_UPSAMPLING_WITH_INTERPOLATION : 0, &h) !=
+          NVJPEG_STATUS_SUCCESS) { h = nullptr; continue; }
+      if (nvjpegJpegStateCreate(h, &st) != NVJPEG_STATUS_SUCCESS) { nvjpegDestroy(h); h = nullptr; st = nullptr; continue; }
+      backend = b;
+      return true;
+    }
+    return false;
+  }
+  void init() {
+    if (h || !candidates.empty()) return;
+    if (const char* v = getenv("ICP_NVJPEG_BACKEND")) candidates = {atoi(v)};
+    else candidates = {NVJPEG_BACKEND_HARDWARE, NVJPEG_BACKEND_GPU_HYBRID, NVJPEG_BACKEND_HYBRID, NVJPEG_BACKEND_DEFAULT};
+    open_next();
+  }
+  ~JpegDecoder() { destroy(); }
+};
+
 // ------------------------------------------------------------------------------------------ engine
 struct GraphKey {
   int n;
@@ -712,8 +751,9 @@ struct icp_engine {
   cudaEvent_t slot_h2d[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
   bool slot_busy[2] = {false, false};
   int graph_k = 5;
-  uint8_t* d_rgb = nullptr;         // staging for icp_classify_rgb8
+  uint8_t* d_rgb = nullptr;         // staging for icp_classify_rgb8 / icp_classify_jpeg / the batch calls
   size_t d_rgb_cap = 0;
+  JpegDecoder jpeg;                 // created on the first icp_classify_jpeg call
   Conv0Params conv0{};              // weights + folded BN of the Cin=3 stem conv, passed by value (FP32-pipe kernel)
   Conv0TcParams conv0_tc_f{}, conv0_tc_u8{};   // tensor-core conv0: 16-bit weights (+ 2/255 for uint8 input), shift
   bool conv0_tc = true;
@@ -1499,20 +1539,56 @@ int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_de
   });
 }
 
+static void reserve_rgb(icp_engine* e, size_t bytes) {
+  if (bytes <= e->d_rgb_cap) return;
+  CK(cudaStreamSynchronize(e->stream));       // earlier work may still read the old buffer
+  if (e->d_rgb) cudaFree(e->d_rgb);
+  e->d_rgb = nullptr;
+  e->d_rgb_cap = 0;
+  bytes = (bytes + (1u << 20)) & ~size_t((1u << 20) - 1);
+  CK(cudaMalloc(&e->d_rgb, bytes));
+  e->d_rgb_cap = bytes;
+}
+
+// decoded uint8 [h,w,3] at d_src (device) -> image `slot` of the fp32 network input
+static void launch_preprocess(icp_engine* e, const uint8_t* d_src, int h, int w, int slot) {
+  const int total = e->S * e->S;
+  preprocess_u8_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(
+      d_src, h, w, e->d_input + static_cast<size_t>(slot) * e->S * e->S * 3, e->S);
+  CK(cudaGetLastError());
+}
+
 static void preprocess_to_input(icp_engine* e, const uint8_t* rgb, int h, int w) {
   if (!rgb || h < 16 || w < 16) fail(ICP_E_INVALID, "image %dx%d invalid", h, w);
   const size_t bytes = static_cast<size_t>(h) * w * 3;
-  if (bytes > e->d_rgb_cap) {
-    if (e->d_rgb) cudaFree(e->d_rgb);
-    e->d_rgb = nullptr;
-    e->d_rgb_cap = 0;
-    CK(cudaMalloc(&e->d_rgb, bytes));
-    e->d_rgb_cap = bytes;
-  }
+  reserve_rgb(e, bytes);
   CK(cudaMemcpyAsync(e->d_rgb, rgb, bytes, cudaMemcpyHostToDevice, e->stream));
-  const int total = e->S * e->S;
-  preprocess_u8_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(e->d_rgb, h, w, e->d_input, e->S);
-  CK(cudaGetLastError());
+  launch_preprocess(e, e->d_rgb, h, w, 0);
+}
+
+// JPEG bytes -> decoded RGB at d_rgb + offset (device), through nvJPEG on the engine's stream; returns h, w.
+static void decode_jpeg_to_device(icp_engine* e, const uint8_t* jpg, size_t len, size_t offset, int* oh, int* ow) {
+  if (!jpg || len < 4) fail(ICP_E_INVALID, "empty JPEG buffer");
+  e->jpeg.init();
+  for (;;) {
+    if (!e->jpeg.h) fail(ICP_E_CUDA, "nvJPEG: no usable decode backend");
+    int ncomp = 0;
+    nvjpegChromaSubsampling_t ss;
+    int ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegStatus_t r = nvjpegGetImageInfo(e->jpeg.h, jpg, len, &ncomp, &ss, ws, hs);
+    if (r != NVJPEG_STATUS_SUCCESS) fail(ICP_E_INVALID, "not a decodable JPEG (nvjpegGetImageInfo status %d)", (int)r);
+    const int w = ws[0], h = hs[0];
+    if (h < 16 || w < 16 || h > 16384 || w > 16384) fail(ICP_E_INVALID, "image %dx%d invalid", h, w);
+    const size_t bytes = static_cast<size_t>(h) * w * 3;
+    reserve_rgb(e, offset + bytes);
+    nvjpegImage_t img{};
+    img.channel[0] = e->d_rgb + offset;
+    img.pitch[0] = static_cast<size_t>(w) * 3;
+    r = nvjpegDecode(e->jpeg.h, e->jpeg.st, jpg, len, NVJPEG_OUTPUT_RGBI, &img, e->stream);
+    if (r == NVJPEG_STATUS_SUCCESS) { *oh = h; *ow = w; return; }
+    // this backend cannot take the stream (progressive / unsupported subsampling / no engine): try the next one
+    if (!e->jpeg.open_next()) fail(ICP_E_INVALID, "nvjpegDecode failed (status %d) on every backend", (int)r);
+  }
 }
 
 int icp_preprocess_rgb8(icp_engine* e, const uint8_t* rgb, int h, int w, float* out_host) {
@@ -1537,6 +1613,114 @@ int icp_classify_rgb8(icp_engine* e, const uint8_t* rgb, int h, int w, int k, fl
     run_tower(*e, e->d_input, false, 1, k, nullptr, e->stream, true);
     CK(cudaMemcpyAsync(topk_vals, e->d_topk_val, k * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(topk_idx, e->d_topk_idx, k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+int icp_classify_jpeg(icp_engine* e, const uint8_t* jpg, size_t len, int k, float* topk_vals, int32_t* topk_idx) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!topk_vals || !topk_idx) fail(ICP_E_INVALID, "null output");
+    if (k < 1) fail(ICP_E_INVALID, "k must be >= 1");
+    CK(cudaSetDevice(e->cfg.device));
+    int h = 0, w = 0;
+    decode_jpeg_to_device(e, jpg, len, 0, &h, &w);
+    launch_preprocess(e, e->d_rgb, h, w, 0);
+    run_tower(*e, e->d_input, false, 1, k, nullptr, e->stream, true);
+    CK(cudaMemcpyAsync(topk_vals, e->d_topk_val, k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(topk_idx, e->d_topk_idx, k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+int icp_decode_jpeg(icp_engine* e, const uint8_t* jpg, size_t len, uint8_t* rgb_out_host, size_t cap, int* h_out,
+                    int* w_out) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!h_out || !w_out) fail(ICP_E_INVALID, "null output");
+    CK(cudaSetDevice(e->cfg.device));
+    int h = 0, w = 0;
+    decode_jpeg_to_device(e, jpg, len, 0, &h, &w);
+    *h_out = h; *w_out = w;
+    const size_t bytes = static_cast<size_t>(h) * w * 3;
+    if (rgb_out_host) {
+      if (cap < bytes) fail(ICP_E_INVALID, "output buffer of %zu bytes is too small for %dx%dx3", cap, h, w);
+      CK(cudaMemcpyAsync(rgb_out_host, e->d_rgb, bytes, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int icp_jpeg_backend(icp_engine* e, int* backend) {
+  if (!e || !backend) return ICP_E_INVALID;
+  *backend = e->jpeg.backend;
+  return ICP_OK;
+}
+
+// n decoded images of different sizes -> one tower launch at batch n (the micro-batcher's call)
+int icp_classify_batch_rgb8(icp_engine* e, const uint8_t* const* rgbs, const int* hs, const int* ws, int n, int k,
+                            float* topk_vals, int32_t* topk_idx) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!rgbs || !hs || !ws || !topk_vals || !topk_idx) fail(ICP_E_INVALID, "null argument");
+    if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
+    if (k < 1) fail(ICP_E_INVALID, "k must be >= 1");
+    CK(cudaSetDevice(e->cfg.device));
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!rgbs[i] || hs[i] < 16 || ws[i] < 16) fail(ICP_E_INVALID, "image %d: %dx%d invalid", i, hs[i], ws[i]);
+      total += (static_cast<size_t>(hs[i]) * ws[i] * 3 + 255) & ~size_t(255);
+    }
+    reserve_rgb(e, total);
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+      const size_t bytes = static_cast<size_t>(hs[i]) * ws[i] * 3;
+      CK(cudaMemcpyAsync(e->d_rgb + off, rgbs[i], bytes, cudaMemcpyHostToDevice, e->stream));
+      launch_preprocess(e, e->d_rgb + off, hs[i], ws[i], i);
+      off += (bytes + 255) & ~size_t(255);
+    }
+    run_tower(*e, e->d_input, false, n, k, nullptr, e->stream, true);
+    CK(cudaMemcpyAsync(topk_vals, e->d_topk_val, static_cast<size_t>(n) * k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(topk_idx, e->d_topk_idx, static_cast<size_t>(n) * k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  });
+}
+
+// same from JPEG bytes: every image is decoded by nvJPEG into the staging buffer, then one tower launch
+int icp_classify_batch_jpeg(icp_engine* e, const uint8_t* const* jpgs, const size_t* lens, int n, int k,
+                            float* topk_vals, int32_t* topk_idx) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!jpgs || !lens || !topk_vals || !topk_idx) fail(ICP_E_INVALID, "null argument");
+    if (n < 1 || n > e->max_batch) fail(ICP_E_INVALID, "batch %d outside [1, %d]", n, e->max_batch);
+    if (k < 1) fail(ICP_E_INVALID, "k must be >= 1");
+    CK(cudaSetDevice(e->cfg.device));
+    // sizes first (header parse only), so that the staging buffer is reserved once and never moves mid-batch
+    e->jpeg.init();
+    if (!e->jpeg.h) fail(ICP_E_CUDA, "nvJPEG: no usable decode backend");
+    std::vector<size_t> offs(n);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+      int ncomp = 0;
+      nvjpegChromaSubsampling_t ss;
+      int w_[NVJPEG_MAX_COMPONENT] = {0}, h_[NVJPEG_MAX_COMPONENT] = {0};
+      if (!jpgs[i] || nvjpegGetImageInfo(e->jpeg.h, jpgs[i], lens[i], &ncomp, &ss, w_, h_) != NVJPEG_STATUS_SUCCESS)
+        fail(ICP_E_INVALID, "image %d is not a decodable JPEG", i);
+      offs[i] = total;
+      total += (static_cast<size_t>(h_[0]) * w_[0] * 3 + 255) & ~size_t(255);
+    }
+    reserve_rgb(e, total);
+    for (int i = 0; i < n; ++i) {
+      int h = 0, w = 0;
+      decode_jpeg_to_device(e, jpgs[i], lens[i], offs[i], &h, &w);
+      launch_preprocess(e, e->d_rgb + offs[i], h, w, i);
+    }
+    run_tower(*e, e->d_input, false, n, k, nullptr, e->stream, true);
+    CK(cudaMemcpyAsync(topk_vals, e->d_topk_val, static_cast<size_t>(n) * k * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(topk_idx, e->d_topk_idx, static_cast<size_t>(n) * k * 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
   });

@@ -55,6 +55,12 @@ SIGNATURES = {
     "icp_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "icp_classify_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _f32p, _i32p]),
     "icp_preprocess_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p]),
+    "icp_classify_jpeg": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, _f32p, _i32p]),
+    "icp_decode_jpeg": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, _u8p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "icp_jpeg_backend": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "icp_classify_batch_rgb8": (C.c_int, [C.c_void_p, C.POINTER(_u8p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                          _f32p, _i32p]),
+    "icp_classify_batch_jpeg": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, _f32p, _i32p]),
     "icp_endpoint_shape": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int * 4)]),
     "icp_endpoint": (C.c_int, [C.c_void_p, C.c_char_p, _f32p]),
     "icp_last_forward_ms": (C.c_int, [C.c_void_p, _f32p]),
@@ -222,6 +228,56 @@ class Engine:
         idx = np.empty(k, np.int32)
         _check(self._lib.icp_classify_rgb8(self._h, rgb.ctypes.data_as(_u8p), rgb.shape[0], rgb.shape[1], k,
                                            _f32(vals), idx.ctypes.data_as(_i32p)), self._h)
+        return vals, idx
+
+    # ------------------------------------------------------------------ JPEG in (nvJPEG on the GPU)
+    JPEG_BACKENDS = {-1: "none", 0: "default", 1: "hybrid (CPU Huffman + GPU IDCT)", 2: "gpu_hybrid (GPU Huffman)",
+                     3: "hardware engine", 4: "gpu_hybrid_device", 5: "hardware_device"}
+
+    def classify_jpeg(self, jpeg: bytes, k: int = 5) -> Tuple[np.ndarray, np.ndarray]:
+        """The reference's request: JPEG bytes -> (top-k probabilities, indices); decode, crop/resize, tower on the GPU."""
+        vals = np.empty(k, np.float32)
+        idx = np.empty(k, np.int32)
+        _check(self._lib.icp_classify_jpeg(self._h, jpeg, len(jpeg), k, _f32(vals), idx.ctypes.data_as(_i32p)), self._h)
+        return vals, idx
+
+    def decode_jpeg(self, jpeg: bytes) -> np.ndarray:
+        h, w = C.c_int(), C.c_int()
+        _check(self._lib.icp_decode_jpeg(self._h, jpeg, len(jpeg), None, 0, C.byref(h), C.byref(w)), self._h)
+        out = np.empty((h.value, w.value, 3), np.uint8)
+        _check(self._lib.icp_decode_jpeg(self._h, jpeg, len(jpeg), out.ctypes.data_as(_u8p), out.nbytes, C.byref(h),
+                                         C.byref(w)), self._h)
+        return out
+
+    @property
+    def jpeg_backend(self) -> str:
+        v = C.c_int()
+        _check(self._lib.icp_jpeg_backend(self._h, C.byref(v)), self._h)
+        return self.JPEG_BACKENDS.get(v.value, str(v.value))
+
+    # ------------------------------------------------------------------ micro-batched requests
+    def classify_batch_rgb8(self, images, k: int = 5) -> Tuple[np.ndarray, np.ndarray]:
+        """images: sequence of uint8 [h,w,3] arrays of any sizes -> (vals [n,k], idx [n,k]) from ONE tower launch."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        for im in imgs:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError("expected uint8 [H,W,3]")
+        ptrs = (_u8p * n)(*[im.ctypes.data_as(_u8p) for im in imgs])
+        hs = (C.c_int * n)(*[im.shape[0] for im in imgs])
+        ws = (C.c_int * n)(*[im.shape[1] for im in imgs])
+        vals = np.empty((n, k), np.float32)
+        idx = np.empty((n, k), np.int32)
+        _check(self._lib.icp_classify_batch_rgb8(self._h, ptrs, hs, ws, n, k, _f32(vals), idx.ctypes.data_as(_i32p)), self._h)
+        return vals, idx
+
+    def classify_batch_jpeg(self, jpegs, k: int = 5) -> Tuple[np.ndarray, np.ndarray]:
+        n = len(jpegs)
+        ptrs = (C.c_char_p * n)(*jpegs)
+        lens = (C.c_size_t * n)(*[len(j) for j in jpegs])
+        vals = np.empty((n, k), np.float32)
+        idx = np.empty((n, k), np.int32)
+        _check(self._lib.icp_classify_batch_jpeg(self._h, ptrs, lens, n, k, _f32(vals), idx.ctypes.data_as(_i32p)), self._h)
         return vals, idx
 
     def preprocess_rgb8(self, rgb: np.ndarray) -> np.ndarray:

@@ -33,6 +33,7 @@ def _jpeg(h=60, w=80, mode="RGB"):
 @pytest.fixture
 def clf(monkeypatch, tmp_path):
     monkeypatch.setattr(P._engine, "Engine", FakeEngine)
+    monkeypatch.setenv("ICP_JPEG", "pil")             # host libjpeg decode -> classify_rgb8
     labels = tmp_path / "synset.txt"
     labels.write_text("daisy\ndandelion\nroses\nsunflowers\ntulips\n")
     model = tmp_path / "model"
@@ -77,3 +78,35 @@ def test_missing_files_raise(monkeypatch, tmp_path):
     monkeypatch.setattr(P._engine, "Engine", FakeEngine)
     with pytest.raises(Exception, match="missing"):
         P.ImagenetClassifier(str(tmp_path / "nope"), str(tmp_path / "nope2"))     # :140-143
+
+
+def test_nvjpeg_route_and_fallback_to_libjpeg(monkeypatch, tmp_path):
+    """Default route: the JPEG bytes go to the engine untouched (icp_classify_jpeg); a stream nvJPEG refuses
+    (ICP_E_INVALID) is retried through PIL -> classify_rgb8; any other engine error is an error (None)."""
+    class JpegEngine(FakeEngine):
+        mode = "ok"
+
+        def classify_jpeg(self, data, k):
+            self.calls.append(("jpeg", len(data)))
+            if self.mode == "refuse":
+                raise P._engine.EngineError(-1, "unsupported stream")
+            if self.mode == "broken":
+                raise P._engine.EngineError(-3, "cuda")
+            return np.float32([0.4, 0.3, 0.2, 0.05, 0.05])[:k], np.int32([1, 2, 3, 4, 5])[:k]
+
+    monkeypatch.setattr(P._engine, "Engine", JpegEngine)
+    monkeypatch.delenv("ICP_JPEG", raising=False)
+    labels = tmp_path / "synset.txt"
+    labels.write_text("daisy\ndandelion\nroses\nsunflowers\ntulips\n")
+    model = tmp_path / "model"
+    model.write_bytes(b"x")
+    clf = P.ImagenetClassifier(str(model), str(labels))
+    assert clf.decode_backend == "nvjpeg"
+    data = _jpeg()
+    out = clf.classify_image(data)
+    assert out[0] == ["daisy", "dandelion", "roses"] and clf.engine.calls == [("jpeg", len(data))]
+    clf.engine.mode = "refuse"
+    out = clf.classify_image(data)
+    assert out[0] == ["roses", "none", "tulips"] and clf.engine.calls[-1] == (60, 80, 3)
+    clf.engine.mode = "broken"
+    assert clf.classify_image(data) is None
