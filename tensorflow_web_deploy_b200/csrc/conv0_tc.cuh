@@ -89,10 +89,12 @@ conv0_tc_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_co
     *reinterpret_cast<uint4*>(gbase + (w_base - base) + n * 64 + ((c ^ ((n >> 1) & 3)) << 4)) = v;
     ptx::fence_proxy_async_smem();
   }
+  ptx::pdl_launch();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  ptx::pdl_wait();
 
   if (warp < 16) {
     // ---------------- A builders: one output pixel (one 64-byte operand row) per thread and tile ----------------

@@ -136,10 +136,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     write_ones_row(gbase + (ones_base - base), static_cast<int>(threadIdx.x) - 64, a.fmt);
     ptx::fence_proxy_async_smem();
   }
+  ptx::pdl_launch();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  ptx::pdl_wait();            // the predecessor's output (this layer's input) is complete from here on
 
   // Every role loop runs warp-converged and hands the uniform-datapath instructions (TMA, MMA, commit) to one
   // elected lane: under `if (lane == 0)` the compiler wraps each of them in an ELECT/branch loop, which cost this

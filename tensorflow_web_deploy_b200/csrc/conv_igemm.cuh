@@ -187,10 +187,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     write_ones_row(gbase + (ones_base - base), static_cast<int>(threadIdx.x) - 64, a.fmt);
     ptx::fence_proxy_async_smem();
   }
+  ptx::pdl_launch();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  ptx::pdl_wait();            // the predecessor's output (this layer's input) is complete from here on
 
   // Role loops run warp-converged; one elected lane issues the TMA / MMA / commit instructions (under a plain
   // `if (lane == 0)` the compiler wraps each of them in an ELECT + branch loop).
@@ -449,6 +451,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const int step = static_cast<int>(gridDim.x) / (kCluster ? 2 : 1);
   auto tile_m0 = [&](int t) { return ((t / n_tiles) * (kCluster ? 2 : 1) + static_cast<int>(crank)) * kBM; };
 
+  ptx::pdl_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
@@ -484,6 +487,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   if constexpr (kCluster) ptx::cluster_sync();   // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  ptx::pdl_wait();            // prologue above overlapped the predecessor's tail; its output is complete from here on
 
   if (warp == 0 || warp == 11) {
     // ---------------- TMA producers #1: A tiles (warp-converged; one elected lane issues) ----------------

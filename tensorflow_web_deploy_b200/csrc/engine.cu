@@ -17,6 +17,7 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/inception_b200.h"
@@ -282,6 +283,36 @@ struct ConvLayer {
 };
 
 static int g_num_sms = 148;
+
+// Every tower kernel goes through cudaLaunchKernelEx so that it can carry the programmatic-dependent-launch
+// attribute (ptx.cuh pdl_wait / pdl_launch): `pdl` is set when the previous operation enqueued on the same stream
+// was one of this library's kernels (see PdlTracker) — then its prologue overlaps that kernel's tail.
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, int cluster,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
 static int pick_n_tile(int cout) {
   if (cout <= 256) return cout;
   for (int parts = 2; parts <= 16; ++parts)
@@ -605,7 +636,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   return L;
 }
 
-static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
+static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = false) {
   if (L.halo) {
     HaloArgs h = L.hargs;
     h.n_images = n;
@@ -614,13 +645,12 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(items < g_num_sms ? items : g_num_sms);
     const bool stem = h.w_resident && !h.tall && !h.transpose_out;
     if (h.epi_direct) {
-      if (stem) conv_halo_kernel<true, true><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
-      else conv_halo_kernel<true, false><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
+      if (stem) launch_k(conv_halo_kernel<true, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
+      else launch_k(conv_halo_kernel<true, false>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
     } else {
-      if (stem) conv_halo_kernel<false, true><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
-      else conv_halo_kernel<false, false><<<grid, kHaloThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_bias, h);
+      if (stem) launch_k(conv_halo_kernel<false, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
+      else launch_k(conv_halo_kernel<false, false>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
     }
-    CK(cudaGetLastError());
     return;
   }
   ConvArgs a = L.args;
@@ -630,31 +660,19 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st) {
     if (L.cluster && m_tiles >= L.cluster_min_tiles * g_num_sms) {
       const int items = ((m_tiles + 1) / 2) * L.n_tiles;
       const int max_clusters = g_num_sms / 2;
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2 * (items < max_clusters ? items : max_clusters));
-      cfg.blockDim = dim3(kPersistThreads);
-      cfg.dynamicSmemBytes = L.smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      CK(cudaLaunchKernelEx(&cfg, conv_igemm_persistent_kernel<true>, L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half,
-                            L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles));
+      launch_k(conv_igemm_persistent_kernel<true>, 2 * (items < max_clusters ? items : max_clusters), kPersistThreads, L.smem,
+               st, pdl, 2, L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2,
+               L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
       return;
     }
     const int total = m_tiles * L.n_tiles;
-    conv_igemm_persistent_kernel<false><<<total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st>>>(
-        L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64,
-        L.tm_o64_2, a, m_tiles, L.n_tiles);
+    launch_k(conv_igemm_persistent_kernel<false>, total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st, pdl, 1,
+             L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64,
+             L.tm_o64_2, a, m_tiles, L.n_tiles);
   } else {
-    dim3 grid(m_tiles, L.n_tiles);
-    conv_igemm_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_bias, a);
+    launch_k(conv_igemm_kernel, dim3(m_tiles, L.n_tiles), kConvThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_a_tail,
+             L.tm_b_tail, L.tm_bias, a);
   }
-  CK(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------ plan ops
@@ -1180,40 +1198,69 @@ struct Builder {
   }
 };
 
-static int run_op(const Op& op, int n, int fmt, cudaStream_t st, int out_image0 = 0) {
+// ICP_NO_PDL=1 launches every kernel with full stream serialisation (A/B switch).
+static bool pdl_enabled() {
+  static const bool on = getenv("ICP_NO_PDL") == nullptr;
+  return on;
+}
+// Which streams' most recent operation was one of our kernels (only then may the next launch on that stream be
+// programmatic: behind an event wait, a memcpy or a timing event it keeps the full dependency).
+struct PdlTracker {
+  cudaStream_t s[8] = {};
+  bool k[8] = {};
+  int find(cudaStream_t st) {
+    for (int i = 0; i < 8; ++i)
+      if (s[i] == st || (!s[i] && !k[i])) { s[i] = st; return i; }
+    return 0;
+  }
+  bool take(cudaStream_t st) {            // -> launch this kernel with the attribute?  (and note that a kernel follows)
+    const int i = find(st);
+    const bool r = k[i] && pdl_enabled();
+    k[i] = true;
+    return r;
+  }
+  void barrier(cudaStream_t st) { k[find(st)] = false; }     // an event wait / record-for-timing / copy was enqueued
+};
+
+static int run_op(const Op& op, int n, int fmt, cudaStream_t st, int out_image0 = 0, bool pdl = false) {
   switch (op.kind) {
     case Op::CONV:
-      launch_conv(op.conv, n, st);
+      launch_conv(op.conv, n, st, pdl);
       return 1;
     case Op::MAXPOOL: {
       const unsigned per_image = static_cast<unsigned>(op.out.h) * ((op.out.w + 1) / 2) * (op.c / 8);
-      maxpool3s2_kernel<<<dim3((per_image + 255) / 256, n), 256, 0, st>>>(
-          op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, 0,
-          op.out.p + static_cast<size_t>(out_image0) * op.out.h * op.out.w * op.out.c, op.out.h, op.out.w, op.out.c,
-          op.out_coff, fmt);
-      CK(cudaGetLastError());
+      launch_k(maxpool3s2_kernel, dim3((per_image + 255) / 256, n), 256, 0, st, pdl, 1, (const uint16_t*)op.in.p, n, op.in.h,
+               op.in.w, op.c, op.in.c, 0, op.out.p + static_cast<size_t>(out_image0) * op.out.h * op.out.w * op.out.c,
+               op.out.h, op.out.w, op.out.c, op.out_coff, fmt);
       return 1;
     }
     case Op::AVGPOOL: {
       const long long total = static_cast<long long>(n) * op.out.h * op.out.w * (op.c / 8);
       if (op.post_relu && op.k == 3 && op.stride == 1 && op.pad == 1) {
-        // band of rows per CTA: the staged tile fits 96 KiB and, when the batch is small, there are >= 2 CTAs per SM
+        // band of rows per CTA: the staged tile fits 100 KiB; more bands only when the batch alone cannot fill the SMs
         const int per_row = (op.in.w + 2) * op.c * 2;
-        int max_rows = 98304 / per_row - 2;
+        const int max_rows = 102400 / per_row - 2;
         if (max_rows < 1) fail(ICP_E_INVALID, "avg_pool tile of %d x %d channels does not fit shared memory", op.in.w, op.c);
         int bands = (op.in.h + max_rows - 1) / max_rows;
-        while (n * bands < 2 * g_num_sms && (op.in.h + bands) / (bands + 1) >= 4) ++bands;
+        while (n * bands < g_num_sms && (op.in.h + bands) / (bands + 1) >= 3) ++bands;
         const int band_rows = (op.in.h + bands - 1) / bands;
         bands = (op.in.h + band_rows - 1) / band_rows;
         const size_t smem = static_cast<size_t>(band_rows + 2) * per_row;
-        avgpool3_relu_kernel<<<static_cast<unsigned>(n * bands), 256, smem, st>>>(
-            op.in.p, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.c, op.out_coff, band_rows, bands, 1, fmt);
+        const int cg = op.c / 8;
+        int threads = (op.in.w * cg + 31) & ~31;
+        if (threads > 512) threads = 512;
+        const unsigned grid = static_cast<unsigned>(n * bands);
+#define ICP_POOL_ARGS (const uint16_t*)op.in.p, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.c, op.out_coff, band_rows, bands, 1, fmt
+        if (cg == 4) launch_k(avgpool3_relu_kernel<4>, grid, threads, smem, st, pdl, 1, ICP_POOL_ARGS);
+        else if (cg == 8) launch_k(avgpool3_relu_kernel<8>, grid, threads, smem, st, pdl, 1, ICP_POOL_ARGS);
+        else if (cg == 24) launch_k(avgpool3_relu_kernel<24>, grid, threads, smem, st, pdl, 1, ICP_POOL_ARGS);
+        else launch_k(avgpool3_relu_kernel<0>, grid, threads, smem, st, pdl, 1, ICP_POOL_ARGS);
+#undef ICP_POOL_ARGS
       } else {
-        avgpool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-            op.in.p, n, op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff,
-            op.k, op.stride, op.pad, nullptr, nullptr, 0, fmt);
+        launch_k(avgpool_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, pdl, 1, (const uint16_t*)op.in.p, n,
+                 op.in.h, op.in.w, op.c, op.in.c, op.in_coff, op.out.p, op.out.h, op.out.w, op.out.c, op.out_coff, op.k,
+                 op.stride, op.pad, (const float*)nullptr, (const float*)nullptr, 0, fmt);
       }
-      CK(cudaGetLastError());
       return 1;
     }
   }
@@ -1222,21 +1269,19 @@ static int run_op(const Op& op, int n, int fmt, cudaStream_t st, int out_image0 
 
 // Head: pooled features -> (partial) logits -> softmax -> top-k (tower_kernels.cuh); returns the launches made.
 static int launch_head(icp_engine& e, const uint16_t* fmap, int hw, int F, int ld, const float* w, const float* b,
-                       float* logits, float* probs, float* feat, float* part, int n, int k, cudaStream_t st) {
+                       float* logits, float* probs, float* feat, float* part, int n, int k, cudaStream_t st, bool pdl) {
   if (F % kHeadSlice) fail(ICP_E_INVALID, "head: %d features is not a multiple of %d", F, kHeadSlice);
   const int C = e.C, slices = F / kHeadSlice;
   const bool small = C <= kHeadSmallC;
+  const bool chain = pdl_enabled();
   int launches = 2;
-  head_pool_kernel<<<dim3(n, slices), 256, 0, st>>>(fmap, hw, F, ld, feat, w, C, part, e.fmt);
-  CK(cudaGetLastError());
+  launch_k(head_pool_kernel, dim3(n, slices), 256, 0, st, pdl, 1, fmap, hw, F, ld, feat, w, C, part, e.fmt);
   if (!small) {
-    head_fc_kernel<<<dim3((C + 63) / 64, (n + 15) / 16), 256, 0, st>>>(feat, n, F, w, b, C, logits);
-    CK(cudaGetLastError());
+    launch_k(head_fc_kernel, dim3((C + 63) / 64, (n + 15) / 16), 256, 0, st, chain, 1, (const float*)feat, n, F, w, b, C, logits);
     ++launches;
   }
-  head_finish_kernel<<<n, 256, C * sizeof(float), st>>>(small ? part : nullptr, slices, b, C, logits, probs, e.d_topk_val,
-                                                       e.d_topk_idx, probs ? k : 0);
-  CK(cudaGetLastError());
+  launch_k(head_finish_kernel, n, 256, C * sizeof(float), st, chain, 1, (const float*)(small ? part : nullptr), slices, b, C,
+           logits, probs, e.d_topk_val, e.d_topk_idx, probs ? k : 0);
   return launches;
 }
 
@@ -1257,7 +1302,11 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
                          cudaStream_t st, OpTimer* tm = nullptr) {
   int launches = 0;
   const int fmt = e.fmt;
-  if (tm) tm->mark();
+  PdlTracker pdl;
+  auto mark = [&](cudaStream_t s_) {
+    if (tm) { tm->mark(); pdl.barrier(s_); }
+  };
+  mark(st);
   // Optional (ICP_STEM_CHUNK=<images>, default off): run the stem in passes over the SAME chunk-sized region of the
   // intermediate buffers so that each producer->consumer pair (<= 88 MB at 32 images) stays in the 126 MB L2
   // instead of making a round trip through HBM.  MEASURED at batch 128: 2.544 ms whole batch, 2.59 / 2.63 / 2.73 ms
@@ -1271,26 +1320,32 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
     const long long pix = static_cast<long long>(nc) * o.h * o.w;
     const unsigned grid = static_cast<unsigned>((pix + 127) / 128);
     const size_t in_off = static_cast<size_t>(i0) * e.S * e.S * 3;
+    // conv0 follows a copy / another stream's work: full dependency (its successors chain programmatically)
+    const bool p0 = i0 > 0 && pdl.take(st);
+    if (i0 == 0) pdl.take(st);
     if (e.conv0_tc) {
       const unsigned tgrid = grid < static_cast<unsigned>(g_num_sms) ? grid : static_cast<unsigned>(g_num_sms);
       if (x_is_u8)
-        conv0_tc_kernel<uint8_t><<<tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st>>>(
-            static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_u8, o.p, o.h, o.w, fmt);
+        launch_k(conv0_tc_kernel<uint8_t>, tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st, p0, 1,
+                 static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_u8, o.p, o.h, o.w, fmt);
       else
-        conv0_tc_kernel<float><<<tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st>>>(
-            static_cast<const float*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_f, o.p, o.h, o.w, fmt);
-    } else if (x_is_u8)
+        launch_k(conv0_tc_kernel<float>, tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st, p0, 1,
+                 static_cast<const float*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_f, o.p, o.h, o.w, fmt);
+    } else if (x_is_u8) {
       conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0,
                                                   o.p, o.h, o.w, fmt);
-    else
+      pdl.barrier(st);            // conv0_kernel has no griddepcontrol.launch: its successor keeps the full dependency
+    } else {
       conv0_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x_dev) + in_off, nc, e.S, e.S, e.conv0, o.p,
                                                 o.h, o.w, fmt);
+      pdl.barrier(st);
+    }
     CK(cudaGetLastError());
     ++launches;
-    if (tm) tm->mark();
+    mark(st);
     for (size_t i = 0; i < e.stem_ops; ++i) {
-      launches += run_op(e.ops[i], nc, fmt, st, i + 1 == e.stem_ops ? i0 : 0);
-      if (tm) tm->mark();
+      launches += run_op(e.ops[i], nc, fmt, st, i + 1 == e.stem_ops ? i0 : 0, pdl.take(st));
+      mark(st);
     }
   }
   // Independent branches of an inception block run on side streams between FORK and JOIN markers when one
@@ -1308,6 +1363,7 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
         if (lane_live[i]) {
           CK(cudaEventRecord(e.join_ev[i], e.lane_stream[i]));
           CK(cudaStreamWaitEvent(st, e.join_ev[i], 0));
+          pdl.barrier(st);
           lane_live[i] = false;
         }
       continue;
@@ -1317,21 +1373,22 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
       os = e.lane_stream[op.lane];
       if (!lane_live[op.lane]) {
         CK(cudaStreamWaitEvent(os, e.fork_ev, 0));
+        pdl.barrier(os);
         lane_live[op.lane] = true;
       }
     }
-    launches += run_op(op, n, fmt, os);
-    if (tm) tm->mark();
+    launches += run_op(op, n, fmt, os, 0, pdl.take(os));
+    mark(os);
   }
   if (e.cfg.enable_aux && !tm) {
-    for (const Op& op : e.aux_ops) launches += run_op(op, n, fmt, st);
+    for (const Op& op : e.aux_ops) launches += run_op(op, n, fmt, st, 0, pdl.take(st));
     launches += launch_head(e, e.aux_feat.p, 1, 768, e.aux_feat.c, e.d_aux_w, e.d_aux_b, e.d_aux_logits, nullptr,
-                            e.d_aux_feat, e.d_aux_part, n, 0, st);
+                            e.d_aux_feat, e.d_aux_part, n, 0, st, pdl.take(st));
   }
   const Act& f = e.final_act;
   launches += launch_head(e, f.p, f.h * f.w, f.c, f.c, e.d_fc_w, e.d_fc_b, e.d_logits, probs_dev ? probs_dev : e.d_probs,
-                          e.d_feat, e.d_part, n, k, st);
-  if (tm) tm->mark();
+                          e.d_feat, e.d_part, n, k, st, pdl.take(st));
+  mark(st);
   return launches;
 }
 
@@ -1411,7 +1468,10 @@ static void set_kernel_attrs(int device) {
                           static_cast<int>(conv0_tc_smem_bytes())));
   CK(cudaFuncSetAttribute(conv0_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           static_cast<int>(conv0_tc_smem_bytes())));
-  CK(cudaFuncSetAttribute(avgpool3_relu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CK(cudaFuncSetAttribute(avgpool3_relu_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CK(cudaFuncSetAttribute(avgpool3_relu_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CK(cudaFuncSetAttribute(avgpool3_relu_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CK(cudaFuncSetAttribute(avgpool3_relu_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   CK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, device));
   if (const char* v = getenv("ICP_MBAR_TIMEOUT_MS")) {
     const long long cycles = atoll(v) * 1900000LL;     // ~1.9 GHz SM clock

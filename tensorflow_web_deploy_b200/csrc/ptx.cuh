@@ -63,6 +63,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: pdl_launch() (issued by every CTA of the predecessor, here right at its start) lets the
+// runtime place the successor's CTAs on SMs as they free up, and pdl_wait() in the successor blocks until the
+// predecessor has COMPLETED and its writes are visible.  Everything a kernel does before pdl_wait() — barrier init,
+// tcgen05.alloc, tensor-map prefetch, constant tiles — therefore overlaps the predecessor's tail and the launch
+// latency.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -7,6 +7,8 @@
 #include <cfloat>
 #include <cstdint>
 
+#include "ptx.cuh"
+
 namespace icp {
 
 __device__ __forceinline__ float h2f(uint16_t h, int fmt) {
@@ -147,6 +149,8 @@ __device__ __forceinline__ uint4 max8_h16(const uint4& a, const uint4& b, int fm
 }
 __global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
                                   uint16_t* __restrict__ out, int OH, int OW, int ldo, int coff, int fmt) {
+  ptx::pdl_launch();
+  ptx::pdl_wait();
   const unsigned cg = static_cast<unsigned>(C) >> 3;
   const unsigned pairs = (static_cast<unsigned>(OW) + 1u) >> 1;
   const unsigned per_image = static_cast<unsigned>(OH) * pairs * cg;
@@ -189,6 +193,8 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, in
                                uint16_t* __restrict__ out, int OH, int OW, int ldo, int coff, int k, int stride,
                                int pad, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                                int fmt) {
+  ptx::pdl_launch();
+  ptx::pdl_wait();
   // scale/shift (nullable): the pool runs AFTER a linear 1x1 projection (avg-pool and a 1x1 conv
   // commute), so the projection's BatchNorm + ReLU (ops.py:231-245) are applied here, on the pooled value.
   const int cg = C / 8;
@@ -261,52 +267,74 @@ __device__ __forceinline__ void acc8(float (&s)[8], const uint4& v, int fmt) {
     }
   }
 }
-__global__ void __launch_bounds__(256)
+// horizontal 3-sum of one tile row at padded columns (x, x+1, x+2): p[0], p[cg], p[2 cg]
+__device__ __forceinline__ void hsum3(float (&h)[8], const uint4* p, int cg, int fmt) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = 0.f;
+  acc8(h, p[0], fmt);
+  acc8(h, p[cg], fmt);
+  acc8(h, p[2 * cg], fmt);
+}
+// CG = channel groups (C / 8) as a compile-time constant for the tower's widths (4, 8, 24: the index arithmetic
+// divides by it), 0 = generic.  After staging, one thread owns one (column, channel group) and walks DOWN the band
+// keeping the horizontal 3-sums of the last three rows: 3 LDS.128 + ~70 instructions per output vector instead of
+// 9 LDS.128 + ~300 (the first smem version recomputed all nine taps and the pixel index per output: it was
+// instruction-bound at 22 us for the 17x17x192 slice).
+template <int CG>
+__global__ void __launch_bounds__(512)
 avgpool3_relu_kernel(const uint16_t* __restrict__ in, int H, int W, int C, int ldi, int cin_off,
                      uint16_t* __restrict__ out, int ldo, int coff, int band_rows, int bands, int relu, int fmt) {
+  ptx::pdl_launch();
+  ptx::pdl_wait();
   extern __shared__ uint4 pool_tile[];          // [(band_rows + 2)][(W + 2)][C / 8] 16-byte vectors
+  const int cg = CG ? CG : (C >> 3);
   const int n = blockIdx.x / bands;
   const int y0 = (blockIdx.x - n * bands) * band_rows;
   const int rows = min(band_rows, H - y0);
-  const int cg = C >> 3;
   const int wp = W + 2;
-  const int tile_vecs = (rows + 2) * wp * cg;
+  const int row_vecs = wp * cg;
   const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(pool_tile));
   const uint16_t* img = in + static_cast<size_t>(n) * H * W * ldi + cin_off;
-  for (int v = threadIdx.x; v < tile_vecs; v += blockDim.x) {
-    const int g = v % cg;
-    const int t = v / cg;
-    const int tx = t % wp, ty = t / wp;
-    const int iy = y0 - 1 + ty, ix = tx - 1;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-      cp_async16(tile_s + static_cast<uint32_t>(v) * 16u, img + (static_cast<size_t>(iy) * W + ix) * ldi + g * 8);
-    else
-      pool_tile[v] = make_uint4(0u, 0u, 0u, 0u);
+  for (int ty = 0; ty < rows + 2; ++ty) {
+    const int iy = y0 - 1 + ty;
+    const bool rin = iy >= 0 && iy < H;
+    const uint16_t* src_row = img + static_cast<size_t>(iy) * W * ldi;
+    for (int v = threadIdx.x; v < row_vecs; v += blockDim.x) {
+      const int g = v % cg;
+      const int ix = v / cg - 1;
+      const int t = ty * row_vecs + v;
+      if (rin && ix >= 0 && ix < W) cp_async16(tile_s + static_cast<uint32_t>(t) * 16u, src_row + static_cast<size_t>(ix) * ldi + g * 8);
+      else pool_tile[t] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int out_vecs = rows * W * cg;
   uint16_t* obase = out + static_cast<size_t>(n) * H * W * ldo + coff;
-  for (int v = threadIdx.x; v < out_vecs; v += blockDim.x) {
+  for (int v = threadIdx.x; v < W * cg; v += blockDim.x) {
     const int g = v % cg;
-    const int t = v / cg;
-    const int ox = t % W, ty = t / W;
-    const int oy = y0 + ty;
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint4* c0 = pool_tile + (ty * wp + ox) * cg + g;      // top-left tap (padded coordinates)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) acc8(s, c0[(r * wp + q) * cg], fmt);
-    const int rows_in = 3 - (oy == 0) - (oy == H - 1);
+    const int ox = v / cg;
     const int cols_in = 3 - (ox == 0) - (ox == W - 1);
-    const float inv = 1.0f / static_cast<float>(rows_in * cols_in);
+    const uint4* p = pool_tile + ox * cg + g;
+    float h0[8], h1[8], h2[8];
+    hsum3(h0, p, cg, fmt);
+    hsum3(h1, p + row_vecs, cg, fmt);
+    uint16_t* o = obase + (static_cast<size_t>(y0) * W + ox) * ldo + g * 8;
+    for (int ty = 0; ty < rows; ++ty) {
+      hsum3(h2, p + (ty + 2) * row_vecs, cg, fmt);
+      const int oy = y0 + ty;
+      const int rows_in = 3 - (oy == 0) - (oy == H - 1);
+      const float inv = 1.0f / static_cast<float>(rows_in * cols_in);
+      float s[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j] *= inv;
-      if (relu) s[j] = fmaxf(s[j], 0.f);
+      for (int j = 0; j < 8; ++j) {
+        s[j] = (h0[j] + h1[j] + h2[j]) * inv;
+        if (relu) s[j] = fmaxf(s[j], 0.f);
+        h0[j] = h1[j];
+        h1[j] = h2[j];
+      }
+      *reinterpret_cast<uint4*>(o) = pack8(s, fmt);
+      o += static_cast<size_t>(W) * ldo;
     }
-    *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(oy) * W + ox) * ldo + g * 8) = pack8(s, fmt);
   }
 }
 
@@ -330,6 +358,8 @@ constexpr int kHeadSlice = 256;      // channels per head_pool CTA
 __global__ void __launch_bounds__(256)
 head_pool_kernel(const uint16_t* __restrict__ feat_map, int hw, int F, int ld, float* __restrict__ feat,
                  const float* __restrict__ fc_w /*[F][C]*/, int C, float* __restrict__ part /*[n][F/256][C]*/, int fmt) {
+  ptx::pdl_launch();
+  ptx::pdl_wait();
   __shared__ float red[8][kHeadSlice];
   __shared__ float fs[kHeadSlice];
   const int n = blockIdx.x, sl = blockIdx.y;
@@ -370,6 +400,8 @@ head_pool_kernel(const uint16_t* __restrict__ feat_map, int hw, int F, int ld, f
 __global__ void __launch_bounds__(256)
 head_fc_kernel(const float* __restrict__ feat, int n, int F, const float* __restrict__ fc_w, const float* __restrict__ fc_b,
                int C, float* __restrict__ logits) {
+  ptx::pdl_launch();
+  ptx::pdl_wait();
   __shared__ float fs[16][256];
   __shared__ float red[4][16][64];
   const int c = blockIdx.x * 64 + (threadIdx.x & 63);
@@ -410,6 +442,8 @@ __global__ void __launch_bounds__(256)
 head_finish_kernel(const float* __restrict__ part, int slices, const float* __restrict__ fc_b, int C,
                    float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ topk_val,
                    int* __restrict__ topk_idx, int k) {
+  ptx::pdl_launch();
+  ptx::pdl_wait();
   extern __shared__ float lg[];      // [C]
   __shared__ float red[32];
   __shared__ int redi[32];

@@ -1,0 +1,329 @@
+"""Cross-process micro-batcher: many HTTP workers, ONE GPU-owner process per GPU.
+
+The reference runs N gunicorn workers, each with a private TF session and a private copy of the weights, each
+serving batch 1 (/root/reference/run.sh:1-3, PyClassification.py:248-252).  On a B200 a batch-1 tower uses ~1 % of
+the chip, so here the workers only parse HTTP; every request is handed to the process that owns the GPU, which
+merges whatever arrived within a short window into one tower launch (north_star: "requests are micro-batched"):
+
+    worker thread --(JPEG bytes in a shared-memory segment, 16-byte header on an AF_UNIX socket)--> GpuOwner
+    GpuOwner: collect up to `max_batch` requests, or until `window_ms` after the first one  ->
+              engine.classify_batch_jpeg(...)   (nvJPEG decode + crop/resize + ONE tower launch at batch n)
+              per-request fallback through libjpeg for streams nvJPEG refuses
+    GpuOwner --(status, top-5 values, top-5 indices)--> worker thread
+
+`BatcherClient.classify_image(bytes)` has the return contract of ImagenetClassifier.classify_image
+(PyClassification.py:205-218): (names[3], probs[:3], seconds, sum of top-5) or None on any error.
+
+Wire format (little-endian): request  = u32 magic | u32 length | u64 request id      (payload: shm[0:length])
+                             response = u64 request id | i32 status | i32 k | k f32 values | k i32 indices
+"""
+from __future__ import annotations
+
+import logging
+import os
+import queue
+import socket
+import struct
+import threading
+import time
+from multiprocessing import shared_memory
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+MAGIC = 0x49435042            # "ICPB"
+REQ = struct.Struct("<IIQ")
+RSP_HEAD = struct.Struct("<Qii")
+HELLO = struct.Struct("<I64s")     # shm size, shm name
+TOP_K = 5
+SHM_BYTES = 16 << 20          # largest request body a worker thread can hand over
+
+log = logging.getLogger("icp.batcher")
+
+
+def _recv_exact(sock: socket.socket, n: int) -> Optional[bytes]:
+    buf = bytearray()
+    while len(buf) < n:
+        chunk = sock.recv(n - len(buf))
+        if not chunk:
+            return None
+        buf += chunk
+    return bytes(buf)
+
+
+class _Pending:
+    __slots__ = ("conn", "lock", "req_id", "data", "t_arrival")
+
+    def __init__(self, conn, lock, req_id, data):
+        self.conn, self.lock, self.req_id, self.data = conn, lock, req_id, data
+        self.t_arrival = time.perf_counter()
+
+
+class GpuOwner:
+    """Owns one engine; serves every connected worker thread.  `engine` needs classify_batch_jpeg(list[bytes], k)
+    -> (vals[n,k], idx[n,k]) and classify_rgb8(rgb, k); tests inject a fake."""
+
+    def __init__(self, engine, socket_path: str, max_batch: int = 32, window_ms: float = 2.0,
+                 decode_fallback: Optional[Callable[[bytes], np.ndarray]] = None):
+        self.engine, self.path, self.max_batch, self.window = engine, socket_path, int(max_batch), window_ms * 1e-3
+        self.decode_fallback = decode_fallback
+        self.q: "queue.Queue[_Pending]" = queue.Queue()
+        self.stop_ev = threading.Event()
+        self.stats = {"requests": 0, "batches": 0, "max_batch_seen": 0, "errors": 0, "batch_hist": {}}
+        self._threads: List[threading.Thread] = []
+        self._listener: Optional[socket.socket] = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def start(self):
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.bind(self.path)
+        s.listen(256)
+        s.settimeout(0.2)
+        self._listener = s
+        for target in (self._accept_loop, self._batch_loop):
+            t = threading.Thread(target=target, daemon=True)
+            t.start()
+            self._threads.append(t)
+        return self
+
+    def stop(self):
+        self.stop_ev.set()
+        for t in self._threads:
+            t.join(timeout=2)
+        if self._listener is not None:
+            self._listener.close()
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+
+    # ------------------------------------------------------------------ connections
+    def _accept_loop(self):
+        while not self.stop_ev.is_set():
+            try:
+                conn, _ = self._listener.accept()
+            except socket.timeout:
+                continue
+            except OSError:
+                return
+            threading.Thread(target=self._serve_conn, args=(conn,), daemon=True).start()
+
+    def _serve_conn(self, conn: socket.socket):
+        shm = None
+        try:
+            hello = _recv_exact(conn, HELLO.size)
+            if hello is None:
+                return
+            size, name = HELLO.unpack(hello)
+            shm = shared_memory.SharedMemory(name=name.rstrip(b"\0").decode())
+            lock = threading.Lock()
+            while not self.stop_ev.is_set():
+                head = _recv_exact(conn, REQ.size)
+                if head is None:
+                    return
+                magic, length, req_id = REQ.unpack(head)
+                if magic != MAGIC or length > size:
+                    log.warning("bad request header from a worker; closing the connection")
+                    return
+                # the bytes are copied out of the segment here: the worker may reuse it as soon as it has its answer,
+                # and a 135 KB memcpy is ~10 us against a ~1 ms request
+                self.q.put(_Pending(conn, lock, req_id, bytes(shm.buf[:length])))
+        except OSError:
+            pass
+        finally:
+            if shm is not None:
+                shm.close()
+            try:
+                conn.close()
+            except OSError:
+                pass
+
+    # ------------------------------------------------------------------ batching
+    def _batch_loop(self):
+        while not self.stop_ev.is_set():
+            try:
+                first = self.q.get(timeout=0.1)
+            except queue.Empty:
+                continue
+            batch = [first]
+            deadline = time.perf_counter() + self.window
+            while len(batch) < self.max_batch:
+                left = deadline - time.perf_counter()
+                try:
+                    batch.append(self.q.get(timeout=max(left, 0)) if left > 0 else self.q.get_nowait())
+                except queue.Empty:
+                    break
+            self._run(batch)
+
+    def _run(self, batch: Sequence[_Pending]):
+        n = len(batch)
+        st = self.stats
+        st["requests"] += n
+        st["batches"] += 1
+        st["max_batch_seen"] = max(st["max_batch_seen"], n)
+        st["batch_hist"][n] = st["batch_hist"].get(n, 0) + 1
+        results = [None] * n
+        try:
+            vals, idx = self.engine.classify_batch_jpeg([p.data for p in batch], TOP_K)
+            results = [(vals[i], idx[i]) for i in range(n)]
+        except Exception as err:                        # one undecodable stream fails the batched call: go one by one
+            log.info("batched call failed (%s); retrying the %d requests individually", err, n)
+            for i, p in enumerate(batch):
+                results[i] = self._single(p.data)
+        for p, r in zip(batch, results):
+            if r is None:
+                st["errors"] += 1
+                payload = RSP_HEAD.pack(p.req_id, -1, 0)
+            else:
+                v, ix = r
+                k = len(v)
+                payload = RSP_HEAD.pack(p.req_id, 0, k) + np.asarray(v, "<f4").tobytes() + np.asarray(ix, "<i4").tobytes()
+            try:
+                with p.lock:
+                    p.conn.sendall(payload)
+            except OSError:
+                pass
+
+    def _single(self, data: bytes):
+        try:
+            v, ix = self.engine.classify_batch_jpeg([data], TOP_K)
+            return v[0], ix[0]
+        except Exception:
+            pass
+        if self.decode_fallback is not None:
+            try:
+                v, ix = self.engine.classify_rgb8(self.decode_fallback(data), TOP_K)
+                return v, ix
+            except Exception as err:
+                log.info("Classification error: %s", err)
+        return None
+
+
+class BatcherClient:
+    """What a worker holds instead of an ImagenetClassifier: same `classify_image` contract, the work happens in the
+    GPU-owner process(es).  One connection + shared-memory segment per (thread, owner); owners are used round-robin."""
+
+    def __init__(self, socket_paths: Sequence[str], label_names: Sequence[str], timeout_s: float = 30.0):
+        self.paths, self.label_names, self.timeout = list(socket_paths), list(label_names), timeout_s
+        self._tls = threading.local()
+        self._rr = 0
+        self._rr_lock = threading.Lock()
+        self._all = []
+        self._all_lock = threading.Lock()
+
+    def _conn(self, owner: int):
+        conns = getattr(self._tls, "conns", None)
+        if conns is None:
+            conns = self._tls.conns = {}
+        c = conns.get(owner)
+        if c is None:
+            s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            s.settimeout(self.timeout)
+            s.connect(self.paths[owner])
+            shm = shared_memory.SharedMemory(create=True, size=SHM_BYTES)
+            s.sendall(HELLO.pack(SHM_BYTES, shm.name.encode()))
+            c = conns[owner] = {"sock": s, "shm": shm, "next_id": 1}
+            with self._all_lock:
+                self._all.append(c)
+        return c
+
+    def _drop(self, owner: int):
+        c = self._tls.conns.pop(owner, None)
+        if c:
+            try:
+                c["sock"].close()
+            except OSError:
+                pass
+
+    def topk(self, image: bytes):
+        """JPEG bytes -> (values[k], indices[k]) or raises."""
+        if len(image) > SHM_BYTES:
+            raise ValueError("request body of %d bytes exceeds the %d-byte hand-over segment" % (len(image), SHM_BYTES))
+        with self._rr_lock:
+            owner = self._rr % len(self.paths)
+            self._rr += 1
+        for attempt in range(2):                        # one reconnect: the owner may have been restarted
+            c = self._conn(owner)
+            try:
+                c["shm"].buf[:len(image)] = image
+                rid = c["next_id"]
+                c["next_id"] += 1
+                c["sock"].sendall(REQ.pack(MAGIC, len(image), rid))
+                head = _recv_exact(c["sock"], RSP_HEAD.size)
+                if head is None:
+                    raise OSError("GPU owner closed the connection")
+                got_id, status, k = RSP_HEAD.unpack(head)
+                if got_id != rid:
+                    raise OSError("response id mismatch")
+                if status != 0:
+                    raise RuntimeError("classification failed in the GPU owner")
+                body = _recv_exact(c["sock"], 8 * k)
+                if body is None:
+                    raise OSError("truncated response")
+                return np.frombuffer(body[:4 * k], "<f4").copy(), np.frombuffer(body[4 * k:], "<i4").copy()
+            except OSError:
+                self._drop(owner)
+                if attempt:
+                    raise
+        raise OSError("unreachable")
+
+    def classify_image(self, image: bytes):
+        try:
+            t0 = time.time()
+            probs, labels = self.topk(image)
+            dt = time.time() - t0
+            names = [self.label_names[labels[0]], self.label_names[labels[1]], self.label_names[labels[2]]]
+            return names, probs[:3], dt, sum(probs)
+        except Exception as err:
+            logging.info("Classification error: %s", err)
+            return None
+
+    def close(self):
+        with self._all_lock:
+            for c in self._all:
+                try:
+                    c["sock"].close()
+                except OSError:
+                    pass
+                try:
+                    c["shm"].close()
+                    c["shm"].unlink()
+                except Exception:
+                    pass
+            self._all.clear()
+
+
+def owner_main(socket_path: str, weights_path: str, num_classes: int, device: int, max_batch: int, window_ms: float,
+               precision: str, ready_path: Optional[str] = None):
+    """Entry point of a GPU-owner process."""
+    from .. import engine as _engine
+    from ..PyClassification import decode_jpeg_rgb
+    logging.basicConfig(level=logging.INFO)
+    eng = _engine.Engine(weights_path, num_classes, device=device, max_batch=max_batch, precision=precision,
+                         use_cuda_graph=True)
+    # warm-up: capture the graphs of the common batch sizes before traffic arrives (PyClassification.py:221-226 warms
+    # the reference up with one request)
+    import io
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(np.zeros((64, 64, 3), np.uint8)).save(buf, "JPEG")
+    for n in sorted({1, 2, 4, 8, 16, max_batch}):
+        if n <= max_batch:
+            eng.classify_batch_jpeg([buf.getvalue()] * n, TOP_K)
+    owner = GpuOwner(eng, socket_path, max_batch, window_ms, decode_fallback=decode_jpeg_rgb).start()
+    if ready_path:
+        open(ready_path, "w").write(str(os.getpid()))
+    log.info("GPU owner pid %d: device %d, max_batch %d, window %.1f ms, socket %s", os.getpid(), device, max_batch,
+             window_ms, socket_path)
+    try:
+        while True:
+            time.sleep(1.0)
+            if os.getppid() == 1:          # parent gone
+                break
+    except KeyboardInterrupt:
+        pass
+    finally:
+        owner.stop()
+        if os.environ.get("ICP_OWNER_STATS"):
+            log.info("owner stats: %s", owner.stats)
+        eng.close()
