@@ -315,11 +315,18 @@ def owner_main(socket_path: str, weights_path: str, num_classes: int, device: in
         open(ready_path, "w").write(str(os.getpid()))
     log.info("GPU owner pid %d: device %d, max_batch %d, window %.1f ms, socket %s", os.getpid(), device, max_batch,
              window_ms, socket_path)
+    import json
     try:
         while True:
-            time.sleep(1.0)
+            time.sleep(0.5)
             if os.getppid() == 1:          # parent gone
                 break
+            try:                           # batch statistics for the load test (tools/http_bench.py)
+                with open(socket_path + ".stats.tmp", "w") as f:
+                    json.dump(owner.stats, f)
+                os.replace(socket_path + ".stats.tmp", socket_path + ".stats")
+            except OSError:
+                pass
     except KeyboardInterrupt:
         pass
     finally:

@@ -308,8 +308,10 @@ def test_preprocess_and_classify_request(eng_mod, synth6):
     eng.close()
 
 
-def test_imagenet_classifier_drop_in(synth6, tmp_path, built_lib):
-    """configs[0]: a JPEG through ImagenetClassifier.classify_image (PyClassification.py:205-218)."""
+def test_imagenet_classifier_drop_in(synth6, tmp_path, built_lib, monkeypatch):
+    """configs[0]: a JPEG through ImagenetClassifier.classify_image (PyClassification.py:205-218), host-libjpeg route
+    (the nvJPEG route has its own tests below)."""
+    monkeypatch.setenv("ICP_JPEG", "pil")
     from PIL import Image
     from oracle import inception_oracle as O
     from tensorflow_web_deploy_b200 import PyClassification as P
