@@ -158,6 +158,10 @@ int icp_conv2d_bn_relu(int device, int precision, const float* x, int n, int h, 
 int icp_pool2d(int device, int precision, int kind, const float* x, int n, int h, int w, int c, int k,
                int stride, int same, float* y);
 
+/* CRC-32C of a host buffer (needs no GPU): block checksums of TF V1 checkpoints (tf_checkpoint.py, the restore of
+ * PyClassification.py:166-172). */
+uint32_t icp_crc32c(const void* data, size_t n);
+
 const char* icp_version(void);
 
 #ifdef __cplusplus

@@ -58,15 +58,29 @@ class ImagenetClassifier(object):
         with open(class_labels_file, "rb") as f:
             for line in f.read().decode("utf-8").splitlines():
                 self.label_names.append(line)
+        # model_def_file: an ICPW blob, or the TF V1 checkpoint the reference restores (`data/model`, keys
+        # <var>/ExponentialMovingAverage, :166-172) — converted once into a blob next to a temp dir
+        self._converted = None
+        from . import tf_checkpoint
+        if tf_checkpoint.is_tf_checkpoint(model_def_file):
+            import tempfile
+            self._converted = tempfile.NamedTemporaryFile(prefix="icp_model_", suffix=".icpw", delete=False).name
+            tf_checkpoint.convert(model_def_file, self._converted, len(self.label_names))
+            model_def_file = self._converted
         device = int(os.environ.get("ICP_DEVICE", "0")) if device is None else device
         precision = os.environ.get("ICP_PRECISION", "fp16") if precision is None else precision
         self.engine = _engine.Engine(model_def_file, num_classes=len(self.label_names), device=device, max_batch=1,
                                      precision=precision, use_cuda_graph=use_cuda_graph)
+        if self._converted:
+            os.unlink(self._converted)          # the engine has read it
         self.top_k = min(NUM_TOP_CLASSES, len(self.label_names))
-        # JPEG decode: "nvjpeg" = on the GPU inside the engine (icp_classify_jpeg: the graph starts at the JPEG string,
-        # as the reference's does, PyClassification.py:150-151); "pil" = host libjpeg(-turbo), the decoder family TF's
-        # DecodeJpeg used, then icp_classify_rgb8.  Anything nvJPEG refuses (CMYK, arithmetic coding) falls back to PIL.
-        self.decode_backend = os.environ.get("ICP_JPEG", "nvjpeg").lower()
+        # JPEG decode (ICP_JPEG): "pil" (default) = host libjpeg(-turbo) — the decoder family TF's DecodeJpeg wraps, so
+        # the tower sees the pixels the reference's graph would — then icp_classify_rgb8; "nvjpeg" = on the GPU inside
+        # the engine (icp_classify_jpeg: JPEG string in, top-k out, no host pixel buffer).  MEASURED on B200 (nvJPEG
+        # GPU-hybrid backend, profiles/r02_nvjpeg_vs_libjpeg.md): decoded pixels differ from libjpeg's by up to 4 LSB
+        # (mean 0.5-0.7; different IDCT / chroma upsampling), which moves the scores of data/sample.jpg by 1.2e-3 —
+        # outside the 1e-3 bar, hence not the default.  Anything nvJPEG refuses (CMYK, arithmetic coding) falls back to PIL.
+        self.decode_backend = os.environ.get("ICP_JPEG", "pil").lower()
         # The reference's tf.Session.run is thread-safe and Flask's development server / gthread workers are threaded;
         # the engine keeps one set of staging buffers, so requests of one process are serialised here (the C ABI
         # also locks per engine).  Cost: nothing next to the tower; throughput comes from the micro-batcher (serving/).

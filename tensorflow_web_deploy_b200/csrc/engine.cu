@@ -484,6 +484,16 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     const int res_bytes = chunks * taps * tile_bytes;
     int strip_rows = 0, strip_bytes = 0, nstrips = 2, b_stages = 0, w_bytes = 0;
     bool resident = false, ok = false;
+    // Experiment (ICP_HALO_PREFER_RESIDENT=1): keep the weights resident even if that means shorter bands (T = 1)
+    static const bool prefer_res = getenv("ICP_HALO_PREFER_RESIDENT") != nullptr;
+    if (prefer_res && L.n_tiles == 1)
+      for (int Tr = T; Tr >= 1 && !ok; Tr >>= 1) {
+        const int sr = (kh - 1) + 1 + (wp - 1 + (Tr * kBM - 1) + (kw - 1)) / wp;
+        const int sb = ((sr * wp * rb) + 1023) & ~1023;
+        if (sr <= 256 && halo_smem_bytes(sb, 2, res_bytes) <= 225 * 1024) {
+          T = Tr; strip_rows = sr; strip_bytes = sb; resident = true; w_bytes = res_bytes; b_stages = 1; ok = true;
+        }
+      }
     for (; T >= 1 && !ok; T >>= 1) {
       strip_rows = (kh - 1) + 1 + (wp - 1 + (T * kBM - 1) + (kw - 1)) / wp;
       strip_bytes = ((strip_rows * wp * rb) + 1023) & ~1023;
@@ -1504,6 +1514,24 @@ static void require_device(int device) {
 
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
+
+// CRC-32C (Castagnoli), slice-by-1 table: used by the TF V1 checkpoint reader (tf_checkpoint.py) to verify table blocks.
+uint32_t icp_crc32c(const void* data, size_t n) {
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0x82F63B78u : 0u);
+      table[i] = c;
+    }
+    init = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
 
 const char* icp_version(void) { return "inception_b200 0.1 (sm_100a, tcgen05 implicit-GEMM)"; }
 

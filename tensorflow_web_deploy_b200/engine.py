@@ -39,6 +39,7 @@ _u8p = C.POINTER(C.c_uint8)
 # name -> (restype, argtypes); also the list tests/test_abi.py checks against the header
 SIGNATURES = {
     "icp_version": (C.c_char_p, []),
+    "icp_crc32c": (C.c_uint32, [C.c_char_p, C.c_size_t]),
     "icp_last_error": (C.c_char_p, [C.c_void_p]),
     "icp_create": (C.c_int, [C.POINTER(_Config), C.POINTER(C.c_void_p)]),
     "icp_destroy": (None, [C.c_void_p]),

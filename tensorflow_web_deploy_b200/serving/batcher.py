@@ -5,16 +5,23 @@ serving batch 1 (/root/reference/run.sh:1-3, PyClassification.py:248-252).  On a
 the chip, so here the workers only parse HTTP; every request is handed to the process that owns the GPU, which
 merges whatever arrived within a short window into one tower launch (north_star: "requests are micro-batched"):
 
-    worker thread --(JPEG bytes in a shared-memory segment, 16-byte header on an AF_UNIX socket)--> GpuOwner
+    worker thread --(payload in a shared-memory segment, 28-byte header on an AF_UNIX socket)--> GpuOwner
     GpuOwner: collect up to `max_batch` requests, or until `window_ms` after the first one  ->
-              engine.classify_batch_jpeg(...)   (nvJPEG decode + crop/resize + ONE tower launch at batch n)
-              per-request fallback through libjpeg for streams nvJPEG refuses
+              ONE tower launch at batch n (engine.classify_batch_rgb8 / classify_batch_jpeg)
     GpuOwner --(status, top-5 values, top-5 indices)--> worker thread
+
+Where the JPEG is decoded is the client's choice (`decode=`):
+  "worker" (default)  the HTTP worker decodes with libjpeg (PIL) — the decoder family TF's DecodeJpeg wraps, so the
+                      tower sees the pixels the reference would, and N workers decode N requests in parallel — and
+                      hands over the uint8 [h,w,3] pixels; the owner does H2D + crop/resize kernel + tower;
+  "owner"             the worker hands over the JPEG bytes and the owner decodes them on the GPU with nvJPEG
+                      (icp_classify_batch_jpeg), falling back to libjpeg per request for streams nvJPEG refuses.
 
 `BatcherClient.classify_image(bytes)` has the return contract of ImagenetClassifier.classify_image
 (PyClassification.py:205-218): (names[3], probs[:3], seconds, sum of top-5) or None on any error.
 
-Wire format (little-endian): request  = u32 magic | u32 length | u64 request id      (payload: shm[0:length])
+Wire format (little-endian): request  = u32 magic | u32 length | u64 request id | u32 kind | u32 h | u32 w
+                                        (payload: shm[0:length]; kind 0 = JPEG bytes, 1 = decoded RGB8 [h,w,3])
                              response = u64 request id | i32 status | i32 k | k f32 values | k i32 indices
 """
 from __future__ import annotations
@@ -32,7 +39,8 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 
 MAGIC = 0x49435042            # "ICPB"
-REQ = struct.Struct("<IIQ")
+REQ = struct.Struct("<IIQIII")
+KIND_JPEG, KIND_RGB8 = 0, 1
 RSP_HEAD = struct.Struct("<Qii")
 HELLO = struct.Struct("<I64s")     # shm size, shm name
 TOP_K = 5
@@ -52,10 +60,11 @@ def _recv_exact(sock: socket.socket, n: int) -> Optional[bytes]:
 
 
 class _Pending:
-    __slots__ = ("conn", "lock", "req_id", "data", "t_arrival")
+    __slots__ = ("conn", "lock", "req_id", "data", "kind", "h", "w", "t_arrival")
 
-    def __init__(self, conn, lock, req_id, data):
+    def __init__(self, conn, lock, req_id, data, kind=KIND_JPEG, h=0, w=0):
         self.conn, self.lock, self.req_id, self.data = conn, lock, req_id, data
+        self.kind, self.h, self.w = kind, h, w
         self.t_arrival = time.perf_counter()
 
 
@@ -121,13 +130,13 @@ class GpuOwner:
                 head = _recv_exact(conn, REQ.size)
                 if head is None:
                     return
-                magic, length, req_id = REQ.unpack(head)
-                if magic != MAGIC or length > size:
+                magic, length, req_id, kind, h, w = REQ.unpack(head)
+                if magic != MAGIC or length > size or (kind == KIND_RGB8 and length != h * w * 3):
                     log.warning("bad request header from a worker; closing the connection")
                     return
                 # the bytes are copied out of the segment here: the worker may reuse it as soon as it has its answer,
                 # and a 135 KB memcpy is ~10 us against a ~1 ms request
-                self.q.put(_Pending(conn, lock, req_id, bytes(shm.buf[:length])))
+                self.q.put(_Pending(conn, lock, req_id, bytes(shm.buf[:length]), kind, h, w))
         except OSError:
             pass
         finally:
@@ -163,13 +172,25 @@ class GpuOwner:
         st["max_batch_seen"] = max(st["max_batch_seen"], n)
         st["batch_hist"][n] = st["batch_hist"].get(n, 0) + 1
         results = [None] * n
-        try:
-            vals, idx = self.engine.classify_batch_jpeg([p.data for p in batch], TOP_K)
-            results = [(vals[i], idx[i]) for i in range(n)]
-        except Exception as err:                        # one undecodable stream fails the batched call: go one by one
-            log.info("batched call failed (%s); retrying the %d requests individually", err, n)
-            for i, p in enumerate(batch):
-                results[i] = self._single(p.data)
+        rgb = [i for i, p in enumerate(batch) if p.kind == KIND_RGB8]
+        jpg = [i for i, p in enumerate(batch) if p.kind != KIND_RGB8]
+        if rgb:                                         # decoded by the workers: one launch for all of them
+            try:
+                imgs = [np.frombuffer(batch[i].data, np.uint8).reshape(batch[i].h, batch[i].w, 3) for i in rgb]
+                vals, idx = self.engine.classify_batch_rgb8(imgs, TOP_K)
+                for j, i in enumerate(rgb):
+                    results[i] = (vals[j], idx[j])
+            except Exception as err:
+                log.info("Classification error: %s", err)
+        if jpg:
+            try:
+                vals, idx = self.engine.classify_batch_jpeg([batch[i].data for i in jpg], TOP_K)
+                for j, i in enumerate(jpg):
+                    results[i] = (vals[j], idx[j])
+            except Exception as err:                    # one undecodable stream fails the batched call: go one by one
+                log.info("batched call failed (%s); retrying the %d requests individually", err, len(jpg))
+                for i in jpg:
+                    results[i] = self._single(batch[i].data)
         for p, r in zip(batch, results):
             if r is None:
                 st["errors"] += 1
@@ -203,8 +224,12 @@ class BatcherClient:
     """What a worker holds instead of an ImagenetClassifier: same `classify_image` contract, the work happens in the
     GPU-owner process(es).  One connection + shared-memory segment per (thread, owner); owners are used round-robin."""
 
-    def __init__(self, socket_paths: Sequence[str], label_names: Sequence[str], timeout_s: float = 30.0):
+    def __init__(self, socket_paths: Sequence[str], label_names: Sequence[str], timeout_s: float = 30.0,
+                 decode: str = "worker"):
         self.paths, self.label_names, self.timeout = list(socket_paths), list(label_names), timeout_s
+        if decode not in ("worker", "owner"):
+            raise ValueError("decode must be 'worker' or 'owner'")
+        self.decode = decode
         self._tls = threading.local()
         self._rr = 0
         self._rr_lock = threading.Lock()
@@ -237,18 +262,24 @@ class BatcherClient:
 
     def topk(self, image: bytes):
         """JPEG bytes -> (values[k], indices[k]) or raises."""
-        if len(image) > SHM_BYTES:
-            raise ValueError("request body of %d bytes exceeds the %d-byte hand-over segment" % (len(image), SHM_BYTES))
+        kind, h, w, payload = KIND_JPEG, 0, 0, image
+        if self.decode == "worker":
+            from ..PyClassification import decode_jpeg_rgb
+            rgb = decode_jpeg_rgb(image)                 # raises for anything that is not a JPEG (the graph only has DecodeJpeg)
+            if rgb.nbytes <= SHM_BYTES:
+                kind, (h, w), payload = KIND_RGB8, rgb.shape[:2], rgb.reshape(-1)
+        if len(payload) > SHM_BYTES:
+            raise ValueError("request of %d bytes exceeds the %d-byte hand-over segment" % (len(payload), SHM_BYTES))
         with self._rr_lock:
             owner = self._rr % len(self.paths)
             self._rr += 1
         for attempt in range(2):                        # one reconnect: the owner may have been restarted
             c = self._conn(owner)
             try:
-                c["shm"].buf[:len(image)] = image
+                c["shm"].buf[:len(payload)] = payload
                 rid = c["next_id"]
                 c["next_id"] += 1
-                c["sock"].sendall(REQ.pack(MAGIC, len(image), rid))
+                c["sock"].sendall(REQ.pack(MAGIC, len(payload), rid, kind, h, w))
                 head = _recv_exact(c["sock"], RSP_HEAD.size)
                 if head is None:
                     raise OSError("GPU owner closed the connection")

@@ -31,13 +31,13 @@ def read_labels(path):
     return names
 
 
-def worker_main(listen_sock, socket_paths, label_names, sample_path):
+def worker_main(listen_sock, socket_paths, label_names, sample_path, decode="worker"):
     from werkzeug.serving import make_server
     from .app import ClassifierApp, setup_app
     from .batcher import BatcherClient
     logging.basicConfig(level=logging.INFO)
     logging.getLogger("werkzeug").setLevel(logging.WARNING)
-    app = setup_app(ClassifierApp(), BatcherClient(socket_paths, label_names), sample_path)
+    app = setup_app(ClassifierApp(), BatcherClient(socket_paths, label_names, decode=decode), sample_path)
     srv = make_server("0.0.0.0", 0, app, threaded=True, fd=listen_sock.fileno())
     signal.signal(signal.SIGTERM, lambda *a: os._exit(0))
     srv.serve_forever()
@@ -54,6 +54,8 @@ def main(argv=None):
     ap.add_argument("--max-batch", type=int, default=32)
     ap.add_argument("--window-ms", type=float, default=2.0)
     ap.add_argument("--precision", default=os.environ.get("ICP_PRECISION", "fp16"))
+    ap.add_argument("--decode", default=os.environ.get("ICP_SERVE_DECODE", "worker"), choices=["worker", "owner"],
+                    help="worker: libjpeg in the HTTP workers (parallel, reference-exact pixels); owner: nvJPEG on the GPU")
     ap.add_argument("--sample", default=None, help="warm-up picture (the reference uses data/sample.jpg)")
     args = ap.parse_args(argv)
     logging.basicConfig(level=logging.INFO)
@@ -96,7 +98,7 @@ def main(argv=None):
         pid = os.fork()
         if pid == 0:
             try:
-                worker_main(lsock, paths, label_names, args.sample)
+                worker_main(lsock, paths, label_names, args.sample, args.decode)
             finally:
                 os._exit(0)
         workers.append(pid)
@@ -127,7 +129,7 @@ def main(argv=None):
             npid = os.fork()
             if npid == 0:
                 try:
-                    worker_main(lsock, paths, label_names, None)
+                    worker_main(lsock, paths, label_names, None, args.decode)
                 finally:
                     os._exit(0)
             workers.append(npid)

@@ -486,8 +486,10 @@ def _jpegs():
 
 def test_nvjpeg_decode_against_libjpeg(eng_mod, synth6):
     """tf.image.decode_jpeg(channels=3) (PyClassification.py:151) on the GPU: the decoded tensor against PIL/libjpeg-turbo
-    (the decoder family TF's DecodeJpeg wraps).  IDCT and chroma-upsampling implementations differ between decoders, so
-    the bar is stated per statistic: mean |d| <= 1 LSB, >= 99 % of samples within 2 LSB; the measured numbers are printed."""
+    (the decoder family TF's DecodeJpeg wraps).  IDCT and chroma-upsampling implementations differ between decoders:
+    MEASURED on B200 (GPU-hybrid backend) max 4 LSB, mean 0.49-0.71, 89-99 % of samples within 1 LSB — NOT the +-1 LSB
+    that would make it a drop-in for libjpeg, which is why ImagenetClassifier defaults to ICP_JPEG=pil.  The bar here
+    only guards against a broken decode: mean |d| <= 1 LSB, >= 98 % within 2 LSB, max <= 8; the numbers are printed."""
     from PIL import Image
     eng = eng_mod.Engine(synth6[0], 6, max_batch=1, precision="fp16")
     for name, jpeg in _jpegs().items():
@@ -497,7 +499,7 @@ def test_nvjpeg_decode_against_libjpeg(eng_mod, synth6):
         d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
         print("JPEG %-18s backend=%s max=%d mean=%.3f within1=%.4f within2=%.4f" % (
             name, eng.jpeg_backend, d.max(), d.mean(), (d <= 1).mean(), (d <= 2).mean()))
-        assert d.mean() <= 1.0 and (d <= 2).mean() >= 0.99, (name, d.max(), d.mean())
+        assert d.mean() <= 1.0 and (d <= 2).mean() >= 0.98 and d.max() <= 8, (name, d.max(), d.mean())
     with pytest.raises(eng_mod.EngineError) as ei:
         eng.decode_jpeg(b"this is not a jpeg at all, not even close.")
     assert ei.value.code == -1
@@ -524,8 +526,8 @@ def test_classify_jpeg_matches_oracle_on_the_same_pixels(eng_mod, synth6):
 
 
 def test_classify_image_nvjpeg_vs_pil_decode(synth6, built_lib, monkeypatch):
-    """The drop-in class with ICP_JPEG=nvjpeg (default) and ICP_JPEG=pil: same labels, scores within 1e-3 on the
-    reference's sample.jpg (decoder differences of ~1 LSB do not move the scores)."""
+    """The drop-in class with ICP_JPEG=nvjpeg and ICP_JPEG=pil (default) on the reference's sample.jpg: same labels;
+    the decoders' pixel differences (up to 4 LSB) move the scores by 1.2e-3 (measured) — bounded here at 3e-3."""
     from tensorflow_web_deploy_b200 import PyClassification as P
     jpeg = open(os.path.join(GOLDEN, "reference_sample.jpg"), "rb").read()
     syn = os.path.join(GOLDEN, "reference_synset.txt")
@@ -537,7 +539,7 @@ def test_classify_image_nvjpeg_vs_pil_decode(synth6, built_lib, monkeypatch):
     ra, rb = a.classify_image(jpeg), b.classify_image(jpeg)
     assert ra is not None and rb is not None
     assert ra[0] == rb[0]
-    assert np.abs(ra[1] - rb[1]).max() <= 1e-3 and abs(float(ra[3]) - float(rb[3])) <= 2e-3
+    assert np.abs(ra[1] - rb[1]).max() <= 3e-3 and abs(float(ra[3]) - float(rb[3])) <= 3e-3
     assert a.classify_image(b"garbage") is None
 
 
@@ -561,3 +563,20 @@ def test_micro_batch_calls_equal_single_requests(eng_mod, synth6):
     with pytest.raises(eng_mod.EngineError):
         eng.classify_batch_rgb8(imgs * 2, 5)          # 10 > max_batch
     eng.close()
+
+
+def test_tf_checkpoint_drops_in_as_model_def_file(synth6, tmp_path, built_lib):
+    """`model_def_file` may be the TF V1 checkpoint the reference restores (PyClassification.py:166-172,
+    keys <var>/ExponentialMovingAverage); the classifier converts it and answers exactly as from the ICPW blob."""
+    from tensorflow_web_deploy_b200 import PyClassification as P, tf_checkpoint as T
+    path, W = synth6
+    ck = {k + T.EMA_SUFFIX: v for k, v in W.items()}
+    ck["global_step"] = np.float32([5000])
+    ckpt = str(tmp_path / "model.ckpt-5000")
+    T.write_checkpoint(ckpt, ck)
+    syn = os.path.join(GOLDEN, "reference_synset.txt")
+    jpeg = open(os.path.join(GOLDEN, "reference_sample.jpg"), "rb").read()
+    a = P.ImagenetClassifier(ckpt, syn).classify_image(jpeg)
+    b = P.ImagenetClassifier(path, syn).classify_image(jpeg)
+    assert a is not None and a[0] == b[0]
+    np.testing.assert_array_equal(a[1], b[1])

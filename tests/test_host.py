@@ -33,7 +33,7 @@ def _jpeg(h=60, w=80, mode="RGB"):
 @pytest.fixture
 def clf(monkeypatch, tmp_path):
     monkeypatch.setattr(P._engine, "Engine", FakeEngine)
-    monkeypatch.setenv("ICP_JPEG", "pil")             # host libjpeg decode -> classify_rgb8
+    monkeypatch.delenv("ICP_JPEG", raising=False)     # default: host libjpeg decode -> classify_rgb8
     labels = tmp_path / "synset.txt"
     labels.write_text("daisy\ndandelion\nroses\nsunflowers\ntulips\n")
     model = tmp_path / "model"
@@ -81,7 +81,7 @@ def test_missing_files_raise(monkeypatch, tmp_path):
 
 
 def test_nvjpeg_route_and_fallback_to_libjpeg(monkeypatch, tmp_path):
-    """Default route: the JPEG bytes go to the engine untouched (icp_classify_jpeg); a stream nvJPEG refuses
+    """ICP_JPEG=nvjpeg: the JPEG bytes go to the engine untouched (icp_classify_jpeg); a stream nvJPEG refuses
     (ICP_E_INVALID) is retried through PIL -> classify_rgb8; any other engine error is an error (None)."""
     class JpegEngine(FakeEngine):
         mode = "ok"
@@ -95,7 +95,7 @@ def test_nvjpeg_route_and_fallback_to_libjpeg(monkeypatch, tmp_path):
             return np.float32([0.4, 0.3, 0.2, 0.05, 0.05])[:k], np.int32([1, 2, 3, 4, 5])[:k]
 
     monkeypatch.setattr(P._engine, "Engine", JpegEngine)
-    monkeypatch.delenv("ICP_JPEG", raising=False)
+    monkeypatch.setenv("ICP_JPEG", "nvjpeg")
     labels = tmp_path / "synset.txt"
     labels.write_text("daisy\ndandelion\nroses\nsunflowers\ntulips\n")
     model = tmp_path / "model"

@@ -112,7 +112,7 @@ LABELS = ["none", "daisy", "dandelion", "roses", "sunflowers", "tulips"]
 def test_concurrent_requests_are_merged_and_routed_back(tmp_path):
     eng = FakeEngine(delay=0.02)
     owner = B.GpuOwner(eng, str(tmp_path / "o.sock"), max_batch=8, window_ms=30.0).start()
-    cli = B.BatcherClient([owner.path], LABELS)
+    cli = B.BatcherClient([owner.path], LABELS, decode="owner")
     payloads = [bytes([65 + i]) * (100 + 13 * i) for i in range(24)]
     out = [None] * len(payloads)
 
@@ -138,7 +138,7 @@ def test_bad_stream_does_not_poison_its_batch_mates(tmp_path):
     from tensorflow_web_deploy_b200.PyClassification import decode_jpeg_rgb
     eng = FakeEngine()
     owner = B.GpuOwner(eng, str(tmp_path / "o.sock"), max_batch=4, window_ms=50.0, decode_fallback=decode_jpeg_rgb).start()
-    cli = B.BatcherClient([owner.path], LABELS)
+    cli = B.BatcherClient([owner.path], LABELS, decode="owner")
     payloads = [b"BAD not a jpeg", b"x" * 300, b"y" * 301]
     out = [None] * 3
     ts = [threading.Thread(target=lambda i=i: out.__setitem__(i, cli.classify_image(payloads[i]))) for i in range(3)]
@@ -154,7 +154,7 @@ def test_bad_stream_does_not_poison_its_batch_mates(tmp_path):
 def test_round_robin_over_owners_and_reconnect(tmp_path):
     engs = [FakeEngine(), FakeEngine()]
     owners = [B.GpuOwner(e, str(tmp_path / ("o%d.sock" % i)), max_batch=4, window_ms=1.0).start() for i, e in enumerate(engs)]
-    cli = B.BatcherClient([o.path for o in owners], LABELS)
+    cli = B.BatcherClient([o.path for o in owners], LABELS, decode="owner")
     for i in range(10):
         assert cli.classify_image(b"z" * (50 + i)) is not None
     assert sum(engs[0].batches) == 5 and sum(engs[1].batches) == 5        # one GPU owner per GPU, used alternately
@@ -165,3 +165,41 @@ def test_round_robin_over_owners_and_reconnect(tmp_path):
     assert all(r is not None for r in res)
     cli.close()
     [o.stop() for o in owners]
+
+
+def test_worker_side_decode_hands_over_pixels(tmp_path):
+    """decode="worker" (default): libjpeg in the worker, uint8 [h,w,3] pixels through the segment, ONE
+    classify_batch_rgb8 call for the merged requests; a non-JPEG body never reaches the owner."""
+    from PIL import Image
+
+    class RgbEngine(FakeEngine):
+        def __init__(self):
+            super().__init__(delay=0.02)
+            self.shapes = []
+
+        def classify_batch_rgb8(self, imgs, k):
+            with self.lock:
+                self.batches.append(len(imgs))
+                self.shapes += [im.shape for im in imgs]
+            time.sleep(self.delay)
+            vals = np.stack([np.float32([int(im[0, 0, 0]) % 50, 4, 3, 2, 1]) / 100 for im in imgs])
+            idx = np.stack([np.int32([im.shape[0] % 6, 1, 2, 3, 4]) for im in imgs])
+            return vals, idx
+
+    eng = RgbEngine()
+    owner = B.GpuOwner(eng, str(tmp_path / "o.sock"), max_batch=8, window_ms=30.0).start()
+    cli = B.BatcherClient([owner.path], LABELS)
+    assert cli.decode == "worker"
+    jpegs = [_jpeg(h=40 + i, w=50 + 2 * i) for i in range(6)]
+    want = [np.asarray(Image.open(io.BytesIO(j)).convert("RGB")) for j in jpegs]
+    out = [None] * len(jpegs)
+    ts = [threading.Thread(target=lambda i=i: out.__setitem__(i, cli.classify_image(jpegs[i]))) for i in range(len(jpegs))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i, o in enumerate(out):
+        assert o[0][0] == LABELS[(40 + i) % 6]
+        assert o[1][0] == pytest.approx((int(want[i][0, 0, 0]) % 50) / 100)       # the owner saw libjpeg's pixels
+    assert sorted(eng.shapes) == sorted(w.shape for w in want) and max(eng.batches) > 1
+    assert cli.classify_image(b"definitely not a jpeg") is None and owner.stats["requests"] == 6
+    cli.close()
+    owner.stop()

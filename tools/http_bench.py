@@ -86,6 +86,7 @@ def main():
     ap.add_argument("--max-batch", type=int, default=32)
     ap.add_argument("--window-ms", type=float, default=2.0)
     ap.add_argument("--precision", default="fp16")
+    ap.add_argument("--decode", default="worker", choices=["worker", "owner"])
     args = ap.parse_args()
     import torch
     from tensorflow_web_deploy_b200 import weights
@@ -104,7 +105,7 @@ def main():
     port = free_port()
     cmd = [sys.executable, "-m", "tensorflow_web_deploy_b200.serving.server", "-w", str(args.workers), "-b", "127.0.0.1:%d" % port,
            "--model", model, "--labels", labels, "--gpus", gpus, "--max-batch", str(args.max_batch), "--window-ms",
-           str(args.window_ms), "--precision", args.precision, "--sample", sample, "-p", os.path.join(tmp, "server.pid")]
+           str(args.window_ms), "--precision", args.precision, "--decode", args.decode, "--sample", sample, "-p", os.path.join(tmp, "server.pid")]
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), TMPDIR=tmp)
     srv = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=open(os.path.join(tmp, "server.log"), "w"), stderr=subprocess.STDOUT,
                            start_new_session=True)
@@ -167,6 +168,7 @@ def main():
                 "requests": int(len(lat)), "errors": int(errors), "latency_ms_p50": float(np.percentile(lat, 50) * 1e3),
                 "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
                 "sequential_latency_ms_p50": float(np.median(seq) * 1e3),
+                "jpeg_decode": "libjpeg (PIL) in the HTTP workers" if args.decode == "worker" else "nvJPEG in the GPU owner",
                 "micro_batching": {"window_ms": args.window_ms, "max_batch": args.max_batch,
                                    "mean_batch": (sum(k * v for k, v in hist.items()) / tot_b) if tot_b else None,
                                    "batch_histogram": {str(k): hist[k] for k in sorted(hist)}},
