@@ -11,21 +11,21 @@ reference legs may import this module.  The product package
 (tensorflow_web_deploy_b200/) never does; it fails loudly without the CUDA
 library.
 
-PARITY PINNING STATUS: **parity unpinned by the reference.**  The arithmetic of
-this path lives in the un-vendored, un-pinned `tensorflow` (~r0.9) wheel; it is
-not installed here, the reference is Python 2, and the trained checkpoint was
-never committed (reference README.md:14), so the reference cannot be run.  Its
-own tests assert shapes / variable counts only (inception/slim/inception_test.py,
-collections_test.py, ops_test.py) — no output value of conv / pool / softmax is
-asserted anywhere.  What IS pinned against reference artefacts:
-  * the 388 variable names decoded from the reference's data/model.meta
-    (tests/golden/model_meta_variables.txt) — every name this oracle asks for;
-  * the structural counts in collections_test.py:43-49,76-92;
-  * the end-point shapes in inception_test.py:27-55,73-85;
-  * frozen-moving-stat BN semantics (ops_test.py:623-655).
-TF kernel semantics not visible in the reference source (exclude-pad SAME
-avg-pool divisor, legacy bilinear resize, integer central-crop offsets) follow
-the published TensorFlow r0.9 kernels as summarised in SURVEY.md Appendix B.
+PARITY PINNING STATUS: **pinned to the reference's own graph** (round 2).  The reference cannot be RUN here (the
+arithmetic lives in the un-vendored, un-pinned `tensorflow` ~r0.9 wheel; Python 2; no checkpoint, reference
+README.md:14) and its own tests assert shapes / variable counts only.  But its data/model.meta is a serialized
+MetaGraphDef of the very graph PyClassification.py:148-164 builds, and tests/test_oracle_pin.py executes THAT graph
+(tests/golden/reference_graph.json, decoded by tools/export_reference_graph.py) with the independent numpy
+interpreter oracle/graph_interpreter.py and holds this oracle equal to it
+  * bit-exactly on the preprocessing output (decode -> x/255 -> crop dim//16 -> legacy bilinear -> (x-.5)*2) for five
+    image geometries, incl. the reference's 500x375 sample.jpg,
+  * to 2e-5 relative on EVERY end point (conv0 ... mixed_8x8x2048b, aux_logits, logits, predictions) at C = 6 and 1001.
+Wiring, op attributes (strides / padding / window sizes), the BatchNorm expansion, concat orders and every constant
+therefore come from the reference's artefact.  The kernel semantics the graph cannot carry (legacy bilinear resize,
+exclude-pad SAME average pooling, VALID/SAME max pooling) are held to known-answer values from TensorFlow's own unit
+tests (tests/test_tf_kats.py).  Also pinned: the 388 variable names/shapes (tests/golden/model_meta_variables.txt),
+collections_test.py:43-49,76-92 counts, inception_test.py:27-55,73-85 end-point shapes, ops_test.py:623-655 frozen BN.
+What remains unpinned: TF's floating-point summation ORDER inside Conv2D/MatMul (Eigen), i.e. last-bit fp32 differences.
 
 Each function cites the reference file:line it restates.
 """

@@ -94,9 +94,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   auto b_empty = [&](int i) { return bar_base + 168u + 8u * i; };
   const uint32_t tmem_slot = bar_base + 232u;
   uint32_t* tap_off = reinterpret_cast<uint32_t*>(gbase + (bar_base - base) + 256);   // [taps] A shift of tap (r,s), 16-B units
-  int* s_pix = reinterpret_cast<int*>(tap_off + 64);                 // [128] output pixel of each sub-tile row, -1 = none
-  const uint32_t stage_base = bar_base + 1024u;                      // epilogue staging: 128 rows x 128 B
-  const uint32_t ones_base = stage_base + 16384u;                    // constant A tile of the bias MMA (conv_igemm.cuh)
+  int* s_pix = reinterpret_cast<int*>(tap_off + 64);                 // [2][128] per team: output pixel of each sub-tile row, -1 = none
+  const uint32_t stage_base = bar_base + 2048u;                      // epilogue staging: 2 teams x 128 rows x 128 B
+  const uint32_t ones_base = stage_base + 2u * 16384u;               // constant A tile of the bias MMA (after both teams' staging)
   const uint32_t bias_base = ones_base + kOnesBytes;                 // resident weights: the [n_tile x 16] shift tile
 
   const int taps = a.kh * a.kw;
@@ -308,20 +308,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else {
     // ---------------- epilogue (warps 2..5 and 7..10) ----------------
-    // Two warps per TMEM lane quarter, each owning half of the 16-column pieces of a <=64-column chunk; the loads
-    // of unit u+1 (next chunk / next sub-tile) are issued before the arithmetic of unit u (tcgen05.ld moves only
-    // 64 B/cycle/SM and one warp per scheduler issues the convert/pack code slowly — see conv_igemm.cuh).
-    // TMEM -> registers -> scale/shift/ReLU -> 16-bit -> shared staging (128 rows x 128 B, 16-byte chunks XOR-
-    // swizzled by row) -> global with 8 consecutive lanes per pixel, so every warp store covers whole lines.
-    const int grp = warp >= 7 ? 1 : 0;
-    const int et = grp ? static_cast<int>(threadIdx.x) - 224 + 128 : static_cast<int>(threadIdx.x) - 64;   // 0..255
+    // TWO independent teams of four warps (one warp per TMEM lane quarter each).  Units = (sub-tile, <= 64-column chunk)
+    // are dealt to the teams alternately by a running counter; each team has its own staging buffer, row->pixel table and
+    // named barrier, so two dependent chains (TMEM wait -> convert -> staging -> copy-out) are in flight at once.
+    // MEASURED before (one 8-warp team, timeline of conv2): ~1600 cycles per 128 x 64 sub-tile, 6500-7100 per band against
+    // 3870 of MMA issue: conv1 / conv2 were bound by this chain, not by the tensor pipe or HBM.
+    // TMEM -> registers -> ReLU -> 16-bit -> (kDirect: 16-byte stores straight from registers | else: shared staging,
+    // 128 rows x 128 B, chunks XOR-swizzled by row -> global with 8 consecutive lanes per pixel = whole 128-byte lines).
+    const int team = warp >= 7 ? 1 : 0;
+    const int tt = team ? static_cast<int>(threadIdx.x) - 224 : static_cast<int>(threadIdx.x) - 64;   // 0..127 in the team
+    const int et = tt + 128 * team;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    uint32_t as = 0, pha = 0;
+    const uint32_t bar_id = 1u + static_cast<uint32_t>(team);
+    uint32_t as = 0, pha = 0, gunit = 0;
     int lt = 0;
-    uint8_t* stage_g = gbase + (stage_base - base);
-    const int cl = et & 7;                     // chunk lane of the copy-out: 8 lanes cover one pixel's 128 bytes
-    const int r0 = et >> 3;                    // copy-out rows r0, r0+32, r0+64, r0+96
+    uint8_t* stage_g = gbase + (stage_base - base) + team * 16384;
+    int* my_pix = s_pix + team * 128;
+    const int cl = tt & 7;                     // chunk lane of the copy-out: 8 lanes cover one pixel's 128 bytes
+    const int r0 = tt >> 3;                    // copy-out rows r0, r0+16, ... r0+112
+    const int cps = (a.n_tile + 63) >> 6;      // <= 64-column chunks per sub-tile
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++lt) {
       const int band = item / a.n_tiles;
       const int n_base = (item - band * a.n_tiles) * a.n_tile;
@@ -329,131 +335,108 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int p0 = (band - img * bands_per_image) * kBM * a.T;
       int nsub = (positions - p0 + kBM - 1) / kBM;
       if (nsub > a.T) nsub = a.T;
+      const int nunits = nsub * cps;
       ICP_STAMP(a.dbg, 6, lt, et == 0);
       ptx::mbar_wait(tmem_full(as), pha);
       ptx::tc_fence_after();
       ICP_STAMP(a.dbg, 4, lt, et == 0);
       const uint32_t tbase = tmem_base + as * a.acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-
-      // 16-column pieces of the chunk at c0 owned by this thread: [first, first + np)
-      auto geom = [&](int c0, int& cp, int& first, int& np) {
-        cp = (a.n_tile - c0) >> 4;
+      int last_mine = -1;
+      if constexpr (kDirect) {
+        last_mine = nunits - 1;
+      } else {
+        for (int u = nunits - 1; u >= 0; --u)
+          if (((gunit + static_cast<uint32_t>(u)) & 1u) == static_cast<uint32_t>(team)) { last_mine = u; break; }
+      }
+      if (last_mine < 0) {                       // nothing of this band is mine: hand the accumulator back at once
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(tmem_empty(as));
+      }
+      for (int u = 0; u < nunits; ++u) {
+        if constexpr (!kDirect) {
+          if (((gunit + static_cast<uint32_t>(u)) & 1u) != static_cast<uint32_t>(team)) continue;
+        }
+        const int j = u / cps;
+        int c0 = (u - j * cps) << 6;
+        int cp = (a.n_tile - c0) >> 4;           // 16-column pieces in this chunk (<= 4)
         if (cp > 4) cp = 4;
-        const int h0 = (cp + 1) >> 1;
-        first = grp ? h0 : 0;
-        np = grp ? cp - h0 : h0;
-      };
-      auto issue = [&](uint32_t (&v)[32], int j, int c0) {
-        int cp, first, np;
-        geom(c0, cp, first, np);
-        const uint32_t t0 = tbase + j * a.n_tile + c0 + 16 * first;
-        if (np > 0) ptx::tmem_ld_32x32b_x16(t0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        if (np > 1) ptx::tmem_ld_32x32b_x16(t0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-      };
-      auto process = [&](uint32_t (&v)[32], uint32_t (&vn)[32], int j, int c0, bool more, int nj, int nc) {
-        int cp, first, np;
-        geom(c0, cp, first, np);
-        if (more) issue(vn, nj, nc);
         if constexpr (kDirect) {
-          // Barrier-free variant: every thread maps its own row, converts its <= 32 columns and writes them with
-          // 16-byte stores (64 contiguous bytes per thread).  MEASURED on conv1 / conv2 against the staged variant
-          // below: see profiles/r01_epilogue.md.
-          const int p = p0 + j * kBM + row;
-          int oy = p / a.wp;
-          const int ox = p - oy * a.wp;
-          int im = img;
-          if (f_tall) { im = oy / a.oh; oy -= im * a.oh; }
-          const bool valid = (im < a.n_images) && (oy < a.oh) && (ox < a.ow);
-          const int pixd = f_transpose ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
-          uint32_t q[16];
+          // no barriers in this variant, so the teams bring nothing: both warps of a lane quarter work on the SAME unit and
+          // split its pieces (MEASURED conv1, 32 columns: 0.111 ms split against 0.120 ms with alternating sub-tiles)
+          const int h0 = (cp + 1) >> 1;
+          c0 += team ? 16 * h0 : 0;
+          cp = team ? cp - h0 : h0;
+        }
+        uint32_t v[64];
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
-            if (jj < np) convert16(&v[16 * jj], &q[8 * jj], a.relu != 0, a.fmt);
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(pixd) * a.ldo +
-                                                  a.coff + n_base + c0 + 16 * first);
+        for (int q = 0; q < 4; ++q)
+          if (q < cp) ptx::tmem_ld_32x32b_x16(tbase + j * a.n_tile + c0 + 16 * q, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * q]));
+        // this thread's row -> output pixel (while the loads are in flight)
+        const int p = p0 + j * kBM + row;
+        int oy = p / a.wp;                       // tall mode: row over all images
+        const int ox = p - oy * a.wp;
+        int im = img;
+        if (f_tall) { im = oy / a.oh; oy -= im * a.oh; }
+        int pix = -1;
+        if ((im < a.n_images) && (oy < a.oh) && (ox < a.ow))
+          pix = f_transpose ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
+        ptx::tmem_ld_wait();
+        ICP_STAMP(a.dbg, 7, lt * a.T + j, et == 0 && c0 == 0);
+        if (u == last_mine) {                    // last TMEM read of this band (for this team) has landed
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(tmem_empty(as));
+        }
+        if constexpr (kDirect) {
+          if (pix >= 0) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + static_cast<size_t>(pix) * a.ldo + a.coff +
+                                                  n_base + c0);
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-              if (jj < np) {
-                dst[2 * jj] = make_uint4(q[8 * jj], q[8 * jj + 1], q[8 * jj + 2], q[8 * jj + 3]);
-                dst[2 * jj + 1] = make_uint4(q[8 * jj + 4], q[8 * jj + 5], q[8 * jj + 6], q[8 * jj + 7]);
+            for (int q = 0; q < 4; ++q) {
+              if (q < cp) {
+                uint32_t pk[8];
+                convert16(&v[16 * q], pk, a.relu != 0, a.fmt);
+                dst[2 * q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                dst[2 * q + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
               }
             }
           }
           ICP_STAMP(a.dbg, 9, lt * a.T + j, et == 0);
         } else {
-        int pix = -1;
-        if (c0 == 0 && grp == 0) {               // one thread per row maps the sub-tile's positions to output pixels
-          const int p = p0 + j * kBM + row;
-          int oy = p / a.wp;                     // tall mode: row over all images
-          const int ox = p - oy * a.wp;
-          int im = img;
-          if (f_tall) { im = oy / a.oh; oy -= im * a.oh; }
-          if ((im < a.n_images) && (oy < a.oh) && (ox < a.ow))
-            pix = f_transpose ? (im * a.ow + ox) * a.oh + oy : (im * a.oh + oy) * a.ow + ox;
-        }
-        uint32_t q[16];
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");       // staging free (this team's previous copy-out finished)
+          my_pix[row] = pix;
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj)
-          if (jj < np) convert16(&v[16 * jj], &q[8 * jj], a.relu != 0, a.fmt);
-        asm volatile("bar.sync 1, 256;" ::: "memory");                 // staging free (previous copy-out finished)
-        if (c0 == 0 && grp == 0) s_pix[row] = pix;
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          if (jj < np) {
-            const int ch = 2 * (first + jj);       // 16-byte chunk index within the 128-byte staging row
-            *reinterpret_cast<uint4*>(stage_g + row * 128 + ((ch ^ (row & 7)) << 4)) =
-                make_uint4(q[8 * jj], q[8 * jj + 1], q[8 * jj + 2], q[8 * jj + 3]);
-            *reinterpret_cast<uint4*>(stage_g + row * 128 + (((ch + 1) ^ (row & 7)) << 4)) =
-                make_uint4(q[8 * jj + 4], q[8 * jj + 5], q[8 * jj + 6], q[8 * jj + 7]);
+          for (int q = 0; q < 4; ++q) {
+            if (q < cp) {
+              uint32_t pk[8];
+              convert16(&v[16 * q], pk, a.relu != 0, a.fmt);
+              *reinterpret_cast<uint4*>(stage_g + row * 128 + (((2 * q) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(stage_g + row * 128 + (((2 * q + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        ICP_STAMP(a.dbg, 8, lt * a.T + j, et == 0);
-        if (cl < 2 * cp) {                         // lane's 8 columns exist in this chunk
-          int px[4];
-          uint4 val[4];
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          ICP_STAMP(a.dbg, 8, lt * a.T + j, et == 0);
+          if (cl < 2 * cp) {                         // lane's 8 columns exist in this chunk
+            uint16_t* dst = reinterpret_cast<uint16_t*>(a.out) + a.coff + n_base + c0 + cl * 8;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) px[i] = s_pix[r0 + 32 * i];
+            for (int h = 0; h < 2; ++h) {
+              int px[4];
+              uint4 val[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = r0 + 32 * i;
-            val[i] = *reinterpret_cast<const uint4*>(stage_g + r * 128 + ((cl ^ (r & 7)) << 4));
+              for (int i = 0; i < 4; ++i) px[i] = my_pix[r0 + 16 * (4 * h + i)];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = r0 + 16 * (4 * h + i);
+                val[i] = *reinterpret_cast<const uint4*>(stage_g + r * 128 + ((cl ^ (r & 7)) << 4));
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (px[i] >= 0) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(px[i]) * a.ldo) = val[i];
+            }
           }
-          uint16_t* dst = reinterpret_cast<uint16_t*>(a.out) + a.coff + n_base + c0 + cl * 8;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (px[i] >= 0) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(px[i]) * a.ldo) = val[i];
+          ICP_STAMP(a.dbg, 9, lt * a.T + j, et == 0);
         }
-        ICP_STAMP(a.dbg, 9, lt * a.T + j, et == 0);
-        }
-      };
-      auto release = [&]() {                       // accumulator fully read: hand it back to the MMA issuer
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(tmem_empty(as));
-      };
-      // units (sub-tile j, chunk c0) in order; the next unit's loads are in flight while this one is converted
-      uint32_t va[32], vb[32];
-      int j = 0, c0 = 0;
-      issue(va, 0, 0);
-      while (true) {
-        int nj = j, nc = c0 + 64;
-        if (nc >= a.n_tile) { nc = 0; ++nj; }
-        ptx::tmem_ld_wait();
-        ICP_STAMP(a.dbg, 7, lt * a.T + j, et == 0 && c0 == 0);
-        if (nj >= nsub) release();
-        process(va, vb, j, c0, nj < nsub, nj, nc);
-        if (nj >= nsub) break;
-        j = nj; c0 = nc;
-        nc = c0 + 64;
-        if (nc >= a.n_tile) { nc = 0; ++nj; }
-        ptx::tmem_ld_wait();
-        ICP_STAMP(a.dbg, 7, lt * a.T + j, et == 0 && c0 == 0);
-        if (nj >= nsub) release();
-        process(vb, va, j, c0, nj < nsub, nj, nc);
-        if (nj >= nsub) break;
-        j = nj; c0 = nc;
       }
+      gunit += static_cast<uint32_t>(nunits);
       ICP_STAMP(a.dbg, 5, lt, et == 0);
       if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
     }
@@ -469,8 +452,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 }
 
 inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes) {
-  return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 1024 +
-         16384 + kOnesBytes + 8192;   // barriers + per-tap offsets + row->pixel table, epilogue staging, ones tile, shift tile
+  return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 2048 +
+         2 * 16384 + kOnesBytes + 8192;   // barriers + per-tap offsets + row->pixel tables, 2 x epilogue staging, ones tile, shift tile
 }
 
 }  // namespace icp

@@ -86,6 +86,7 @@ struct ConvArgs {
   // (pool-after-projection: BatchNorm shift + ReLU of those channels run after the pool).
   int relu_lo, relu_hi;
   int epi_staged;      // one-tile kernel: 1 = epilogue through shared staging + coalesced stores, 0 = row-per-thread stores
+  int epi_teams;       // persistent kernel: 2 = two independent 4-warp epilogue teams (own staging each), 1 = one 8-warp team
   long long* dbg;      // optional timeline buffer (CTA 0 only): [role][event] clock64 stamps, see tools/timeline.py
 };
 
@@ -432,7 +433,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;
   const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u; // stage pitch keeps every tile on a swizzle period
   const uint32_t out_stage = base + a.stages * stage_bytes;    // 16 KiB epilogue staging
-  const uint32_t ones_base = out_stage + kOutStageBytes;       // 4 KiB constant A tile of the bias MMA
+  const uint32_t ones_base = out_stage + static_cast<uint32_t>(a.epi_teams) * kOutStageBytes;  // 4 KiB constant A tile of the bias MMA
   const uint32_t bar_base = ones_base + kOnesBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (a.stages + s); };
@@ -696,129 +697,236 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       __syncwarp();
     }
   } else {
-    // ---------------- epilogue (warps 2..5 and 7..10) ----------------
-    // Each TMEM lane quarter has two warps (w and w+5 share w & 3), each owning half of the 16-column pieces of a
-    // 64-column chunk; the next chunk's TMEM loads are in flight while this one is converted and staged.
-    const int grp = warp >= 7 ? 1 : 0;                 // column half of each 64-column chunk
-    const int et = grp ? static_cast<int>(threadIdx.x) - 224 + 128 : static_cast<int>(threadIdx.x) - 64;   // 0..255
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    uint32_t lt = 0;
-    for (int t = first; t < total_tiles; t += step, ++lt) {
-      const int m0 = tile_m0(t);
-      const int n_base = (t % n_tiles) * a.n_tile;
-      // columns of this tile that exist: the weight / shift boxes of a narrower last tile are zero-filled past Cout
-      // (the MMAs run at full width), the epilogue simply stops at `cols`
-      const int cols = a.cout - n_base < a.n_tile ? a.cout - n_base : a.n_tile;
-      const uint32_t as = lt & 1u;
-      ICP_STAMP(a.dbg, 6, lt, et == 0);
-      ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
-      ptx::tc_fence_after();
-      ICP_STAMP(a.dbg, 4, lt, et == 0);
-      const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-
-      // 16-column pieces of the chunk at c0 owned by this thread: [fp, fp + np) of the chunk's cp (<= 4) pieces
-      auto geom = [&](int c0, int& cp, int& fp, int& np) {
-        cp = (cols - c0) >> 4;
-        if (cp > 4) cp = 4;
-        const int h0 = (cp + 1) >> 1;
-        fp = grp ? h0 : 0;
-        np = grp ? cp - h0 : h0;
-      };
-      auto issue = [&](uint32_t (&v)[32], int c0) {
-        int cp, fp, np;
-        geom(c0, cp, fp, np);
-        if (np > 0) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * fp, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        if (np > 1) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * fp + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-      };
-      // The accumulator leaves through shared memory and TMA stores: each thread converts its <=32 columns of one
-      // output pixel (TMEM lane), writes them into the 16 KiB staging buffer, and one thread stores the chunk into
-      // the destination slice(s).  Rows past the last valid pixel land in the unused tail of the buffer or are
-      // clipped by the tensor map.
-      auto process = [&](uint32_t (&v)[32], uint32_t (&vn)[32], int c0) {
-        int chunk_pieces, fp, np;
-        geom(c0, chunk_pieces, fp, np);
-        if (c0 + 64 < cols) issue(vn, c0 + 64);
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (j < np) {
-            const int col = n_base + c0 + 16 * (fp + j);
-            convert16(&v[16 * j], &pk[8 * j], col >= a.relu_lo && col < a.relu_hi, a.fmt);
+    if (a.epi_teams == 2) {
+      // ---------------- epilogue (warps 2..5 and 7..10) ----------------
+      // TWO independent teams of four warps (one warp per TMEM lane quarter each): the 64-column chunks of the tile
+      // stream are dealt to the teams alternately (running chunk counter, so single-chunk tiles alternate too), each team
+      // with its own 16 KiB staging buffer, its own named barrier and its own TMA-store thread.  MEASURED before (one
+      // 8-warp team, r01_epilogue.md): ~1350 cycles per 128 x 64 chunk as ONE dependent chain (TMEM wait -> convert ->
+      // staging free -> STS -> proxy fence -> barrier -> TMA store issue by one thread -> its read of the staging), so
+      // every short-K layer (35x35 1x1s, conv3: <= 2500 cycles of loads + MMAs per tile against 2700-5400 of epilogue)
+      // was epilogue-bound; two chains in flight halve the period without adding work.
+      const int team = warp >= 7 ? 1 : 0;
+      const int tt = team ? static_cast<int>(threadIdx.x) - 224 : static_cast<int>(threadIdx.x) - 64;   // 0..127 in the team
+      const int et = tt + 128 * team;
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t my_stage = out_stage + static_cast<uint32_t>(team) * kOutStageBytes;
+      const uint32_t bar_id = 1u + static_cast<uint32_t>(team);
+      uint32_t lt = 0, gchunk = 0;
+      for (int t = first; t < total_tiles; t += step, ++lt) {
+        const int m0 = tile_m0(t);
+        const int n_base = (t % n_tiles) * a.n_tile;
+        // columns of this tile that exist: the weight / shift boxes of a narrower last tile are zero-filled past Cout
+        // (the MMAs run at full width), the epilogue simply stops at `cols`
+        const int cols = a.cout - n_base < a.n_tile ? a.cout - n_base : a.n_tile;
+        const int nchunks = (cols + 63) >> 6;
+        const uint32_t as = lt & 1u;
+        ICP_STAMP(a.dbg, 6, lt, et == 0);
+        ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
+        ptx::tc_fence_after();
+        ICP_STAMP(a.dbg, 4, lt, et == 0);
+        const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+        // my chunks of this tile: c with (gchunk + c) odd/even = team; the last of them releases the accumulator
+        int last_mine = -1;
+        for (int c = nchunks - 1; c >= 0; --c)
+          if (((gchunk + static_cast<uint32_t>(c)) & 1u) == static_cast<uint32_t>(team)) { last_mine = c; break; }
+        if (last_mine < 0) {                         // nothing of this tile is mine: hand the accumulator back at once
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(tmem_empty(as));
+        }
+        for (int c = 0; c < nchunks; ++c) {
+          if (((gchunk + static_cast<uint32_t>(c)) & 1u) != static_cast<uint32_t>(team)) continue;
+          const int c0 = c << 6;
+          int cp = (cols - c0) >> 4;                 // 16-column pieces in this chunk (<= 4)
+          if (cp > 4) cp = 4;
+          uint32_t v[64];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < cp) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
+          ptx::tmem_ld_wait();
+          ICP_STAMP(a.dbg, 13, lt * 4 + c, et == 0);
+          if (c == last_mine) {                      // last TMEM read of this tile (for this team) has landed
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(tmem_empty(as));
+          }
+          const int col0 = n_base + c0;
+          // A full 64-column chunk that lies in one destination goes out as ONE [128 rows x 128 B] box (128-byte
+          // swizzled staging: conflict-free 16-byte writes); tails and chunks straddling n_split use 16-column boxes.
+          const bool wide = (cp == 4) && (col0 >= a.n_split || col0 + 64 <= a.n_split);
+          // staging buffer is free once this team's previous store has read it
+          if (tt == 0) ptx::tma_store_wait_read();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          ICP_STAMP(a.dbg, 8, lt * 4 + c, et == 0);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < cp) {
+              const int col = col0 + 16 * j;
+              uint32_t pk[8];
+              convert16(&v[16 * j], pk, col >= a.relu_lo && col < a.relu_hi, a.fmt);
+              if (wide) {
+  #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const uint32_t dst = my_stage + static_cast<uint32_t>(row) * 128u +
+                                       (static_cast<uint32_t>((2 * j + q) ^ (row & 7)) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                               "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+                }
+              } else {
+                const uint32_t dst = my_stage + static_cast<uint32_t>(j) * 4096u + static_cast<uint32_t>(row) * 32u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                             : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]),
+                             "r"(pk[7]) : "memory");
+              }
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (tt == 0) {
+            if (wide) {
+              if (col0 < a.n_split) ptx::tma_store_2d(&tm_o64, my_stage, a.coff + col0, m0);
+              else ptx::tma_store_2d(&tm_o64_2, my_stage, a.coff2 + col0 - a.n_split, m0);
+            } else {
+              for (int j = 0; j < cp; ++j) {
+                const int col = col0 + 16 * j;
+                if (col < a.n_split) ptx::tma_store_2d(&tm_o, my_stage + j * 4096u, a.coff + col, m0);
+                else ptx::tma_store_2d(&tm_o2, my_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
+              }
+            }
+            ptx::tma_store_commit();
+            ICP_STAMP(a.dbg, 9, lt * 4 + c, true);
           }
         }
-        // staging buffer is free once the previous chunk's stores have read it
-        ICP_STAMP(a.dbg, 7, lt * 4 + (c0 >> 6), et == 0);
-        if (et == 0) ptx::tma_store_wait_read();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        ICP_STAMP(a.dbg, 8, lt * 4 + (c0 >> 6), et == 0);
-        // A full 64-column chunk that lies in one destination goes out as ONE [128 rows x 128 B] box (128-byte
-        // swizzled staging: conflict-free 16-byte writes, and a quarter of the box rows the TMA unit has to walk
-        // compared with four 32-byte-row boxes); tails and chunks straddling n_split use 16-column boxes.
-        const int col0 = n_base + c0;
-        const bool wide = (chunk_pieces == 4) && (col0 >= a.n_split || col0 + 64 <= a.n_split);
-        if (wide) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {            // 16-byte chunk 4*grp+q of this thread's 128-byte row
-            const uint32_t dst = out_stage + static_cast<uint32_t>(row) * 128u +
-                                 (static_cast<uint32_t>((4 * grp + q) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-          }
-        } else {
-#pragma unroll
+        gchunk += static_cast<uint32_t>(nchunks);
+        ICP_STAMP(a.dbg, 5, lt, et == 0);
+      }
+      if (tt == 0) ptx::tma_store_wait_all();      // smem must outlive the last store's read
+    } else {
+      // ---------------- epilogue (warps 2..5 and 7..10) ----------------
+      // Each TMEM lane quarter has two warps (w and w+5 share w & 3), each owning half of the 16-column pieces of a
+      // 64-column chunk; the next chunk's TMEM loads are in flight while this one is converted and staged.
+      const int grp = warp >= 7 ? 1 : 0;                 // column half of each 64-column chunk
+      const int et = grp ? static_cast<int>(threadIdx.x) - 224 + 128 : static_cast<int>(threadIdx.x) - 64;   // 0..255
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      uint32_t lt = 0;
+      for (int t = first; t < total_tiles; t += step, ++lt) {
+        const int m0 = tile_m0(t);
+        const int n_base = (t % n_tiles) * a.n_tile;
+        // columns of this tile that exist: the weight / shift boxes of a narrower last tile are zero-filled past Cout
+        // (the MMAs run at full width), the epilogue simply stops at `cols`
+        const int cols = a.cout - n_base < a.n_tile ? a.cout - n_base : a.n_tile;
+        const uint32_t as = lt & 1u;
+        ICP_STAMP(a.dbg, 6, lt, et == 0);
+        ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
+        ptx::tc_fence_after();
+        ICP_STAMP(a.dbg, 4, lt, et == 0);
+        const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+
+        // 16-column pieces of the chunk at c0 owned by this thread: [fp, fp + np) of the chunk's cp (<= 4) pieces
+        auto geom = [&](int c0, int& cp, int& fp, int& np) {
+          cp = (cols - c0) >> 4;
+          if (cp > 4) cp = 4;
+          const int h0 = (cp + 1) >> 1;
+          fp = grp ? h0 : 0;
+          np = grp ? cp - h0 : h0;
+        };
+        auto issue = [&](uint32_t (&v)[32], int c0) {
+          int cp, fp, np;
+          geom(c0, cp, fp, np);
+          if (np > 0) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * fp, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          if (np > 1) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * fp + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        };
+        // The accumulator leaves through shared memory and TMA stores: each thread converts its <=32 columns of one
+        // output pixel (TMEM lane), writes them into the 16 KiB staging buffer, and one thread stores the chunk into
+        // the destination slice(s).  Rows past the last valid pixel land in the unused tail of the buffer or are
+        // clipped by the tensor map.
+        auto process = [&](uint32_t (&v)[32], uint32_t (&vn)[32], int c0) {
+          int chunk_pieces, fp, np;
+          geom(c0, chunk_pieces, fp, np);
+          if (c0 + 64 < cols) issue(vn, c0 + 64);
+          uint32_t pk[16];
+  #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (j < np) {
-              const uint32_t dst = out_stage + (fp + j) * 4096u + static_cast<uint32_t>(row) * 32u;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[8 * j]), "r"(pk[8 * j + 1]),
-                           "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[8 * j + 4]),
-                           "r"(pk[8 * j + 5]), "r"(pk[8 * j + 6]), "r"(pk[8 * j + 7]) : "memory");
+              const int col = n_base + c0 + 16 * (fp + j);
+              convert16(&v[16 * j], &pk[8 * j], col >= a.relu_lo && col < a.relu_hi, a.fmt);
             }
           }
-        }
-        ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
+          // staging buffer is free once the previous chunk's stores have read it
+          ICP_STAMP(a.dbg, 7, lt * 4 + (c0 >> 6), et == 0);
+          if (et == 0) ptx::tma_store_wait_read();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          ICP_STAMP(a.dbg, 8, lt * 4 + (c0 >> 6), et == 0);
+          // A full 64-column chunk that lies in one destination goes out as ONE [128 rows x 128 B] box (128-byte
+          // swizzled staging: conflict-free 16-byte writes, and a quarter of the box rows the TMA unit has to walk
+          // compared with four 32-byte-row boxes); tails and chunks straddling n_split use 16-column boxes.
+          const int col0 = n_base + c0;
+          const bool wide = (chunk_pieces == 4) && (col0 >= a.n_split || col0 + 64 <= a.n_split);
           if (wide) {
-            if (col0 < a.n_split) ptx::tma_store_2d(&tm_o64, out_stage, a.coff + col0, m0);
-            else ptx::tma_store_2d(&tm_o64_2, out_stage, a.coff2 + col0 - a.n_split, m0);
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) {            // 16-byte chunk 4*grp+q of this thread's 128-byte row
+              const uint32_t dst = out_stage + static_cast<uint32_t>(row) * 128u +
+                                   (static_cast<uint32_t>((4 * grp + q) ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                           "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+            }
           } else {
-            for (int j = 0; j < chunk_pieces; ++j) {
-              const int col = col0 + 16 * j;
-              if (col < a.n_split) ptx::tma_store_2d(&tm_o, out_stage + j * 4096u, a.coff + col, m0);
-              else ptx::tma_store_2d(&tm_o2, out_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
+  #pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (j < np) {
+                const uint32_t dst = out_stage + (fp + j) * 4096u + static_cast<uint32_t>(row) * 32u;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[8 * j]), "r"(pk[8 * j + 1]),
+                             "r"(pk[8 * j + 2]), "r"(pk[8 * j + 3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[8 * j + 4]),
+                             "r"(pk[8 * j + 5]), "r"(pk[8 * j + 6]), "r"(pk[8 * j + 7]) : "memory");
+              }
             }
           }
-          ptx::tma_store_commit();
-          ICP_STAMP(a.dbg, 9, lt * 4 + (c0 >> 6), true);
-        }
-      };
-      auto release = [&]() {                       // last TMEM read of this tile has landed: hand the accumulator back
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(tmem_empty(as));
-      };
+          ptx::fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            if (wide) {
+              if (col0 < a.n_split) ptx::tma_store_2d(&tm_o64, out_stage, a.coff + col0, m0);
+              else ptx::tma_store_2d(&tm_o64_2, out_stage, a.coff2 + col0 - a.n_split, m0);
+            } else {
+              for (int j = 0; j < chunk_pieces; ++j) {
+                const int col = col0 + 16 * j;
+                if (col < a.n_split) ptx::tma_store_2d(&tm_o, out_stage + j * 4096u, a.coff + col, m0);
+                else ptx::tma_store_2d(&tm_o2, out_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
+              }
+            }
+            ptx::tma_store_commit();
+            ICP_STAMP(a.dbg, 9, lt * 4 + (c0 >> 6), true);
+          }
+        };
+        auto release = [&]() {                       // last TMEM read of this tile has landed: hand the accumulator back
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(tmem_empty(as));
+        };
 
-      uint32_t va[32], vb[32];
-      int c0 = 0;
-      issue(va, 0);
-      while (true) {
-        ptx::tmem_ld_wait();
-        ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
-        if (c0 + 64 >= cols) release();
-        process(va, vb, c0);
-        c0 += 64;
-        if (c0 >= cols) break;
-        ptx::tmem_ld_wait();
-        ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
-        if (c0 + 64 >= cols) release();
-        process(vb, va, c0);
-        c0 += 64;
-        if (c0 >= cols) break;
+        uint32_t va[32], vb[32];
+        int c0 = 0;
+        issue(va, 0);
+        while (true) {
+          ptx::tmem_ld_wait();
+          ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
+          if (c0 + 64 >= cols) release();
+          process(va, vb, c0);
+          c0 += 64;
+          if (c0 >= cols) break;
+          ptx::tmem_ld_wait();
+          ICP_STAMP(a.dbg, 13, lt * 4 + (c0 >> 6), et == 0);
+          if (c0 + 64 >= cols) release();
+          process(vb, va, c0);
+          c0 += 64;
+          if (c0 >= cols) break;
+        }
+        ICP_STAMP(a.dbg, 5, lt, et == 0);
       }
-      ICP_STAMP(a.dbg, 5, lt, et == 0);
+      if (et == 0) ptx::tma_store_wait_all();      // smem must outlive the last store's read
     }
-    if (et == 0) ptx::tma_store_wait_all();      // smem must outlive the last store's read
   }
 
   ptx::tc_fence_before();
@@ -834,10 +942,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
 inline size_t conv_stage_bytes(int n_tile, int row_bytes) {
   return (static_cast<size_t>(kBM + n_tile) * row_bytes + 1023) & ~size_t(1023);
 }
-inline size_t conv_smem_bytes(int stages, int n_tile, int row_bytes, bool persistent = false) {
+inline size_t conv_smem_bytes(int stages, int n_tile, int row_bytes, bool persistent = false, int teams = 1) {
   size_t ring = static_cast<size_t>(stages) * conv_stage_bytes(n_tile, row_bytes);
   if (!persistent && ring < kOutStageBytes) ring = kOutStageBytes;   // the one-tile kernel stages its epilogue in the ring
-  return 1024 + ring + (persistent ? kOutStageBytes : 0) + kOnesBytes + 256 + 1024;
+  return 1024 + ring + (persistent ? teams * kOutStageBytes : 0) + kOnesBytes + 256 + 1024;
 }
 
 }  // namespace icp

@@ -23,6 +23,8 @@
 #include "../../include/inception_b200.h"
 #include "conv_igemm.cuh"
 #include "conv_halo.cuh"
+#include "conv_pair.cuh"
+#include "pool_conv.cuh"
 #include "conv0_tc.cuh"
 #include "tower_kernels.cuh"
 
@@ -280,6 +282,12 @@ struct ConvLayer {
   bool persistent = true;  // conv_igemm_persistent_kernel (one CTA per SM walks the tiles)
   bool halo = false;       // conv_halo_kernel instead of conv_igemm_kernel
   HaloArgs hargs{};
+  const uint16_t* d_w = nullptr;      // im2col layers: packed K-major weights [cout][taps * cblocks * ck] and
+  const uint16_t* d_bias16 = nullptr; //   the [cout][16] (hi, lo) shift matrix (pool_conv.cuh reads them directly)
+  bool pair = false;       // conv_pair_kernel (CTA pairs, resident weights); `alt` serves batches below pair_min_batch
+  PairArgs pargs{};
+  int pair_min_batch = 0;
+  std::shared_ptr<ConvLayer> alt;
 };
 
 static int g_num_sms = 148;
@@ -383,12 +391,108 @@ static std::vector<uint16_t> pack_weights_halo(const float* w, int kh, int kw, i
 }
 
 
+// Pair kernel's B operand for channels [c0, c0 + cn): K index = ((chunk * taps + tap) * ck + j), channel = c0 + chunk*ck + j.
+static std::vector<uint16_t> pack_weights_range(const float* w, int kh, int kw, int cin, int cout, int c0, int cn, int ck,
+                                                int fmt, const float* scale) {
+  const int chunks = (cn + ck - 1) / ck, taps = kh * kw;
+  const size_t kp = static_cast<size_t>(chunks) * taps * ck;
+  std::vector<uint16_t> out(static_cast<size_t>(cout) * kp, 0);
+  for (int t = 0; t < taps; ++t)
+    for (int ci = 0; ci < cn; ++ci) {
+      const float* src = w + (static_cast<size_t>(t) * cin + c0 + ci) * cout;
+      const size_t kidx = (static_cast<size_t>(ci / ck) * taps + t) * ck + (ci % ck);
+      for (int co = 0; co < cout; ++co) out[co * kp + kidx] = host_f2h(scale ? src[co] * scale[co] : src[co], fmt);
+    }
+  return out;
+}
+
+// CTA-pair, weight-resident halo kernel (conv_pair.cuh).  Returns false when the layer is not eligible.
+static bool make_pair_conv(ConvLayer& L, DevicePool& pool, int max_n, const Act& in, int in_coff, int cin, const float* w_hwio,
+                           int kh, int kw, int cout, int pad_h, int pad_w, int oh, int ow, const float* scale, const float* shift,
+                           bool relu, const Act& out, int out_coff, int fmt) {
+  if (cin % 16) return false;
+  const int taps = kh * kw, wp = in.w + 2 * pad_w;
+  if (wp > 256) return false;
+  // N tile: the whole layer up to 128 columns, else an even split (conv4: 192 = 2 x 96)
+  int n_tile = 0, n_tiles = 0;
+  for (int parts = 1; parts <= 8 && !n_tile; ++parts)
+    if (cout % parts == 0 && (cout / parts) % 32 == 0 && cout / parts <= 128) { n_tiles = parts; n_tile = cout / parts; }
+  if (!n_tile) return false;
+  if (n_tile % 32) return false;                       // each CTA supplies n_tile / 2 rows, a multiple of 16
+  const int half = n_tile / 2;
+  const int q = cin / 64, rem = cin % 64;
+  const int tail_split = (rem == 16 || rem == 32) ? 1 : 0;
+  const int chunks = q + (rem ? 1 : 0);
+  const int tail_rb = rem == 16 ? 32 : (rem == 32 ? 64 : 128);
+  const int tail_ksteps = rem ? rem / 16 : 4;
+  const int main_chunks = chunks - tail_split;
+  const int w_main_bytes = main_chunks * taps * half * 128;
+  const int w_tail_bytes = tail_split ? taps * half * tail_rb : 0;
+  const int w_bytes = (w_main_bytes + w_tail_bytes + 1023) & ~1023;
+  // sub-tiles per band: as many as TMEM holds with two accumulator sets (<= 4)
+  int T = 4;
+  while (T > 1 && 2 * T * n_tile > 512) T >>= 1;
+  if (2 * T * n_tile > 512) return false;
+  int nstrips = 0, slot_bytes = 0, band_rows = 0, chunk_pitch = 0;
+  for (; T >= 1; T >>= 1) {
+    band_rows = (T * kBM) / wp;
+    if (band_rows < 1) continue;
+    if (band_rows > oh) band_rows = oh;
+    const int positions = T * kBM + (kh - 1) * wp + (kw - 1);            // furthest strip position any MMA row touches
+    chunk_pitch = (positions * 128 + 1023) & ~1023;
+    slot_bytes = main_chunks * chunk_pitch + (tail_split ? ((positions * tail_rb + 1023) & ~1023) : 0);
+    for (nstrips = 4; nstrips >= 2; --nstrips)
+      if (pair_smem_bytes(slot_bytes, nstrips, w_bytes) <= 227 * 1024) break;
+    if (nstrips >= 2 && band_rows + kh - 1 <= 256) break;
+  }
+  if (T < 1) return false;
+  PairArgs& a = L.pargs;
+  a = PairArgs{};
+  a.oh = oh; a.ow = ow; a.wp = wp; a.pad_h = pad_h; a.pad_w = pad_w; a.kh = kh; a.kw = kw;
+  a.chunks = chunks; a.tail_rb = tail_rb; a.tail_ksteps = tail_ksteps; a.tail_split = tail_split;
+  a.T = T; a.band_rows = band_rows; a.bands_per_image = (oh + band_rows - 1) / band_rows; a.strip_rows = band_rows + kh - 1;
+  a.chunk_pitch = chunk_pitch; a.slot_bytes = slot_bytes; a.nstrips = nstrips;
+  a.n_tile = n_tile; a.n_tiles = n_tiles; a.acc_cols = T * n_tile; a.acc_sets = 2; a.tmem_cols = pow2_cols(2 * T * n_tile);
+  a.w_main_bytes = w_main_bytes; a.w_bytes = w_bytes;
+  a.fmt = fmt; a.relu = relu ? 1 : 0;
+  a.out = out.p; a.ldo = out.c; a.coff = out_coff;
+  L.smem = pair_smem_bytes(slot_bytes, nstrips, w_bytes);
+  // operands
+  const int cmain = tail_split ? q * 64 : cin;
+  std::vector<uint16_t> wm = pack_weights_range(w_hwio, kh, kw, cin, cout, 0, cmain, 64, fmt, scale);
+  void* d_wm = pool.alloc(wm.size() * 2 + 256);
+  if (!wm.empty()) CK(cudaMemcpy(d_wm, wm.data(), wm.size() * 2, cudaMemcpyHostToDevice));
+  const uint16_t* a_ptr = in.p + in_coff;
+  if (main_chunks > 0) {
+    L.tm_b = make_tm_2d_rows(d_wm, cout, static_cast<uint64_t>(main_chunks) * taps * 64, half, 128, fmt);
+    L.tm_a = make_tm_strip(a_ptr, max_n, in.h, in.w, cin, in.c, wp, a.strip_rows, 128, fmt);
+  }
+  L.tm_b_tail = L.tm_b;
+  L.tm_a_tail = L.tm_a;
+  if (tail_split) {
+    const int tck = tail_rb / 2;
+    std::vector<uint16_t> wt = pack_weights_range(w_hwio, kh, kw, cin, cout, q * 64, rem, tck, fmt, scale);
+    void* d_wt = pool.alloc(wt.size() * 2);
+    CK(cudaMemcpy(d_wt, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+    L.tm_b_tail = make_tm_2d_rows(d_wt, cout, static_cast<uint64_t>(taps) * tck, half, tail_rb, fmt);
+    L.tm_a_tail = make_tm_strip(a_ptr, max_n, in.h, in.w, cin, in.c, wp, a.strip_rows, tail_rb, fmt);
+    if (main_chunks == 0) { L.tm_b = L.tm_b_tail; L.tm_a = L.tm_a_tail; }     // Cin < 64: the narrow chunk is the only one
+  }
+  std::vector<uint16_t> bp = pack_bias(shift, cout, fmt);
+  void* d_bias = pool.alloc(bp.size() * 2);
+  CK(cudaMemcpy(d_bias, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice));
+  L.tm_bias = make_tm_2d_rows(d_bias, cout, 16, half, 32, fmt);
+  L.pair = true;
+  L.n_tiles = n_tiles;
+  return true;
+}
+
 // in: NHWC buffer (pitch in.c) of which channels [in_coff, in_coff+cin) feed the conv.
 static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n, const Act& in, int in_coff, int cin,
                            const float* w_hwio, int kh, int kw, int cout, int stride, bool same, const float* scale,
                            const float* shift, bool relu, const Act& out, int out_coff, int fmt,
                            const float* floor = nullptr, const Act* out2 = nullptr, int out2_coff = 0,
-                           int n_split = 0, bool transpose_out = false) {
+                           int n_split = 0, bool transpose_out = false, bool allow_pair = true) {
   if (same && stride != 1) fail(ICP_E_INVALID, "%s: SAME padding is only supported with stride 1", name.c_str());
   if (cout % 16) fail(ICP_E_INVALID, "%s: cout=%d is not a multiple of 16", name.c_str(), cout);
   if (cin % 8 || in.c % 8 || in_coff % 8 || out.c % 8 || out_coff % 8)
@@ -406,6 +510,24 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.pix_per_image = oh * ow;
   L.macs_per_image = static_cast<long long>(oh) * ow * cout * kh * kw * cin;
   L.in_elems_per_image = static_cast<long long>(in.h) * in.w * cin;
+  // CTA-pair weight-resident kernel (conv_pair.cuh) for the k x k stride-1 layers on maps at least ICP_PAIR_MIN_W wide
+  // (ICP_PAIR=0 disables it); batches below ICP_PAIR_MIN_BATCH use the plain layer built next to it.
+  {
+    static const bool pair_on = getenv("ICP_PAIR") ? atoi(getenv("ICP_PAIR")) != 0 : false;
+    static const int pair_min_w = getenv("ICP_PAIR_MIN_W") ? atoi(getenv("ICP_PAIR_MIN_W")) : 30;
+    static const int pair_max_w = getenv("ICP_PAIR_MAX_W") ? atoi(getenv("ICP_PAIR_MAX_W")) : 100;
+    static const int pair_min_batch = getenv("ICP_PAIR_MIN_BATCH") ? atoi(getenv("ICP_PAIR_MIN_BATCH")) : 8;
+    if (pair_on && allow_pair && !out2 && !floor && !transpose_out && stride == 1 && kh * kw > 1 && ow >= pair_min_w &&
+        ow <= pair_max_w &&
+        make_pair_conv(L, pool, max_n, in, in_coff, cin, w_hwio, kh, kw, cout, pad_h, pad_w, oh, ow, scale, shift, relu, out,
+                       out_coff, fmt)) {
+      L.pair_min_batch = pair_min_batch;
+      L.alt = std::make_shared<ConvLayer>(make_conv(pool, name, max_n, in, in_coff, cin, w_hwio, kh, kw, cout, stride, same, scale,
+                                                    shift, relu, out, out_coff, fmt, floor, out2, out2_coff, n_split,
+                                                    transpose_out, false));
+      return L;
+    }
+  }
   // Operand row width: the widest of 128/64/32 bytes (64/32/16 channels per K block) that pads Cin by at most
   // 12 % — Cin = 80 -> 5 x 16, 160 -> 5 x 32, 48 -> 3 x 16, 96 -> 3 x 32, 288 -> 5 x 64 (11 %), the rest x 64.
   // MEASURED: the TMA unit retires ~one box row per 2.7 cycles per SM whatever the row's width, so narrower
@@ -437,6 +559,18 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   const size_t budget = conv_v1 ? ((n_tile <= 128) ? 100 * 1024 : 200 * 1024) : 204 * 1024;
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  // Two epilogue teams need a second 16 KiB staging buffer.  MEASURED: where that costs a pipeline stage (the 17x17
+  // fused 1x1s, n_tile 176: 5 -> 4 stages) the layer got 10-20 % SLOWER (load-latency-bound), where it does not (conv3,
+  // 35x35 fused 1x1s: epilogue-bound) 6-16 % faster — so: two teams only if the ring keeps its depth.  ICP_EPI_TEAMS=1|2 forces.
+  int epi_teams = 1;
+  {
+    int s2 = static_cast<int>((budget - kOutStageBytes) / stage_bytes);
+    if (s2 > kMaxStages) s2 = kMaxStages;
+    if (s2 == stages) epi_teams = 2;
+    static const int force = getenv("ICP_EPI_TEAMS") ? atoi(getenv("ICP_EPI_TEAMS")) : 0;
+    if (force == 1) epi_teams = 1;
+    if (force == 2) { epi_teams = 2; stages = s2 < 1 ? 1 : s2; }
+  }
   if (conv_v1 && stages > num_kb) stages = num_kb;
   if (stages < 1) stages = 1;
   // The persistent kernel is used for every layer: since its role loops and epilogue were tightened it also beats
@@ -555,6 +689,8 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   void* d_bias = pool.alloc(bp.size() * 2);
   CK(cudaMemcpy(d_bias, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice));
   L.tm_bias = make_tm_2d_rows(d_bias, cout, 16, n_tile, 32, fmt);
+  L.d_w = static_cast<const uint16_t*>(d_w);
+  L.d_bias16 = static_cast<const uint16_t*>(d_bias);
 
   const uint64_t kp = static_cast<uint64_t>(num_kb) * ck;
   L.tm_b = make_tm_2d(d_w, cout, kp, kp, n_tile, fmt, rb);
@@ -619,6 +755,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.coff = out_coff;
   static const bool v1_staged = getenv("ICP_V1_STAGED") != nullptr;
   a.epi_staged = v1_staged ? 1 : 0;
+  a.epi_teams = persistent ? epi_teams : 1;
   a.dbg = nullptr;
   // ReLU column range: everything, nothing, or (fused siblings) the leading run of channels whose floor is 0
   a.relu_lo = 0;
@@ -635,7 +772,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.ldo2 = out2 ? out2->c : 0;
   a.coff2 = out2_coff;
   a.n_split = out2 ? n_split : (1 << 30);
-  L.smem = conv_smem_bytes(stages, n_tile, rb, persistent);
+  L.smem = conv_smem_bytes(stages, n_tile, rb, persistent, persistent ? epi_teams : 1);
   {
     const uint64_t out_rows = static_cast<uint64_t>(max_n) * oh * ow;
     L.tm_o = make_tm_out(out.p, out_rows, out.c, fmt);
@@ -647,6 +784,16 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
 }
 
 static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = false) {
+  if (L.pair) {
+    if (n < L.pair_min_batch && L.alt) { launch_conv(*L.alt, n, st, pdl); return; }
+    PairArgs a = L.pargs;
+    a.n_images = n;
+    const int items = ((n + 1) / 2) * a.bands_per_image;             // per N tile
+    int nclusters = (g_num_sms / 2) / a.n_tiles * a.n_tiles;
+    if (items * a.n_tiles < nclusters) nclusters = items * a.n_tiles;
+    launch_k(conv_pair_kernel, 2 * nclusters, kPairThreads, L.smem, st, pdl, 0, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_b_tail, L.tm_bias, a);
+    return;
+  }
   if (L.halo) {
     HaloArgs h = L.hargs;
     h.n_images = n;
@@ -804,6 +951,9 @@ struct icp_engine {
   cudaEvent_t fork_ev = nullptr;
   cudaEvent_t join_ev[kLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t stem_ops = 0;              // leading entries of `ops` that form the stem (conv1 .. pool2)
+  int fuse_pool_op = -1, fuse_conv_op = -1;   // pool1 / conv3: one pool_conv_kernel launch for batches >= fuse_min_batch
+  int fuse_min_batch = 16;
+  bool last_fused = false;          // the most recent forward did not materialise pool1
   int stem_chunk = 0;               // images per pass of the stem (0 = whole batch at once), see enqueue_tower
   int lanes_max_batch = 1 << 30;    // measured faster at every batch size (0.86 -> 0.61 ms at 1, 3.37 -> 3.23 ms at 128)
   int launches = 0;
@@ -1144,7 +1294,9 @@ struct Builder {
       x = p;
       tap("pool1", x);
     }
+    e.fuse_pool_op = static_cast<int>(ops.size()) - 1;
     x = conv_new(ops, "conv3", x, 80, 1, 1, 1, false);
+    e.fuse_conv_op = static_cast<int>(ops.size()) - 1;
     tap("conv3", x);
     x = conv_new(ops, "conv4", x, 192, 3, 3, 1, false);
     tap("conv4", x);
@@ -1358,7 +1510,26 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
     CK(cudaGetLastError());
     ++launches;
     mark(st);
+    // pool1 -> conv3 as ONE kernel (pool_conv.cuh) for throughput batches: the pooled tensor is never written
+    const Op* fc = e.fuse_conv_op >= 0 ? &e.ops[e.fuse_conv_op] : nullptr;
+    const bool fuse = !tm && chunk == n && fc && nc >= e.fuse_min_batch && fc->conv.d_w && !fc->conv.halo && !fc->conv.pair &&
+                      fc->conv.args.taps == 1 && fc->conv.args.cblocks == 1 && fc->conv.cout <= kPoolConvMaxCout &&
+                      e.ops[e.fuse_pool_op].in.c == 64 && e.ops[e.fuse_pool_op].c == 64;
+    e.last_fused = fuse;
     for (size_t i = 0; i < e.stem_ops; ++i) {
+      if (fuse && static_cast<int>(i) == e.fuse_pool_op) continue;
+      if (fuse && static_cast<int>(i) == e.fuse_conv_op) {
+        const Op& po = e.ops[e.fuse_pool_op];
+        PoolConvArgs pa{};
+        pa.in = po.in.p; pa.N = nc; pa.H = po.in.h; pa.W = po.in.w;
+        pa.w = fc->conv.d_w; pa.bias16 = fc->conv.d_bias16; pa.cout = fc->conv.cout;
+        pa.out = static_cast<uint16_t*>(fc->conv.args.out); pa.OH = po.out.h; pa.OW = po.out.w; pa.ldo = fc->conv.args.ldo;
+        pa.coff = fc->conv.args.coff; pa.relu = fc->conv.args.relu_hi > 0 ? 1 : 0; pa.fmt = fmt;
+        const int tiles = (nc * pa.OH * pa.OW + kBM - 1) / kBM;
+        launch_k(pool_conv_kernel, tiles < g_num_sms ? tiles : g_num_sms, kPoolConvThreads, pool_conv_smem_bytes(), st, pdl.take(st), 1, pa);
+        ++launches;
+        continue;
+      }
       launches += run_op(e.ops[i], nc, fmt, st, i + 1 == e.stem_ops ? i0 : 0, pdl.take(st));
       mark(st);
     }
@@ -1479,6 +1650,8 @@ static void set_kernel_attrs(int device) {
   CK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(pool_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pool_conv_smem_bytes())));
   CK(cudaFuncSetAttribute(conv0_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           static_cast<int>(conv0_tc_smem_bytes())));
   CK(cudaFuncSetAttribute(conv0_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1571,6 +1744,7 @@ int icp_create(const icp_config* cfg, icp_engine** out) {
     CK(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
     if (const char* v = getenv("ICP_LANES_MAX_BATCH")) e->lanes_max_batch = atoi(v);
     if (const char* v = getenv("ICP_STEM_CHUNK")) e->stem_chunk = atoi(v);
+    if (const char* v = getenv("ICP_FUSE_POOL_MIN_BATCH")) e->fuse_min_batch = atoi(v);
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&e->slot_h2d[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
@@ -2001,6 +2175,9 @@ int icp_endpoint(icp_engine* e, const char* name, float* out_host) {
     auto it = e->endpoints.find(name);
     if (it == e->endpoints.end()) fail(ICP_E_INVALID, "unknown end point '%s'", name);
     const Endpoint& ep = it->second;
+    if (e->last_fused && strcmp(name, "pool1") == 0)
+      fail(ICP_E_INVALID, "end point 'pool1' was not materialised: at batch >= %d pool1 is fused into conv3's operand load "
+                          "(ICP_FUSE_POOL_MIN_BATCH)", e->fuse_min_batch);
     CK(cudaStreamSynchronize(e->stream));
     if (ep.vec) {
       CK(cudaMemcpy(out_host, ep.vec, static_cast<size_t>(e->last_n) * ep.c * 4, cudaMemcpyDeviceToHost));
@@ -2067,11 +2244,12 @@ int icp_conv2d_bn_relu(int device, int precision, const float* x, int n, int h, 
                             relu != 0, out, 0, fmt);
     const char* tl_path = getenv("ICP_TIMELINE");
     long long* d_dbg = nullptr;
-    if (tl_path && (L.persistent || L.halo)) {
+    if (tl_path && (L.persistent || L.halo || L.pair)) {
       d_dbg = static_cast<long long*>(pool.alloc(14 * 512 * 8));
       CK(cudaMemsetAsync(d_dbg, 0, 14 * 512 * 8, st));
       L.args.dbg = d_dbg;
       L.hargs.dbg = d_dbg;
+      L.pargs.dbg = d_dbg;
     }
     launch_conv(L, n, st);
     if (d_dbg) {
@@ -2081,6 +2259,7 @@ int icp_conv2d_bn_relu(int device, int precision, const float* x, int n, int h, 
       if (FILE* f = fopen(tl_path, "wb")) { fwrite(hd.data(), 8, hd.size(), f); fclose(f); }
       L.args.dbg = nullptr;
       L.hargs.dbg = nullptr;
+      L.pargs.dbg = nullptr;
     }
     h16_to_f32_kernel<<<static_cast<unsigned>((out_elems + 255) / 256), 256, 0, st>>>(out.p, d_yf,
                                                                                      static_cast<size_t>(n) * oh * ow,

@@ -3,10 +3,11 @@
 The reference builds this graph imperatively with TF-Slim
 (/root/reference/inception/slim/inception_model.py:86-329).  Here the same
 topology is data: a stem list plus eleven block tables, walked by
-``conv_layers()`` / ``variables()``.  The CUDA engine (csrc/tower.cu) carries
-its own copy of this table; tests/test_spec.py checks the two against each
-other, against the oracle, and against the 388 variable names decoded from the
-reference's data/model.meta (tests/golden/model_meta_variables.txt).
+``conv_layers()`` / ``variables()``.  The CUDA engine builds its launch plan from the same
+topology in csrc/engine.cu (``Builder::build``: it asks the weight blob for exactly these names and
+shapes and fails loudly on any mismatch); tests/test_spec.py checks this table against the oracle's
+recorded variable requests and against the 388 variable names/shapes decoded from the reference's
+data/model.meta (tests/golden/model_meta_variables.txt); the GPU parity tests check the engine.
 
 Naming follows the reference's variable scopes: a conv inside
 ``with tf.variable_scope('mixed_35x35x256a'): with tf.variable_scope('branch5x5')``

@@ -8,7 +8,8 @@ reference's layouts (conv HWIO fp32, fc [in,out] fp32):
 
     "ICPWv001" | u32 count | count x { u16 len | name | u8 ndim | u32 dims[ndim] | f32 data }
 
-(all little-endian).  csrc/weights_blob.cpp reads the same format.
+(all little-endian).  csrc/engine.cu (read_blob) reads the same format; tf_checkpoint.py converts the TF V1
+checkpoint the reference restores into it.
 """
 from __future__ import annotations
 

@@ -397,8 +397,14 @@ def test_large_class_head(eng_mod, tmp_path, num_classes):
 
 @pytest.mark.parametrize("precision", ["fp16", "bf16"])
 def test_trained_like_batchnorm_statistics(eng_mod, tmp_path, precision):
-    """with trained statistics (|mean|/sigma of several units, variances over orders of magnitude) the BN
-    fold — and in particular the pool branch, whose affine is applied BEFORE the avg-pool now — must still meet the bar."""
+    """with TRUE statistics (|mean|/sigma of several units, variances over orders of magnitude) the BN fold —
+    and in particular the pool branch, whose whole affine is applied BEFORE the avg-pool now — must add no error of its own.
+
+    A random net whose BatchNorm really normalises is chaotic (MEASURED, pure fp32 on the CPU: an input perturbation of
+    1.7e-4 relative grows to 6e-2 at mixed_8x8x2048b), so ANY 16-bit storage drifts from the fp32 oracle (0.19 relative at the
+    last block, GPU and CPU simulation alike) and a fixed 1e-3 bar is meaningless here.  The bar is therefore relative to the
+    oracle run with the same storage rounding on the CPU (Tower(quant=...)): the engine may not be worse than 1.5x that, on
+    whole blocks AND on their branch_pool slices, and it must agree with the rounded oracle better than with the fp32 one."""
     from conftest import calibrated_weights
     from oracle import inception_oracle as O
     from tensorflow_web_deploy_b200 import weights
@@ -409,16 +415,26 @@ def test_trained_like_batchnorm_statistics(eng_mod, tmp_path, precision):
     x = np.random.default_rng(5).uniform(-1, 1, (2, 299, 299, 3)).astype(np.float32)
     tw = O.Tower(W)
     _, pred = tw.forward(x, 6, with_aux=False)
+    dt = torch.float16 if precision == "fp16" else torch.bfloat16
+    sim = O.Tower(W, quant=lambda t: t.to(dt).to(torch.float32))
+    _, spred = sim.forward(x, 6, with_aux=False)
     eng = eng_mod.Engine(path, 6, max_batch=2, precision=precision)
     probs = eng.forward(x)
-    assert np.abs(probs - pred).max() <= PROB_TOL[precision]
-    rel_lim = 2.5e-3 if precision == "fp16" else 2e-2
-    for k in ("mixed_35x35x256a", "mixed_17x17x768b", "mixed_17x17x768e", "mixed_8x8x2048b"):
-        got, ref = eng.endpoint(k), tw.end_points[k]
-        pool = slice(got.shape[3] - (32 if k.endswith("256a") else 192), got.shape[3])     # the branch_pool slice
-        for sl in (slice(None), pool):
-            rel = np.sqrt(((got[..., sl] - ref[..., sl]) ** 2).mean()) / (np.sqrt((ref[..., sl] ** 2).mean()) + 1e-12)
-            assert rel <= rel_lim, (k, sl, rel)
+
+    def rel(a, b):
+        return float(np.sqrt(((a - b) ** 2).mean()) / (np.sqrt((b ** 2).mean()) + 1e-12))
+
+    for k in ("conv4", "mixed_35x35x256a", "mixed_35x35x288b", "mixed_17x17x768b", "mixed_17x17x768e", "mixed_8x8x2048b"):
+        got, ref, sr = eng.endpoint(k), tw.end_points[k], sim.end_points[k]
+        slices = [slice(None)]
+        if k.startswith("mixed"):
+            slices.append(slice(got.shape[3] - (32 if k.endswith("256a") else (64 if "35x35" in k else 192)), got.shape[3]))   # branch_pool
+        for sl in slices:
+            e_gpu, e_sim = rel(got[..., sl], ref[..., sl]), rel(sr[..., sl], ref[..., sl])
+            assert e_gpu <= 1.5 * e_sim + 1e-3, (k, sl, e_gpu, e_sim)
+    d_gpu, d_sim = float(np.abs(probs - pred).max()), float(np.abs(spred - pred).max())
+    assert d_gpu <= 1.5 * d_sim + 1e-3, (d_gpu, d_sim)
+    np.testing.assert_array_equal(np.argsort(-probs, axis=1, kind="stable")[:, :3], np.argsort(-pred, axis=1, kind="stable")[:, :3])
     eng.close()
 
 
@@ -580,3 +596,28 @@ def test_tf_checkpoint_drops_in_as_model_def_file(synth6, tmp_path, built_lib):
     b = P.ImagenetClassifier(path, syn).classify_image(jpeg)
     assert a is not None and a[0] == b[0]
     np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_pool1_conv3_fusion_is_bit_identical(eng_mod, synth6):
+    """Batches >= ICP_FUSE_POOL_MIN_BATCH (16) run pool1 -> conv3 as ONE kernel (csrc/pool_conv.cuh: the 3x3/2 max is taken
+    while the A operand tile is built; the pooled tensor is never written).  max() is exact and the MMA sequence is the
+    unfused conv3's, so every image must come out bit-identical to its batch-1 (unfused) result."""
+    from oracle import inception_oracle as O
+    rng = np.random.default_rng(31)
+    x = rng.uniform(-1, 1, (17, 299, 299, 3)).astype(np.float32)
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=17, precision="fp16", use_cuda_graph=True)
+    p = eng.forward(x)
+    conv3 = eng.endpoint("conv3")
+    with pytest.raises(eng_mod.EngineError, match="pool1"):
+        eng.endpoint("pool1")                                    # not materialised in the fused path
+    for i in (0, 8, 16):
+        np.testing.assert_array_equal(eng.forward(x[i:i + 1]), p[i:i + 1])
+        np.testing.assert_array_equal(eng.endpoint("conv3")[0], conv3[i])
+        assert eng.endpoint("pool1").shape == (1, 73, 73, 64)    # batch 1: the two-kernel path, pool1 exists
+    tw = O.Tower(synth6[1])
+    _, pred = tw.forward(x[:3], 6, with_aux=False)
+    assert np.abs(p[:3] - pred).max() <= 1e-3
+    ref = tw.end_points["conv3"]
+    rel = np.sqrt(((conv3[:3] - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean())
+    assert rel <= 2.5e-3
+    eng.close()

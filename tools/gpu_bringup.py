@@ -173,6 +173,14 @@ def cmd_tower(args):
     from tensorflow_web_deploy_b200 import engine
     C = 6
     path, W = _weights_file(C)
+    if getattr(args, "calibrated", False):      # trained-like BatchNorm statistics (tests/conftest.py)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from conftest import calibrated_weights
+        from tensorflow_web_deploy_b200 import weights as _w
+        W = calibrated_weights(C)
+        W["logits/logits/weights"] = (W["logits/logits/weights"] * args.fc_scale).astype(np.float32)
+        path = os.path.join(tempfile.gettempdir(), "icp_calibrated_c%d.icpw" % C)
+        _w.save_blob(path, W)
     x = np.random.default_rng(0).uniform(-1, 1, (args.n, 299, 299, 3)).astype(np.float32)
     t0 = time.time()
     tw = O.Tower(W)
@@ -302,7 +310,8 @@ def main():
     p = sub.add_parser("conv"); p.add_argument("--only", default=None)
     sub.add_parser("pools")
     p = sub.add_parser("tower"); p.add_argument("--precision", default="fp16"); p.add_argument("--n", type=int, default=2)
-    p.add_argument("--graph", action="store_true")
+    p.add_argument("--graph", action="store_true"); p.add_argument("--calibrated", action="store_true")
+    p.add_argument("--fc-scale", type=float, default=4.0)
     p = sub.add_parser("speed"); p.add_argument("--precision", default="bf16"); p.add_argument("--n", type=int, default=128)
     p.add_argument("--iters", type=int, default=10); p.add_argument("--graph", action="store_true")
     p = sub.add_parser("profile"); p.add_argument("--precision", default="bf16"); p.add_argument("--n", type=int, default=128)
