@@ -202,7 +202,13 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra sustained run (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--http", action="store_true",
+                    help="BASELINE configs[4]: the HTTP load test (tools/http_bench.py: 8 pre-fork workers, concurrent POSTs of "
+                         "sample.jpg, micro-batched on every visible GPU) instead of the tower benchmark")
     args = ap.parse_args()
+    if args.http:
+        os.execv(sys.executable, [sys.executable, os.path.join(ROOT, "tools", "http_bench.py"), "--workers", "8",
+                                  "--precision", args.precision])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

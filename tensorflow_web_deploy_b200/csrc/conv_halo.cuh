@@ -51,7 +51,9 @@ struct HaloArgs {
   int acc_cols;         // TMEM columns of one accumulator set: T * n_tile
   int acc_sets;         // 2 when 2 * acc_cols <= 512, else 1
   int tmem_cols;        // power of two >= acc_sets * acc_cols
-  int w_resident;       // 1: all weights live in smem (n_tiles == 1)
+  int w_resident;       // 1: the weights of this CTA's N tile live in smem for its whole life (grid is a multiple of n_tiles,
+                        //    so a CTA's items all have N tile blockIdx.x % n_tiles)
+  int tail_ksteps;      // K = 16 MMAs issued for the LAST channel chunk (its zero-padded K slices are skipped)
   int w_bytes;          // resident: chunks * taps * n_tile * row_bytes; streaming: b_stages * tile pitch
   int b_stages;         // streaming ring depth (<= 8)
   int fmt;
@@ -96,7 +98,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint32_t* tap_off = reinterpret_cast<uint32_t*>(gbase + (bar_base - base) + 256);   // [taps] A shift of tap (r,s), 16-B units
   int* s_pix = reinterpret_cast<int*>(tap_off + 64);                 // [2][128] per team: output pixel of each sub-tile row, -1 = none
   const uint32_t stage_base = bar_base + 2048u;                      // epilogue staging: 2 teams x 128 rows x 128 B
-  const uint32_t ones_base = stage_base + 2u * 16384u;               // constant A tile of the bias MMA (after both teams' staging)
+  const uint32_t ones_base = stage_base + (kDirect ? 0u : 2u * 16384u);   // constant A tile of the bias MMA (after the staged epilogue's buffers)
   const uint32_t bias_base = ones_base + kOnesBytes;                 // resident weights: the [n_tile x 16] shift tile
 
   const int taps = a.kh * a.kw;
@@ -172,9 +174,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // ---------------- weight producer ----------------
     if (f_resident) {
       if (ptx::elect_one()) {
+        const int n_row = (static_cast<int>(blockIdx.x) % a.n_tiles) * a.n_tile;     // this CTA's N tile (static)
         ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes + static_cast<uint32_t>(a.n_tile) * 32u);
-        ptx::tma_load_2d(bias_base, &tm_bias, w_full, 0, 0);
-        for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, 0);
+        ptx::tma_load_2d(bias_base, &tm_bias, w_full, 0, n_row);
+        for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, n_row);
       }
       __syncwarp();
     } else {
@@ -254,11 +257,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (f_resident) {
           if (ptx::elect_one()) {
             uint32_t b_units = (wbase >> 4) + static_cast<uint32_t>(c * taps) * tap_units;
+            const int ks = (c == a.chunks - 1) ? a.tail_ksteps : ksteps;
             for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
               uint32_t au = a_units0 + tap_off[tap];
               uint32_t tacc = tacc0;
               for (int j = 0; j < nsub; ++j, au += sub_units, tacc += a.n_tile) {
-                if (ksteps == 2) {
+                if (ks != ksteps) {
+                  // tail chunk: only the K slices that hold channels (unrolled: a counted loop costs the issuing thread ~100
+                  // cycles per MMA, MEASURED on the 5x5 48->64 layer, against ~50 for straight-line code)
+                  ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, 1u);
+                  if (ks > 1) ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
+                  if (ks > 2) ptx::umma_f16(tacc, desc_hi | (au + 4u), desc_hi | (b_units + 4u), idesc, 1u);
+                } else if (ksteps == 2) {
                   ptx::umma_f16(tacc, desc_hi | au, desc_hi | b_units, idesc, 1u);
                   ptx::umma_f16(tacc, desc_hi | (au + 2u), desc_hi | (b_units + 2u), idesc, 1u);
                 } else {
@@ -451,9 +461,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
-inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes) {
+inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes, bool direct = false) {
   return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 2048 +
-         2 * 16384 + kOnesBytes + 8192;   // barriers + per-tap offsets + row->pixel tables, 2 x epilogue staging, ones tile, shift tile
+         (direct ? 0 : 2 * 16384) + kOnesBytes + 8192;   // barriers + per-tap offsets + row->pixel tables, 2 x epilogue staging, ones tile, shift tile
 }
 
 }  // namespace icp

@@ -598,6 +598,68 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   static const int halo_min_w = getenv("ICP_HALO_MIN_W") ? atoi(getenv("ICP_HALO_MIN_W")) : 100;
   static const bool halo_tall = getenv("ICP_HALO_TALL") != nullptr;
   const bool tall = (kh == 1) && halo_tall;
+  // Weight-resident strips with a STATIC N tile per CTA (profiles/r02_pair_kernel.md §3): the layer's output channels are
+  // split into n_tiles slices small enough that one slice's weights stay in shared memory for the CTA's whole life (the grid is
+  // a multiple of n_tiles, so CTA b only ever sees N tile b % n_tiles); the input strip is the only stream and is re-read once
+  // per slice.  Narrow N costs MMA efficiency ((128 + n_tile) x 32 B of operands per MMA against 128 B/cycle of shared memory)
+  // but removes both per-tap re-reads that bound the im2col kernel.  ICP_HALO_RES=0 disables, ICP_HALO_RES_MIN_W / _MAX_W bound the maps.
+  static const bool halo_res = getenv("ICP_HALO_RES") ? atoi(getenv("ICP_HALO_RES")) != 0 : false;
+  static const int res_min_w = getenv("ICP_HALO_RES_MIN_W") ? atoi(getenv("ICP_HALO_RES_MIN_W")) : 30;
+  static const int res_max_w = getenv("ICP_HALO_RES_MAX_W") ? atoi(getenv("ICP_HALO_RES_MAX_W")) : 50;
+  if (halo_res && allow_pair && !no_halo && !out2 && !floor && !transpose_out && stride == 1 && kh * kw > 1 && cin % 16 == 0 &&
+      ow >= res_min_w && ow <= res_max_w && in.w + 2 * pad_w <= 256) {
+    const int rb = cin <= 32 ? 64 : 128, ck = rb / 2;
+    const int wp = in.w + 2 * pad_w, chunks = (cin + ck - 1) / ck, taps = kh * kw;
+    int best_nt = 0, best_T = 0, best_ns = 0, best_rows = 0, best_sb = 0;
+    for (int parts = 1; parts <= 8 && !best_nt; ++parts) {
+      if (cout % parts || (cout / parts) % 16) continue;
+      const int nt = cout / parts;
+      if (nt > 256) continue;
+      const int res_bytes = chunks * taps * nt * rb;
+      for (int T = 4; T >= 1 && !best_nt; T >>= 1) {
+        if (2 * T * nt > 512) continue;
+        const int sr = (kh - 1) + 1 + (wp - 1 + (T * kBM - 1) + (kw - 1)) / wp;
+        const int sb = ((sr * wp * rb) + 1023) & ~1023;
+        if (sr > 256) continue;
+        int ns = 4;
+        while (ns >= 2 && halo_smem_bytes(sb, ns, res_bytes, true) > 225 * 1024) --ns;
+        if (ns < 2) continue;
+        best_nt = nt; best_T = T; best_ns = ns; best_rows = sr; best_sb = sb;
+      }
+    }
+    if (best_nt) {
+      const int n_tile_r = best_nt, T = best_T;
+      const int res_bytes = chunks * taps * n_tile_r * rb;
+      std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt, scale);
+      void* d_w = pool.alloc(wp_host.size() * 2);
+      CK(cudaMemcpy(d_w, wp_host.data(), wp_host.size() * 2, cudaMemcpyHostToDevice));
+      std::vector<uint16_t> bp = pack_bias(shift, cout, fmt);
+      void* d_bias = pool.alloc(bp.size() * 2);
+      CK(cudaMemcpy(d_bias, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice));
+      L.tm_bias = make_tm_2d_rows(d_bias, cout, 16, n_tile_r, 32, fmt);
+      L.tm_b = make_tm_2d_rows(d_w, cout, static_cast<uint64_t>(chunks) * taps * ck, n_tile_r, rb, fmt);
+      L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, best_rows, rb, fmt);
+      L.halo = true;
+      L.n_tiles = cout / n_tile_r;
+      HaloArgs& h = L.hargs;
+      h = HaloArgs{};
+      h.oh = oh; h.ow = ow; h.wp = wp; h.pad_h = pad_h; h.pad_w = pad_w; h.kh = kh; h.kw = kw;
+      h.chunks = chunks; h.row_bytes = rb; h.T = T; h.strip_rows = best_rows; h.strip_bytes = best_sb; h.nstrips = best_ns;
+      h.bands_per_image = (oh * wp + kBM * T - 1) / (kBM * T);
+      h.n_tile = n_tile_r; h.n_tiles = L.n_tiles;
+      h.acc_cols = T * n_tile_r; h.acc_sets = 2; h.tmem_cols = pow2_cols(2 * T * n_tile_r);
+      h.w_resident = 1; h.w_bytes = res_bytes; h.b_stages = 1;
+      h.tail_ksteps = (cin - (chunks - 1) * ck + 15) / 16;
+      h.fmt = fmt; h.relu = relu ? 1 : 0; h.epi_direct = 1;
+      h.out = out.p; h.ldo = out.c; h.coff = out_coff;
+      L.smem = halo_smem_bytes(best_sb, best_ns, res_bytes, true);
+      L.pair_min_batch = getenv("ICP_HALO_RES_MIN_BATCH") ? atoi(getenv("ICP_HALO_RES_MIN_BATCH")) : 8;
+      L.alt = std::make_shared<ConvLayer>(make_conv(pool, name, max_n, in, in_coff, cin, w_hwio, kh, kw, cout, stride, same, scale,
+                                                    shift, relu, out, out_coff, fmt, floor, out2, out2_coff, n_split,
+                                                    transpose_out, false));
+      return L;
+    }
+  }
   if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && in.w + 2 * pad_w <= 256 &&
       (tall || ow >= halo_min_w) && (!transpose_out || (tall && oh == ow))) {
     const int rb = cin <= 32 ? 64 : 128, ck = rb / 2;
@@ -670,6 +732,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       h.n_tile = n_tile; h.n_tiles = L.n_tiles;
       h.acc_cols = T * n_tile; h.acc_sets = acc_sets; h.tmem_cols = pow2_cols(acc_sets * T * n_tile);
       h.w_resident = resident ? 1 : 0; h.w_bytes = w_bytes; h.b_stages = b_stages;
+      h.tail_ksteps = rb / 32;                 // this configuration multiplies the zero-padded K slices of the last chunk too
       h.fmt = fmt; h.relu = relu ? 1 : 0;
       // narrow tiles store straight from registers (conv1, 32 channels: 0.147 -> 0.117 ms); at 64 channels the 16-byte
       // stores of one warp touch 32 lines per instruction and the staged copy-out is as fast (conv2 0.165 vs 0.169 ms)
@@ -795,11 +858,13 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
     return;
   }
   if (L.halo) {
+    if (L.alt && n < L.pair_min_batch) { launch_conv(*L.alt, n, st, pdl); return; }
     HaloArgs h = L.hargs;
     h.n_images = n;
     const int bands = h.tall ? (n * h.oh * h.wp + kBM * h.T - 1) / (kBM * h.T) : h.bands_per_image * n;
     const int items = bands * h.n_tiles;
-    const unsigned grid = static_cast<unsigned>(items < g_num_sms ? items : g_num_sms);
+    unsigned grid = static_cast<unsigned>(items < g_num_sms ? items : g_num_sms);
+    if (h.w_resident && h.n_tiles > 1) grid = grid / h.n_tiles * h.n_tiles;       // static N tile per CTA: b % n_tiles
     const bool stem = h.w_resident && !h.tall && !h.transpose_out;
     if (h.epi_direct) {
       if (stem) launch_k(conv_halo_kernel<true, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
