@@ -87,6 +87,8 @@ struct ConvArgs {
   int relu_lo, relu_hi;
   int epi_staged;      // one-tile kernel: 1 = epilogue through shared staging + coalesced stores, 0 = row-per-thread stores
   int epi_teams;       // persistent kernel: 2 = two independent 4-warp epilogue teams (own staging each), 1 = one 8-warp team
+  int dual;            // persistent kernel (epi_teams == 2 only): 1 = a work item is TWO consecutive M tiles that share every
+                       //   weight tile (stage = A0 | A1 | W); the two TMEM halves are simultaneous accumulators, not a double buffer
   long long* dbg;      // optional timeline buffer (CTA 0 only): [role][event] clock64 stamps, see tools/timeline.py
 };
 
@@ -431,7 +433,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const int ck = a.row_bytes / 2;
   const uint32_t a_bytes = static_cast<uint32_t>(kBM) * rb;
   const uint32_t b_bytes = static_cast<uint32_t>(a.n_tile) * rb;
-  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u; // stage pitch keeps every tile on a swizzle period
+  const bool dual = !kCluster && a.dual != 0;
+  const uint32_t mts = dual ? 2u : 1u;                         // M tiles per work item
+  const uint32_t a_all = a_bytes * mts;                        // A bytes of a stage (W tile follows)
+  const uint32_t stage_bytes = (a_all + b_bytes + 1023u) & ~1023u; // stage pitch keeps every tile on a swizzle period
   const uint32_t out_stage = base + a.stages * stage_bytes;    // 16 KiB epilogue staging
   const uint32_t ones_base = out_stage + static_cast<uint32_t>(a.epi_teams) * kOutStageBytes;  // 4 KiB constant A tile of the bias MMA
   const uint32_t bar_base = ones_base + kOnesBytes;
@@ -445,12 +450,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   // work item t -> (M tile or, in a cluster, pair of M tiles; N tile).  tile_of(t) = this CTA's M tile.
   uint32_t crank = 0;
   if constexpr (kCluster) crank = ptx::cluster_ctarank();
-  const int total_tiles = (kCluster ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int total_tiles = ((kCluster || dual) ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
   const int num_kb = a.taps * a.cblocks;
   const bool narrow_tail = a.tail_rb != a.row_bytes;
   const int first = static_cast<int>(blockIdx.x) / (kCluster ? 2 : 1);
   const int step = static_cast<int>(gridDim.x) / (kCluster ? 2 : 1);
-  auto tile_m0 = [&](int t) { return ((t / n_tiles) * (kCluster ? 2 : 1) + static_cast<int>(crank)) * kBM; };
+  auto tile_m0 = [&](int t) { return ((t / n_tiles) * ((kCluster || dual) ? 2 : 1) + static_cast<int>(crank)) * kBM; };
 
   ptx::pdl_launch();
   if (warp == 0 && lane == 0) {
@@ -509,13 +514,20 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     };
     for (int t = first; t < total_tiles; t += step) {
       const int m0 = tile_m0(t);
-      int bw = 0, bh = 0, bn = 0;
+      int bw = 0, bh = 0, bn = 0, bw1 = 0, bh1 = 0, bn1 = 0;
       if (a.im2col) {
         const int q = m0 % a.ow;
         const int r = m0 / a.ow;
         bw = q * a.stride - a.pad_w;
         bh = (r % a.oh) * a.stride - a.pad_h;
         bn = r / a.oh;
+        if (dual) {                               // second M tile of the item: base pixel m0 + 128
+          const int q1 = (m0 + kBM) % a.ow;
+          const int r1 = (m0 + kBM) / a.ow;
+          bw1 = q1 * a.stride - a.pad_w;
+          bh1 = (r1 % a.oh) * a.stride - a.pad_h;
+          bn1 = r1 / a.oh;
+        }
       }
       // bias block: the ones tile is resident, nothing to load
       if (gpar == mine) {
@@ -533,12 +545,16 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           if (ptx::elect_one()) {
             const bool tail = narrow_tail && cb == cb_last;
             const CUtensorMap* ma = tail ? &tm_a_tail : &tm_a;
-            ptx::mbar_expect_tx(full_bar(s), tail ? a_tail_bytes : a_bytes);
+            ptx::mbar_expect_tx(full_bar(s), (tail ? a_tail_bytes : a_bytes) * mts);
             if (a.im2col) {
               ptx::tma_load_im2col_4d(sa, ma, full_bar(s), cb * ck, bw, bh, bn, static_cast<uint16_t>(ts),
                                       static_cast<uint16_t>(tr));
+              if (dual)
+                ptx::tma_load_im2col_4d(sa + a_bytes, ma, full_bar(s), cb * ck, bw1, bh1, bn1, static_cast<uint16_t>(ts),
+                                        static_cast<uint16_t>(tr));
             } else {
               ptx::tma_load_2d(sa, ma, full_bar(s), cb * ck, m0);
+              if (dual) ptx::tma_load_2d(sa + a_bytes, ma, full_bar(s), cb * ck, m0 + kBM);
             }
           }
           __syncwarp();
@@ -557,12 +573,12 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     uint32_t it = 0;
     int s = 0;
     uint32_t ph = 0;
-    uint32_t sb = base + a_bytes;
+    uint32_t sb = base + a_all;
     const uint32_t b_tail_bytes = static_cast<uint32_t>(a.n_tile) * a.tail_rb;
     const int cb_last = a.cblocks - 1;
     auto advance = [&]() {
       sb += stage_bytes;
-      if (++s == a.stages) { s = 0; ph ^= 1u; sb = base + a_bytes; }
+      if (++s == a.stages) { s = 0; ph ^= 1u; sb = base + a_all; }
     };
     for (int t = first; t < total_tiles; t += step) {
       const int n_base = (t % n_tiles) * a.n_tile;
@@ -612,7 +628,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     const uint64_t hi_tail = ptx::make_smem_desc_rows(0, a.tail_rb);
     const uint64_t hi_32 = ptx::make_smem_desc_rows(0, 32);
     const uint64_t d_ones = hi_32 | ((ones_base & 0x3FFFFu) >> 4);
-    const uint32_t a_units = a_bytes >> 4;
+    const uint32_t a_units = a_all >> 4;                                    // W tile offset inside a stage
+    const uint32_t a1_units = a_bytes >> 4;                                 // dual: second A tile offset
     const uint32_t stage_units = stage_bytes >> 4;
     const uint32_t base_units = (base & 0x3FFFFu) >> 4;
     const int cb_last = a.cblocks - 1;
@@ -630,15 +647,18 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       if (++s == a.stages) { s = 0; ph ^= 1u; su = base_units; }
     };
     for (int t = first; t < total_tiles; t += step, ++lt) {
-      const uint32_t as = lt & 1u;
-      ptx::mbar_wait(tmem_empty(as), ((lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+      // dual: both TMEM halves belong to this item (barrier pair 0, one phase per item); else they alternate per tile
+      const uint32_t as = dual ? 0u : (lt & 1u);
+      ptx::mbar_wait(tmem_empty(as), ((dual ? lt : (lt >> 1)) & 1u) ^ 1u);   // epilogue has drained this accumulator
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + as * a.tmem_cols;
+      const uint32_t tacc1 = tmem_base + a.tmem_cols;          // dual: accumulator of the item's second M tile
       // bias block: accumulator := shift (hi + lo halves) broadcast down the 128 rows
       ptx::mbar_wait(full_bar(s), ph);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         ptx::umma_f16(tacc, d_ones, hi_32 | (su + a_units), idesc, 0u);
+        if (dual) ptx::umma_f16(tacc1, d_ones, hi_32 | (su + a_units), idesc, 0u);
         commit_empty(s);
       }
       __syncwarp();
@@ -650,12 +670,26 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           if (ksteps == 4) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
+            if (dual) {
+              const uint64_t da1 = hi_main | (su_ + a1_units);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tacc1, da1 + 2u * k, db + 2u * k, idesc, 1u);
+            }
           } else {
             for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
+            if (dual) {
+              const uint64_t da1 = hi_main | (su_ + a1_units);
+              for (int k = 0; k < ksteps; ++k) ptx::umma_f16(tacc1, da1 + 2u * k, db + 2u * k, idesc, 1u);
+            }
           }
         } else {
           const uint64_t da = hi_tail | su_, db = hi_tail | (su_ + a_units);
           for (int k = 0; k < a.tail_ksteps; ++k) ptx::umma_f16(tacc, da + 2u * k, db + 2u * k, idesc, 1u);
+          if (dual) {
+            // narrow tail tiles: the second A tile sits at the FULL tile pitch (a_bytes), rows of tail_rb bytes
+            const uint64_t da1 = hi_tail | (su_ + a1_units);
+            for (int k = 0; k < a.tail_ksteps; ++k) ptx::umma_f16(tacc1, da1 + 2u * k, db + 2u * k, idesc, 1u);
+          }
         }
       };
       int kb = 0;
@@ -721,32 +755,39 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
         // (the MMAs run at full width), the epilogue simply stops at `cols`
         const int cols = a.cout - n_base < a.n_tile ? a.cout - n_base : a.n_tile;
         const int nchunks = (cols + 63) >> 6;
-        const uint32_t as = lt & 1u;
+        // dual: the item's two M tiles sit in the two TMEM halves (the second may lie past the last tile: skipped)
+        const int subs = dual ? ((m0 / kBM + 1 < m_tiles) ? 2 : 1) : 1;
+        const int tchunks = nchunks * subs;
+        const uint32_t as = dual ? 0u : (lt & 1u);
         ICP_STAMP(a.dbg, 6, lt, et == 0);
-        ptx::mbar_wait(tmem_full(as), (lt >> 1) & 1u);
+        ptx::mbar_wait(tmem_full(as), (dual ? lt : (lt >> 1)) & 1u);
         ptx::tc_fence_after();
         ICP_STAMP(a.dbg, 4, lt, et == 0);
-        const uint32_t taddr = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-        // my chunks of this tile: c with (gchunk + c) odd/even = team; the last of them releases the accumulator
+        const uint32_t taddr0 = tmem_base + as * a.tmem_cols + (static_cast<uint32_t>(quarter * 32) << 16);
+        // my chunks of this item: cc with (gchunk + cc) odd/even = team; the last of them releases the accumulator(s)
         int last_mine = -1;
-        for (int c = nchunks - 1; c >= 0; --c)
-          if (((gchunk + static_cast<uint32_t>(c)) & 1u) == static_cast<uint32_t>(team)) { last_mine = c; break; }
-        if (last_mine < 0) {                         // nothing of this tile is mine: hand the accumulator back at once
+        for (int cc = tchunks - 1; cc >= 0; --cc)
+          if (((gchunk + static_cast<uint32_t>(cc)) & 1u) == static_cast<uint32_t>(team)) { last_mine = cc; break; }
+        if (last_mine < 0) {                         // nothing of this item is mine: hand the accumulator back at once
           ptx::tc_fence_before();
           ptx::mbar_arrive(tmem_empty(as));
         }
-        for (int c = 0; c < nchunks; ++c) {
-          if (((gchunk + static_cast<uint32_t>(c)) & 1u) != static_cast<uint32_t>(team)) continue;
+        for (int cc = 0; cc < tchunks; ++cc) {
+          if (((gchunk + static_cast<uint32_t>(cc)) & 1u) != static_cast<uint32_t>(team)) continue;
+          const int sub = cc >= nchunks ? 1 : 0;
+          const int c = cc - sub * nchunks;
+          const int ms = m0 + sub * kBM;
+          const uint32_t taddr = taddr0 + static_cast<uint32_t>(sub) * a.tmem_cols;
           const int c0 = c << 6;
           int cp = (cols - c0) >> 4;                 // 16-column pieces in this chunk (<= 4)
           if (cp > 4) cp = 4;
           uint32_t v[64];
-  #pragma unroll
+#pragma unroll
           for (int j = 0; j < 4; ++j)
             if (j < cp) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
           ptx::tmem_ld_wait();
           ICP_STAMP(a.dbg, 13, lt * 4 + c, et == 0);
-          if (c == last_mine) {                      // last TMEM read of this tile (for this team) has landed
+          if (cc == last_mine) {                     // last TMEM read of this item (for this team) has landed
             ptx::tc_fence_before();
             ptx::mbar_arrive(tmem_empty(as));
           }
@@ -758,14 +799,14 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           if (tt == 0) ptx::tma_store_wait_read();
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           ICP_STAMP(a.dbg, 8, lt * 4 + c, et == 0);
-  #pragma unroll
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (j < cp) {
               const int col = col0 + 16 * j;
               uint32_t pk[8];
               convert16(&v[16 * j], pk, col >= a.relu_lo && col < a.relu_hi, a.fmt);
               if (wide) {
-  #pragma unroll
+#pragma unroll
                 for (int q = 0; q < 2; ++q) {
                   const uint32_t dst = my_stage + static_cast<uint32_t>(row) * 128u +
                                        (static_cast<uint32_t>((2 * j + q) ^ (row & 7)) << 4);
@@ -785,20 +826,20 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (tt == 0) {
             if (wide) {
-              if (col0 < a.n_split) ptx::tma_store_2d(&tm_o64, my_stage, a.coff + col0, m0);
-              else ptx::tma_store_2d(&tm_o64_2, my_stage, a.coff2 + col0 - a.n_split, m0);
+              if (col0 < a.n_split) ptx::tma_store_2d(&tm_o64, my_stage, a.coff + col0, ms);
+              else ptx::tma_store_2d(&tm_o64_2, my_stage, a.coff2 + col0 - a.n_split, ms);
             } else {
               for (int j = 0; j < cp; ++j) {
                 const int col = col0 + 16 * j;
-                if (col < a.n_split) ptx::tma_store_2d(&tm_o, my_stage + j * 4096u, a.coff + col, m0);
-                else ptx::tma_store_2d(&tm_o2, my_stage + j * 4096u, a.coff2 + col - a.n_split, m0);
+                if (col < a.n_split) ptx::tma_store_2d(&tm_o, my_stage + j * 4096u, a.coff + col, ms);
+                else ptx::tma_store_2d(&tm_o2, my_stage + j * 4096u, a.coff2 + col - a.n_split, ms);
               }
             }
             ptx::tma_store_commit();
             ICP_STAMP(a.dbg, 9, lt * 4 + c, true);
           }
         }
-        gchunk += static_cast<uint32_t>(nchunks);
+        gchunk += static_cast<uint32_t>(tchunks);
         ICP_STAMP(a.dbg, 5, lt, et == 0);
       }
       if (tt == 0) ptx::tma_store_wait_all();      // smem must outlive the last store's read

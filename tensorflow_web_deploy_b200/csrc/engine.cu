@@ -282,6 +282,8 @@ struct ConvLayer {
   bool persistent = true;  // conv_igemm_persistent_kernel (one CTA per SM walks the tiles)
   bool halo = false;       // conv_halo_kernel instead of conv_igemm_kernel
   HaloArgs hargs{};
+  int dual_stages = 0;     // > 0: a dual-tile configuration exists (two M tiles per item share the weight tile)
+  size_t dual_smem = 0;
   const uint16_t* d_w = nullptr;      // im2col layers: packed K-major weights [cout][taps * cblocks * ck] and
   const uint16_t* d_bias16 = nullptr; //   the [cout][16] (hi, lo) shift matrix (pool_conv.cuh reads them directly)
   bool pair = false;       // conv_pair_kernel (CTA pairs, resident weights); `alt` serves batches below pair_min_batch
@@ -836,6 +838,19 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   a.coff2 = out2_coff;
   a.n_split = out2 ? n_split : (1 << 30);
   L.smem = conv_smem_bytes(stages, n_tile, rb, persistent, persistent ? epi_teams : 1);
+  a.dual = 0;
+  // Dual-tile items (conv_igemm.cuh): two consecutive M tiles share every weight tile — the weight bytes, the larger half of
+  // what the tap-heavy 17x17 layers pull through L2->SM, halve — at the price of the TMEM double buffer (the epilogue of an
+  // item no longer overlaps the next item's MMAs), so it is used only for launches with few tiles per SM (launch_conv).
+  if (persistent && pow2_cols(n_tile) <= 256) {
+    const size_t dstage = (static_cast<size_t>(2 * kBM + n_tile) * rb + 1023) & ~size_t(1023);
+    int ds = static_cast<int>((204 * 1024 - kOutStageBytes) / dstage);
+    if (ds > kMaxStages) ds = kMaxStages;
+    if (ds >= 2) {
+      L.dual_stages = ds;
+      L.dual_smem = 1024 + static_cast<size_t>(ds) * dstage + 2 * kOutStageBytes + kOnesBytes + 256 + 1024;
+    }
+  }
   {
     const uint64_t out_rows = static_cast<uint64_t>(max_n) * oh * ow;
     L.tm_o = make_tm_out(out.p, out_rows, out.c, fmt);
@@ -885,6 +900,23 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
       launch_k(conv_igemm_persistent_kernel<true>, 2 * (items < max_clusters ? items : max_clusters), kPersistThreads, L.smem,
                st, pdl, 2, L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2,
                L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
+      return;
+    }
+    // dual-tile items when the launch has between ICP_DUAL_MIN and ICP_DUAL_MAX tiles per SM (default 1.5 .. 3: the 17x17 stage
+    // at batch 128) and the layer has a real filter footprint; ICP_DUAL=0 disables
+    static const bool dual_on = getenv("ICP_DUAL") ? atoi(getenv("ICP_DUAL")) != 0 : false;
+    static const double dual_min = getenv("ICP_DUAL_MIN") ? atof(getenv("ICP_DUAL_MIN")) : 1.5;
+    static const double dual_max = getenv("ICP_DUAL_MAX") ? atof(getenv("ICP_DUAL_MAX")) : 3.0;
+    static const int dual_taps = getenv("ICP_DUAL_MIN_TAPS") ? atoi(getenv("ICP_DUAL_MIN_TAPS")) : 2;
+    const double per_sm = static_cast<double>(m_tiles) * L.n_tiles / g_num_sms;
+    if (dual_on && L.dual_stages > 0 && a.taps >= dual_taps && per_sm >= dual_min && per_sm <= dual_max) {
+      a.dual = 1;
+      a.epi_teams = 2;
+      a.stages = L.dual_stages;
+      const int items = ((m_tiles + 1) / 2) * L.n_tiles;
+      launch_k(conv_igemm_persistent_kernel<false>, items < g_num_sms ? items : g_num_sms, kPersistThreads, L.dual_smem, st, pdl, 1,
+               L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64,
+               L.tm_o64_2, a, m_tiles, L.n_tiles);
       return;
     }
     const int total = m_tiles * L.n_tiles;

@@ -203,3 +203,22 @@ def test_worker_side_decode_hands_over_pixels(tmp_path):
     assert cli.classify_image(b"definitely not a jpeg") is None and owner.stats["requests"] == 6
     cli.close()
     owner.stop()
+
+
+def test_connections_are_pooled_not_per_thread(tmp_path):
+    """A threaded WSGI server runs every request on a fresh thread: the client must reuse its connections (one shared-memory
+    segment + socket each), growing the pool only to the number of requests in flight."""
+    eng = FakeEngine()
+    owner = B.GpuOwner(eng, str(tmp_path / "o.sock"), max_batch=8, window_ms=1.0).start()
+    cli = B.BatcherClient([owner.path], LABELS, decode="owner")
+    for i in range(40):                                       # 40 sequential requests, each on its own thread
+        t = threading.Thread(target=lambda: cli.classify_image(b"q" * 64))
+        t.start()
+        t.join()
+    assert len(cli._all) == 1
+    ts = [threading.Thread(target=lambda: cli.classify_image(b"r" * 65)) for _ in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert 1 <= len(cli._all) <= 6 and owner.stats["requests"] == 46
+    cli.close()
+    owner.stop()

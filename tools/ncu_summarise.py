@@ -3,6 +3,8 @@
 
   launches <launches.csv> <out.csv>          per-kernel-name count / total / mean gpu__time_duration (one forward)
   traffic  <conv_traffic.csv> <out.json>     DRAM and L2->SM bytes summed over the conv launches of one forward
+  kernels  <kernels.csv> <out.csv>           ONE ROW PER KERNEL of the last forward: launches, time, DRAM GB/s and % of
+                                             peak, tensor-pipe % (time-weighted), L2->SM bytes, LTS / SM throughput %
 """
 import csv
 import json
@@ -76,5 +78,42 @@ def traffic(src, dst):
     print(json.dumps(d, indent=1))
 
 
+def kernels(src, dst):
+    rs, units = rows(src)
+    T, DR, DW = "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
+    DP = "dram__throughput.avg.pct_of_peak_sustained_elapsed"
+    TP = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
+    XB = "l1tex__m_xbar2l1tex_read_bytes.sum"
+    LT = "lts__throughput.avg.pct_of_peak_sustained_elapsed"
+    SM = "sm__throughput.avg.pct_of_peak_sustained_elapsed"
+    agg = {}
+    for r in rs:
+        k = r["Kernel Name"].split("(")[0].replace("void ", "")
+        a = agg.setdefault(k, {"n": 0, "us": 0.0, "dram": 0.0, "xbar": 0.0, "w": {DP: 0.0, TP: 0.0, LT: 0.0, SM: 0.0}})
+        t = to_us(r[T], units[T])
+        a["n"] += 1
+        a["us"] += t
+        a["dram"] += to_bytes(r[DR], units[DR]) + to_bytes(r[DW], units[DW])
+        if XB in r:
+            a["xbar"] += to_bytes(r[XB], units[XB])
+        for m in a["w"]:
+            if m in r:
+                a["w"][m] += num(r[m]) * t          # time-weighted mean over the kernel's launches
+    total = sum(a["us"] for a in agg.values())
+    with open(dst, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "launches", "total_us", "share", "dram_GB", "dram_GBps", "dram_pct_of_peak", "tensor_pipe_pct_active",
+                    "l2_to_sm_GB", "l2_to_sm_TBps", "lts_throughput_pct", "sm_throughput_pct"])
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+            t = a["us"]
+            w.writerow([k, a["n"], "%.1f" % t, "%.4f" % (t / total), "%.3f" % (a["dram"] / 1e9), "%.0f" % (a["dram"] / t / 1e3),
+                        "%.1f" % (a["w"][DP] / t), "%.1f" % (a["w"][TP] / t), "%.3f" % (a["xbar"] / 1e9),
+                        "%.2f" % (a["xbar"] / t / 1e6), "%.1f" % (a["w"][LT] / t), "%.1f" % (a["w"][SM] / t)])
+        w.writerow(["TOTAL", sum(a["n"] for a in agg.values()), "%.1f" % total, "1.0",
+                    "%.3f" % (sum(a["dram"] for a in agg.values()) / 1e9), "", "", "",
+                    "%.3f" % (sum(a["xbar"] for a in agg.values()) / 1e9), "", "", ""])
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "traffic": traffic, "kernels": kernels}[sys.argv[1]](sys.argv[2], sys.argv[3])
