@@ -66,6 +66,7 @@ conv0_tc_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_co
   const int lane = threadIdx.x & 31;
   const int total = N * OH * OW;
   const int tiles = (total + kBM - 1) / kBM;
+  const TIn* in_end = in + static_cast<size_t>(N) * H * W * 3;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kConv0Stages; ++s) {
@@ -104,42 +105,150 @@ conv0_tc_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_co
     const int row = threadIdx.x & 127;
     const int sw = (row >> 1) & 3;
     uint32_t ph = 0;
-    for (int t0 = blockIdx.x + 2 * grp * gridDim.x; t0 < tiles; t0 += 8 * gridDim.x, ph ^= 1u) {
-      uint32_t q[2][16];                          // per tile: 32 x 16-bit, k = 0..26 inputs, 27..31 zero
+    const int step = 8 * static_cast<int>(gridDim.x);
+    auto publish = [&](int u, const uint32_t (&q)[16]) {
+      const int s = 2 * grp + u;
+      ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+      uint8_t* arow = gbase + s * kABytes0 + row * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(arow + ((c ^ sw) << 4)) = make_uint4(q[4 * c], q[4 * c + 1], q[4 * c + 2], q[4 * c + 3]);
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(full_bar(s));
+    };
+    if constexpr (sizeof(TIn) == 1) {
+      // uint8 input.  A run of 9 bytes at any address lies inside three ALIGNED 32-bit words; two funnel shifts bring it to
+      // byte 0: 9 word loads per pixel instead of 27 byte loads.  (Requesting the NEXT pair of tiles' words before converting
+      // the current pair — software pipelining — was MEASURED slower, 85.6 vs 80.5 us: the registers it holds spill.)
+      int t0 = blockIdx.x + 2 * grp * static_cast<int>(gridDim.x);
+      int pn[2], py[2], px[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
+        const long long m = static_cast<long long>(t0 + u * static_cast<int>(gridDim.x)) * kBM + row;
+        px[u] = static_cast<int>(m % OW);
+        py[u] = static_cast<int>((m / OW) % OH);
+        pn[u] = static_cast<int>(m / (static_cast<long long>(OW) * OH));
+      }
+      const long long delta = static_cast<long long>(step) * kBM;       // pixels between a slot's consecutive tiles
+      const int dx = static_cast<int>(delta % OW), dy = static_cast<int>((delta / OW) % OH);
+      const int dn = static_cast<int>(delta / (static_cast<long long>(OW) * OH));
+      auto request = [&](int tq, uint32_t (&w)[2][9], uint32_t (&sh)[2]) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) q[u][i] = 0u;
-        const int m = (t0 + u * static_cast<int>(gridDim.x)) * kBM + row;
-        if (m < total) {
-          const int ox = m % OW;
-          const int r2 = m / OW;
-          const int oy = r2 % OH;
-          const int n = r2 / OH;
-          const TIn* ip = in + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
-          uint16_t h[28];
+        for (int u = 0; u < 2; ++u) {
+          sh[u] = 0xFFFFFFFFu;                                    // no pixel: zero row
+          const int n = pn[u], oy = py[u], ox = px[u];            // this thread's pixel of tile tq + u * gridDim.x
+          px[u] += dx;                                            // ... and of the same slot one iteration later (no divisions)
+          if (px[u] >= OW) { px[u] -= OW; ++py[u]; }
+          py[u] += dy;
+          if (py[u] >= OH) { py[u] -= OH; ++pn[u]; }
+          pn[u] += dn;
+          if (tq + u * static_cast<int>(gridDim.x) < tiles && n < N) {
+            const uint8_t* a = reinterpret_cast<const uint8_t*>(in) + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
+            uint32_t shs = 0;
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r, a += static_cast<size_t>(W) * 3) {
+              const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+              const uint32_t* wp = reinterpret_cast<const uint32_t*>(ai & ~uintptr_t(3));
+              if (reinterpret_cast<const uint8_t*>(wp) >= reinterpret_cast<const uint8_t*>(in) &&
+                  reinterpret_cast<const uint8_t*>(wp + 3) <= reinterpret_cast<const uint8_t*>(in_end)) {
+                w[u][3 * r] = __ldg(wp);
+                w[u][3 * r + 1] = __ldg(wp + 1);
+                w[u][3 * r + 2] = __ldg(wp + 2);
+                shs |= static_cast<uint32_t>(ai & 3u) << (8 * r + 3);        // shift in bits, one byte of `sh` per row
+              } else {                                                         // first / last bytes of the buffer: byte loads
+                uint32_t b[9];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) h[r * 9 + j] = conv0_tc_cvt<TIn>(__ldg(ip + static_cast<size_t>(r) * W * 3 + j), fmt);
-          h[27] = 0;
+                for (int j = 0; j < 9; ++j) b[j] = __ldg(a + j);
+                w[u][3 * r] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+                w[u][3 * r + 1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+                w[u][3 * r + 2] = b[8];
+              }
+            }
+            sh[u] = shs;
+          }
+        }
+      };
+      // bytes -> 16-bit without the conversion unit (I2F + F2F run at a quarter of the ALU rate; 54 of them per pixel were
+      // ~65k of the kernel's ~150k cycles per SM): fp16 0x6400|b IS 1024 + b, minus 1024 exactly b (HSUB2, two values per
+      // instruction); bf16: fp32 0x4B000000|b is 2^23 + b, minus 2^23 exactly b, whose upper 16 bits are the bf16 (b < 256).
+      auto convert = [&](const uint32_t (&w)[9], uint32_t shs, uint32_t (&q)[16]) {
+        uint32_t by[28];
 #pragma unroll
-          for (int i = 0; i < 14; ++i) q[u][i] = static_cast<uint32_t>(h[2 * i]) | (static_cast<uint32_t>(h[2 * i + 1]) << 16);
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t sb = (shs >> (8 * r)) & 0xFFu;
+          const uint32_t v0 = __funnelshift_r(w[3 * r], w[3 * r + 1], sb), v1 = __funnelshift_r(w[3 * r + 1], w[3 * r + 2], sb);
+          const uint32_t v2 = w[3 * r + 2] >> sb;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            by[r * 9 + j] = (v0 >> (8 * j)) & 0xFFu;
+            by[r * 9 + 4 + j] = (v1 >> (8 * j)) & 0xFFu;
+          }
+          by[r * 9 + 8] = v2 & 0xFFu;
+        }
+        by[27] = 0u;
+        if (fmt == 0) {
+          const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
+#pragma unroll
+          for (int i = 0; i < 14; ++i) {
+            const uint32_t two = 0x64006400u | by[2 * i] | (by[2 * i + 1] << 16);
+            const __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&two), k1024);
+            q[i] = *reinterpret_cast<const uint32_t*>(&d);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 14; ++i) {
+            const float f0 = __uint_as_float(0x4B000000u | by[2 * i]) - 8388608.f;
+            const float f1 = __uint_as_float(0x4B000000u | by[2 * i + 1]) - 8388608.f;
+            q[i] = (__float_as_uint(f0) >> 16) | (__float_as_uint(f1) & 0xFFFF0000u);
+          }
+        }
+        q[14] = 0u;
+        q[15] = 0u;
+      };
+      uint32_t wc[2][9], sc[2];
+      for (; t0 < tiles; t0 += step, ph ^= 1u) {
+        request(t0, wc, sc);                       // both tiles' 18 word loads in flight before the first conversion
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (t0 + u * static_cast<int>(gridDim.x) < tiles) {
+            uint32_t q[16];
+            if (sc[u] == 0xFFFFFFFFu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) q[i] = 0u;
+            } else {
+              convert(wc[u], sc[u], q);
+            }
+            publish(u, q);
+          }
         }
       }
+    } else {
+      for (int t0 = blockIdx.x + 2 * grp * gridDim.x; t0 < tiles; t0 += step, ph ^= 1u) {
+        uint32_t q[2][16];                          // per tile: 32 x 16-bit, k = 0..26 inputs, 27..31 zero
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (t0 + u * static_cast<int>(gridDim.x) < tiles) {
-          const int s = 2 * grp + u;
-          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-          uint8_t* arow = gbase + s * kABytes0 + row * 64;
+        for (int u = 0; u < 2; ++u) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(arow + ((c ^ sw) << 4)) =
-                make_uint4(q[u][4 * c], q[u][4 * c + 1], q[u][4 * c + 2], q[u][4 * c + 3]);
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(full_bar(s));
+          for (int i = 0; i < 16; ++i) q[u][i] = 0u;
+          const int m = (t0 + u * static_cast<int>(gridDim.x)) * kBM + row;
+          if (m < total) {
+            const int ox = m % OW;
+            const int r2 = m / OW;
+            const int oy = r2 % OH;
+            const int n = r2 / OH;
+            const TIn* ip = in + ((static_cast<size_t>(n) * H + oy * 2) * W + ox * 2) * 3;
+            uint16_t h[28];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int j = 0; j < 9; ++j) h[r * 9 + j] = conv0_tc_cvt<TIn>(__ldg(ip + static_cast<size_t>(r) * W * 3 + j), fmt);
+            h[27] = 0;
+#pragma unroll
+            for (int i = 0; i < 14; ++i) q[u][i] = static_cast<uint32_t>(h[2 * i]) | (static_cast<uint32_t>(h[2 * i + 1]) << 16);
+          }
         }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (t0 + u * static_cast<int>(gridDim.x) < tiles) publish(u, q[u]);
       }
     }
   } else if (warp == 16) {
@@ -166,6 +275,7 @@ conv0_tc_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_co
     }
   } else {
     // ---------------- epilogue: + shift, ReLU, 64 contiguous bytes per pixel ----------------
+    // (a second epilogue team — 8 warps, alternate tiles — was MEASURED: 0.098 -> 0.105 ms; this chain is not the bound)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint32_t lt = 0;

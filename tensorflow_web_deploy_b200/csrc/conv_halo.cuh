@@ -62,16 +62,27 @@ struct HaloArgs {
   int ldo, coff;
   int epi_direct;       // 1: epilogue threads store their 32 columns straight from registers (no staging, no barriers)
   long long* dbg;       // optional timeline buffer (CTA 0 only), same rows as the persistent kernel (tools/timeline.py)
+  // strip = nbox boxes of box_rows rows (+ one of rem_rows through tm_a_rem): several boxes in flight per strip
+  int box_rows, nbox, rem_rows;
+  // kCp (strips copied by cp.async instead of TMA): the input tensor itself
+  const uint16_t* in;   // first channel of this layer's input slice
+  int ih, iw, ldi;      // input height, width, channels per pixel of the buffer (elements)
 };
 
 // kDirect: the epilogue variant is a compile-time choice — carrying both in one kernel cost the direct path 20 %
 // (conv1 0.120 -> 0.147 ms when a third variant was added experimentally).
 // kStem: the configuration of the two stem layers that use this kernel by default — weights resident, per-image bands,
 // no transposed store — as compile-time constants (the streamed / tall / transposed paths are the opt-in ones).
-template <bool kDirect, bool kStem>
+// kCp (stem only): warps 0 and 6 copy the strips with 16-byte cp.async (zero fill outside the image) instead of one TMA box.
+// MEASURED: a TMA box of 64-byte rows lands ~one row per 5 cycles per SM, and a band of 4 sub-tiles needs a 7-row strip of a
+// 149-wide map = 1043 rows = ~5.2k cycles against ~3.9k of MMA issue — the strip loads, not HBM (2.7 of 6.5 TB/s) or the tensor
+// pipe, bounded conv1 / conv2.  The LSU path has no per-row cost: 64 threads x 16 B per instruction.
+// RESULT: slower (conv1 0.135 -> 0.215 ms, conv2 0.145 -> 0.231 ms): two warps cannot issue the copies fast enough; kept
+// opt-in (ICP_HALO_CP=1) as the measured negative.
+template <bool kDirect, bool kStem, bool kCp = false>
 __global__ void __launch_bounds__(kHaloThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_bias, const HaloArgs a) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_rem,
+                 const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_bias, const HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -113,10 +124,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
+    ptx::prefetch_tmap(&tm_a_rem);
     ptx::prefetch_tmap(&tm_b);
     ptx::prefetch_tmap(&tm_bias);
     for (int i = 0; i < a.nstrips; ++i) {
-      ptx::mbar_init(strip_full(i), 1);
+      ptx::mbar_init(strip_full(i), kCp ? 64 : 1);
       ptx::mbar_init(strip_empty(i), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -148,9 +160,72 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   // Every role loop runs warp-converged and hands the uniform-datapath instructions (TMA, MMA, commit) to one
   // elected lane: under `if (lane == 0)` the compiler wraps each of them in an ELECT/branch loop, which cost this
   // kernel ~160 cycles per MMA (timeline of conv1: 72 MMAs in 11.6k cycles) against ~32 of tensor-pipe time.
-  if (warp == 0) {
+  if (kCp && (warp == 0 || warp == 6)) {
+    // ---------------- strip copiers (cp.async) ----------------
+    if (warp == 6) {
+      if (ptx::elect_one()) {
+        const int n_row = (static_cast<int>(blockIdx.x) % a.n_tiles) * a.n_tile;
+        ptx::mbar_expect_tx(w_full, static_cast<uint32_t>(a.chunks * taps) * tap_bytes + static_cast<uint32_t>(a.n_tile) * 32u);
+        ptx::tma_load_2d(bias_base, &tm_bias, w_full, 0, n_row);
+        for (int i = 0; i < a.chunks * taps; ++i) ptx::tma_load_2d(wbase + i * tap_bytes, &tm_b, w_full, i * ck, n_row);
+      }
+      __syncwarp();
+    }
+    // 64 threads; thread t owns 16-byte chunk j = t % cpr of pixels pl + ppi * k (k = 0, 1, ...): ppi = 64 / cpr is a multiple
+    // of the swizzle period in pixels (8 for both row sizes), so the swizzled chunk slot is a per-thread constant and the
+    // destination advances by exactly 1024 bytes per step.
+    const int lt = (warp == 0 ? 0 : 32) + lane;
+    const int cpr = a.row_bytes >> 4;
+    const int ppi = 64 / cpr;
+    const int j = lt % cpr, pl = lt / cpr;
+    const int sw = (a.row_bytes == 64) ? ((pl >> 1) & 3) : (pl & 7);
+    const uint32_t dst_off = static_cast<uint32_t>(pl) * rb + (static_cast<uint32_t>(j ^ sw) << 4);
+    const int npix = a.strip_rows * a.wp;
+    const int nit = (npix + ppi - 1) / ppi;
+    const size_t pix_bytes = static_cast<size_t>(a.ldi) * 2;
+    uint32_t s = 0, ph = 0;
+    int prev = -1;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int band = item / a.n_tiles;
+      const int img = band / bands_per_image;
+      const int p0 = (band - img * bands_per_image) * kBM * a.T;
+      const int gy0 = p0 / a.wp - a.pad_h;
+      for (int c = 0; c < a.chunks; ++c) {
+        const char* src0 = reinterpret_cast<const char*>(a.in) + static_cast<size_t>(img) * a.ih * a.iw * pix_bytes +
+                           static_cast<size_t>(c) * rb + j * 16;
+        ptx::mbar_wait(strip_empty(s), ph ^ 1u);
+        uint32_t dst = strip0 + s * a.strip_bytes + dst_off;
+        int row = 0, col = pl;
+#pragma unroll 4
+        for (int k = 0; k < nit; ++k) {
+          const int gy = gy0 + row, gx = col - a.pad_w;
+          const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(a.ih) &&
+                          static_cast<unsigned>(gx) < static_cast<unsigned>(a.iw) && row < a.strip_rows;
+          const char* src = ok ? src0 + (static_cast<size_t>(gy) * a.iw + gx) * pix_bytes : src0;
+          ptx::cp_async16_zfill(dst, src, ok ? 16u : 0u);
+          dst += 1024u;
+          col += ppi;
+          if (col >= a.wp) { col -= a.wp; ++row; }
+        }
+        ptx::cp_async_commit();
+        if (prev >= 0) {                       // the strip issued one step earlier has landed: publish it to the async proxy
+          ptx::cp_async_wait_group<1>();
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(strip_full(prev));
+        }
+        prev = static_cast<int>(s);
+        if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
+      }
+    }
+    if (prev >= 0) {
+      ptx::cp_async_wait_group<0>();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(strip_full(prev));
+    }
+  } else if (warp == 0) {
     // ---------------- strip producer ----------------
     const uint32_t strip_tx = static_cast<uint32_t>(a.strip_rows) * a.wp * rb;
+    const uint32_t box_bytes = static_cast<uint32_t>(a.box_rows) * a.wp * rb;
     uint32_t s = 0, ph = 0;                // ring position kept incrementally: no division in the loops
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -163,8 +238,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         ICP_STAMP(a.dbg, 0, it, lane == 0);
         ++it;
         if (ptx::elect_one()) {
+          // MEASURED (timeline of conv1 / conv2, one 7-row box of 149 x 64 B rows): 7050 cycles from issue to landing =
+          // one row per 6.8 cycles = ~9 B/cycle — one box keeps too few requests in flight; split, the boxes overlap.
           ptx::mbar_expect_tx(strip_full(s), strip_tx);
-          ptx::tma_load_4d(strip0 + s * a.strip_bytes, &tm_a, strip_full(s), c * ck, -a.pad_w, h_first - a.pad_h, img);
+          const uint32_t dst = strip0 + s * a.strip_bytes;
+          int h = h_first - a.pad_h;
+          for (int b = 0; b < a.nbox; ++b, h += a.box_rows)
+            ptx::tma_load_4d(dst + static_cast<uint32_t>(b) * box_bytes, &tm_a, strip_full(s), c * ck, -a.pad_w, h, img);
+          if (a.rem_rows) ptx::tma_load_4d(dst + static_cast<uint32_t>(a.nbox) * box_bytes, &tm_a_rem, strip_full(s), c * ck, -a.pad_w, h, img);
         }
         __syncwarp();
         if (++s == static_cast<uint32_t>(a.nstrips)) { s = 0; ph ^= 1u; }
@@ -258,6 +339,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (ptx::elect_one()) {
             uint32_t b_units = (wbase >> 4) + static_cast<uint32_t>(c * taps) * tap_units;
             const int ks = (c == a.chunks - 1) ? a.tail_ksteps : ksteps;
+            if (ks == 2 && ksteps == 2 && nsub == 4) {
+              // the stem layers' full band (64-byte rows, four sub-tiles): eight MMAs per tap in straight-line code.
+              // MEASURED (timeline, conv1 / conv2): 69 cycles per MMA through the generic loops below against the ~50 the
+              // issuing thread manages without a loop branch between MMAs.
+              const uint32_t nt = static_cast<uint32_t>(a.n_tile);
+              for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
+                const uint32_t au = a_units0 + tap_off[tap];
+                const uint64_t db0 = desc_hi | b_units, db1 = desc_hi | (b_units + 2u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  ptx::umma_f16(tacc0 + j * nt, desc_hi | (au + j * sub_units), db0, idesc, 1u);
+                  ptx::umma_f16(tacc0 + j * nt, desc_hi | (au + j * sub_units + 2u), db1, idesc, 1u);
+                }
+              }
+            } else
             for (int tap = 0; tap < taps; ++tap, b_units += tap_units) {
               uint32_t au = a_units0 + tap_off[tap];
               uint32_t tacc = tacc0;
@@ -461,9 +557,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
-inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes, bool direct = false) {
+inline size_t halo_smem_bytes(int strip_bytes, int nstrips, int w_bytes, bool direct = false, int n_tile = 256) {
+  // alignment slack, strips, weights (resident or ring), barriers + per-tap offsets + row->pixel tables, 2 x epilogue staging
+  // (staged variant only), ones tile, shift tile of the resident-weights bias MMA ([n_tile x 32 B])
   return 1024 + static_cast<size_t>(nstrips) * strip_bytes + ((static_cast<size_t>(w_bytes) + 1023) & ~size_t(1023)) + 2048 +
-         (direct ? 0 : 2 * 16384) + kOnesBytes + 8192;   // barriers + per-tap offsets + row->pixel tables, 2 x epilogue staging, ones tile, shift tile
+         (direct ? 0 : 2 * 16384) + kOnesBytes + ((static_cast<size_t>(n_tile) * 32 + 1023) & ~size_t(1023));
 }
 
 }  // namespace icp

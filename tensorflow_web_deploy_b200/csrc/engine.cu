@@ -281,6 +281,7 @@ struct ConvLayer {
   long long in_elems_per_image = 0;
   bool persistent = true;  // conv_igemm_persistent_kernel (one CTA per SM walks the tiles)
   bool halo = false;       // conv_halo_kernel instead of conv_igemm_kernel
+  bool halo_cp = false;    // ... with its strips copied by cp.async (stem configuration)
   HaloArgs hargs{};
   int dual_stages = 0;     // > 0: a dual-tile configuration exists (two M tiles per item share the weight tile)
   size_t dual_smem = 0;
@@ -641,6 +642,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       L.tm_bias = make_tm_2d_rows(d_bias, cout, 16, n_tile_r, 32, fmt);
       L.tm_b = make_tm_2d_rows(d_w, cout, static_cast<uint64_t>(chunks) * taps * ck, n_tile_r, rb, fmt);
       L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, best_rows, rb, fmt);
+      L.tm_a_tail = L.tm_a;
       L.halo = true;
       L.n_tiles = cout / n_tile_r;
       HaloArgs& h = L.hargs;
@@ -651,6 +653,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       h.n_tile = n_tile_r; h.n_tiles = L.n_tiles;
       h.acc_cols = T * n_tile_r; h.acc_sets = 2; h.tmem_cols = pow2_cols(2 * T * n_tile_r);
       h.w_resident = 1; h.w_bytes = res_bytes; h.b_stages = 1;
+      h.box_rows = best_rows; h.nbox = 1; h.rem_rows = 0;
       h.tail_ksteps = (cin - (chunks - 1) * ck + 15) / 16;
       h.fmt = fmt; h.relu = relu ? 1 : 0; h.epi_direct = 1;
       h.out = out.p; h.ldo = out.c; h.coff = out_coff;
@@ -669,11 +672,12 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     const int chunks = (cin + ck - 1) / ck;
     const int taps = kh * kw;
     // sub-tiles per band: double-buffered accumulators when they leave at least two sub-tiles, else one set
-    int T = 4, acc_sets = 2;
+    static const int halo_t = getenv("ICP_HALO_T") ? atoi(getenv("ICP_HALO_T")) : 4;    // longest band tried (sub-tiles)
+    int T = halo_t, acc_sets = 2;
     while (T > 1 && 2 * T * n_tile > 512) T >>= 1;
     if (2 * T * n_tile > 512 || T == 1) {
       acc_sets = 1;
-      T = 4;
+      T = halo_t;
       while (T > 1 && T * n_tile > 512) T >>= 1;
       if (2 * T * n_tile <= 512) acc_sets = 2;
     }
@@ -707,8 +711,18 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     }
     if (ok) {
       acc_sets = (2 * T * n_tile <= 512) ? 2 : 1;
-      while (nstrips < 4 && halo_smem_bytes(strip_bytes, nstrips + 1, w_bytes) <= 225 * 1024) ++nstrips;
-      const size_t smem = halo_smem_bytes(strip_bytes, nstrips, w_bytes);
+      // narrow tiles store straight from registers (conv1, 32 channels: 0.147 -> 0.117 ms); at 64 channels the 16-byte
+      // stores of one warp touch 32 lines per instruction and the staged copy-out is as fast (conv2 0.165 vs 0.169 ms)
+      const bool direct = getenv("ICP_HALO_DIRECT") ? atoi(getenv("ICP_HALO_DIRECT")) != 0 : n_tile <= 32;
+      // strips in the ring.  MEASURED (timeline, conv1): a strip lands ~5.4k cycles after its issue while the band's MMAs take
+      // ~3.3k, so with two strips the band period is their mean (4.4k) — but a THIRD strip (it fits once the direct epilogue's
+      // unused staging is not allocated) made conv1 slower, 0.1067 -> 0.1167 ms: these MMAs (N = 32, K = 16: 5 KB of operands
+      // for 16 cycles of tensor work) saturate the shared-memory port, and strip writes in flight during them take it away.
+      // Streamed-weight layers (opt-in) keep up to 4.  ICP_HALO_MAX_STRIPS overrides.
+      static const int max_strips_env = getenv("ICP_HALO_MAX_STRIPS") ? atoi(getenv("ICP_HALO_MAX_STRIPS")) : 0;
+      const int max_strips = max_strips_env ? max_strips_env : (resident ? 2 : 4);
+      while (nstrips < max_strips && halo_smem_bytes(strip_bytes, nstrips + 1, w_bytes, direct, n_tile) <= 226 * 1024) ++nstrips;
+      const size_t smem = halo_smem_bytes(strip_bytes, nstrips, w_bytes, direct, n_tile);
       std::vector<uint16_t> wp_host = pack_weights_halo(w_hwio, kh, kw, cin, cout, ck, fmt, scale);
       void* d_w = pool.alloc(wp_host.size() * 2);
       CK(cudaMemcpy(d_w, wp_host.data(), wp_host.size() * 2, cudaMemcpyHostToDevice));
@@ -719,12 +733,18 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       const uint64_t kp = static_cast<uint64_t>(chunks) * taps * ck;
       L.halo = true;
       L.tm_b = make_tm_2d_rows(d_w, cout, kp, n_tile, rb, fmt);
-      if (tall)   // rows of all images form one grid: dims {C, W, N*H, 1}
-        L.tm_a = make_tm_strip(in.p + in_coff, 1, max_n * in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
-      else
-        L.tm_a = make_tm_strip(in.p + in_coff, max_n, in.h, in.w, cin, in.c, wp, strip_rows, rb, fmt);
+      // boxes per strip: box_rows rows each such that every box starts on a 128-byte boundary of the strip (TMA destination
+      // alignment; the swizzle is a function of the absolute address, so the boxes tile the strip seamlessly)
+      static const int box_rows_env = getenv("ICP_HALO_BOX_ROWS") ? atoi(getenv("ICP_HALO_BOX_ROWS")) : 0;
+      int box_rows = strip_rows;
+      if (box_rows_env > 0 && box_rows_env < strip_rows && (static_cast<long long>(box_rows_env) * wp * rb) % 128 == 0) box_rows = box_rows_env;
+      const int nbox = strip_rows / box_rows, rem_rows = strip_rows - nbox * box_rows;
+      const int gn = tall ? 1 : max_n, gh = tall ? max_n * in.h : in.h;     // tall: rows of all images form one grid {C, W, N*H, 1}
+      L.tm_a = make_tm_strip(in.p + in_coff, gn, gh, in.w, cin, in.c, wp, box_rows, rb, fmt);
+      L.tm_a_tail = rem_rows ? make_tm_strip(in.p + in_coff, gn, gh, in.w, cin, in.c, wp, rem_rows, rb, fmt) : L.tm_a;
       HaloArgs& h = L.hargs;
       h.n_images = 0;
+      h.box_rows = box_rows; h.nbox = nbox; h.rem_rows = rem_rows;
       h.oh = oh; h.ow = ow; h.wp = wp; h.pad_h = pad_h; h.pad_w = pad_w; h.kh = kh; h.kw = kw;
       h.chunks = chunks; h.row_bytes = rb; h.T = T; h.strip_rows = strip_rows; h.strip_bytes = strip_bytes;
       h.nstrips = nstrips;
@@ -736,10 +756,14 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       h.w_resident = resident ? 1 : 0; h.w_bytes = w_bytes; h.b_stages = b_stages;
       h.tail_ksteps = rb / 32;                 // this configuration multiplies the zero-padded K slices of the last chunk too
       h.fmt = fmt; h.relu = relu ? 1 : 0;
-      // narrow tiles store straight from registers (conv1, 32 channels: 0.147 -> 0.117 ms); at 64 channels the 16-byte
-      // stores of one warp touch 32 lines per instruction and the staged copy-out is as fast (conv2 0.165 vs 0.169 ms)
-      h.epi_direct = getenv("ICP_HALO_DIRECT") ? atoi(getenv("ICP_HALO_DIRECT")) : (n_tile <= 32 ? 1 : 0);
-      h.out = out.p; h.ldo = out.c; h.coff = out_coff; 
+      h.epi_direct = direct ? 1 : 0;
+      h.out = out.p; h.ldo = out.c; h.coff = out_coff;
+      h.in = in.p + in_coff; h.ih = in.h; h.iw = in.w; h.ldi = in.c;
+      // strips by cp.async instead of TMA (conv_halo.cuh kCp): opt-in (ICP_HALO_CP=1).  MEASURED at batch 128 with the two
+      // spare warps as copiers: conv1 0.135 -> 0.215 ms, conv2 0.145 -> 0.231 ms — 64 threads cannot issue a 67 KB strip
+      // (65 copies each, ~150 cycles apiece including the index arithmetic) as fast as one TMA box lands it.
+      static const bool halo_cp = getenv("ICP_HALO_CP") ? atoi(getenv("ICP_HALO_CP")) != 0 : false;
+      L.halo_cp = halo_cp && resident && !tall && !transpose_out && cin % ck == 0 && (in_coff % 8) == 0 && (in.c % 8) == 0;
       L.smem = smem;
       return L;
     }
@@ -881,12 +905,17 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
     unsigned grid = static_cast<unsigned>(items < g_num_sms ? items : g_num_sms);
     if (h.w_resident && h.n_tiles > 1) grid = grid / h.n_tiles * h.n_tiles;       // static N tile per CTA: b % n_tiles
     const bool stem = h.w_resident && !h.tall && !h.transpose_out;
+    if (stem && L.halo_cp) {
+      if (h.epi_direct) launch_k(conv_halo_kernel<true, true, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_bias, h);
+      else launch_k(conv_halo_kernel<false, true, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_bias, h);
+      return;
+    }
     if (h.epi_direct) {
-      if (stem) launch_k(conv_halo_kernel<true, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
-      else launch_k(conv_halo_kernel<true, false>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
+      if (stem) launch_k(conv_halo_kernel<true, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_bias, h);
+      else launch_k(conv_halo_kernel<true, false>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_bias, h);
     } else {
-      if (stem) launch_k(conv_halo_kernel<false, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
-      else launch_k(conv_halo_kernel<false, false>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_b, L.tm_bias, h);
+      if (stem) launch_k(conv_halo_kernel<false, true>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_bias, h);
+      else launch_k(conv_halo_kernel<false, false>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_bias, h);
     }
     return;
   }
@@ -1747,6 +1776,8 @@ static void set_kernel_attrs(int device) {
   CK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_halo_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_halo_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(pool_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pool_conv_smem_bytes())));
   CK(cudaFuncSetAttribute(conv0_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,4 +1,5 @@
 cd /root/repo
+mkdir -p gpurun_out/r02
 timeout 900 python tools/http_bench.py --workers 8 --procs 8 --threads 4 --requests 6000 > gpurun_out/r02/http.log 2>&1; grep "^{" gpurun_out/r02/http.log | cut -c1-900
 timeout 900 python tools/http_bench.py --workers 8 --procs 8 --threads 8 --requests 6000 --max-batch 64 --window-ms 3 > gpurun_out/r02/http64.log 2>&1; grep "^{" gpurun_out/r02/http64.log | cut -c1-600
 timeout 900 python tools/http_bench.py --workers 8 --procs 8 --threads 4 --requests 3000 --decode owner > gpurun_out/r02/http_owner.log 2>&1; grep "^{" gpurun_out/r02/http_owner.log | cut -c1-400

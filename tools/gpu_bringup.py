@@ -224,14 +224,19 @@ def cmd_speed(args):
     x = np.random.default_rng(1).uniform(-1, 1, (n, 299, 299, 3)).astype(np.float32)
     eng = engine.Engine(path, C, max_batch=n, precision=args.precision, use_cuda_graph=args.graph)
     ms = []
+    if args.u8:      # the uint8 entry (what bench.py and the serving path use: normalisation folded into conv0)
+        x = np.random.default_rng(1).integers(0, 256, (n, 299, 299, 3), dtype=np.uint8)
     for i in range(args.iters + 3):
-        eng.forward(x)
+        if args.u8:
+            eng.forward_u8(x)
+        else:
+            eng.forward(x)
         if i >= 3:
             ms.append(eng.last_forward_ms)
     ms = np.array(ms)
     flops = 2 * 5711168096 * n
-    print("SPEED n=%d %s graph=%s: device ms median=%.3f min=%.3f -> %.0f img/s, %.1f TFLOP/s (%.1f%% of 1667)" % (
-        n, args.precision, args.graph, np.median(ms), ms.min(), n / (np.median(ms) * 1e-3),
+    print("SPEED n=%d %s graph=%s%s: device ms median=%.3f min=%.3f -> %.0f img/s, %.1f TFLOP/s (%.1f%% of 1667)" % (
+        n, args.precision, args.graph, " u8" if args.u8 else "", np.median(ms), ms.min(), n / (np.median(ms) * 1e-3),
         flops / (np.median(ms) * 1e-3) / 1e12, 100 * flops / (np.median(ms) * 1e-3) / 1667.1e12), flush=True)
     return 0
 
@@ -314,6 +319,7 @@ def main():
     p.add_argument("--fc-scale", type=float, default=4.0)
     p = sub.add_parser("speed"); p.add_argument("--precision", default="bf16"); p.add_argument("--n", type=int, default=128)
     p.add_argument("--iters", type=int, default=10); p.add_argument("--graph", action="store_true")
+    p.add_argument("--u8", action="store_true")
     p = sub.add_parser("profile"); p.add_argument("--precision", default="bf16"); p.add_argument("--n", type=int, default=128)
     p.add_argument("--reps", type=int, default=5)
     p = sub.add_parser("layer"); p.add_argument("--name", required=True); p.add_argument("--n", type=int, default=128)
