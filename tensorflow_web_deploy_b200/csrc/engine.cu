@@ -291,6 +291,7 @@ struct ConvLayer {
   PairArgs pargs{};
   int pair_min_batch = 0;
   std::shared_ptr<ConvLayer> alt;
+  std::shared_ptr<ConvLayer> narrow;   // small-batch twin: same weights, narrow N work items (make_conv)
 };
 
 static int g_num_sms = 148;
@@ -495,7 +496,10 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
                            const float* w_hwio, int kh, int kw, int cout, int stride, bool same, const float* scale,
                            const float* shift, bool relu, const Act& out, int out_coff, int fmt,
                            const float* floor = nullptr, const Act* out2 = nullptr, int out2_coff = 0,
-                           int n_split = 0, bool transpose_out = false, bool allow_pair = true) {
+                           int n_split = 0, bool transpose_out = false, bool allow_pair = true,
+                           const ConvLayer* narrow_of = nullptr, int narrow_n_tile = 0) {
+  // narrow_of: build the small-batch twin of that layer — same packed weights, output channels cut into narrow_n_tile-wide
+  // work items (see the end of this function)
   if (same && stride != 1) fail(ICP_E_INVALID, "%s: SAME padding is only supported with stride 1", name.c_str());
   if (cout % 16) fail(ICP_E_INVALID, "%s: cout=%d is not a multiple of 16", name.c_str(), cout);
   if (cin % 8 || in.c % 8 || in_coff % 8 || out.c % 8 || out_coff % 8)
@@ -520,7 +524,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     static const int pair_min_w = getenv("ICP_PAIR_MIN_W") ? atoi(getenv("ICP_PAIR_MIN_W")) : 30;
     static const int pair_max_w = getenv("ICP_PAIR_MAX_W") ? atoi(getenv("ICP_PAIR_MAX_W")) : 100;
     static const int pair_min_batch = getenv("ICP_PAIR_MIN_BATCH") ? atoi(getenv("ICP_PAIR_MIN_BATCH")) : 8;
-    if (pair_on && allow_pair && !out2 && !floor && !transpose_out && stride == 1 && kh * kw > 1 && ow >= pair_min_w &&
+    if (pair_on && allow_pair && !narrow_of && !out2 && !floor && !transpose_out && stride == 1 && kh * kw > 1 && ow >= pair_min_w &&
         ow <= pair_max_w &&
         make_pair_conv(L, pool, max_n, in, in_coff, cin, w_hwio, kh, kw, cout, pad_h, pad_w, oh, ow, scale, shift, relu, out,
                        out_coff, fmt)) {
@@ -545,14 +549,14 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     }
   const int ck = rb / 2;
   const int cb = (cin + ck - 1) / ck;
-  int n_tile = pick_n_tile(cout);
+  int n_tile = narrow_of ? narrow_n_tile : pick_n_tile(cout);
   L.n_tiles = cout / n_tile;
   // Experiment (ICP_UNEVEN_N=1): full 256-column tiles plus a narrower last one when that needs FEWER tiles than the
   // even split (640 = 256 + 256 + 128 instead of 4 x 160, 704 = 256 + 256 + 192 instead of 4 x 176).  MEASURED: no
   // gain (2.461 vs 2.461 ms/step; 17x17 1x1 768->704 0.0246 vs 0.0232 ms) — at 256 columns the K block is MMA-bound
   // and the ring is one stage shorter.
   static const bool no_uneven = getenv("ICP_UNEVEN_N") == nullptr;
-  if (!no_uneven && getenv("ICP_CONV_V1") == nullptr && kh * kw == 1 && (cout + 255) / 256 < L.n_tiles) {
+  if (!no_uneven && !narrow_of && getenv("ICP_CONV_V1") == nullptr && kh * kw == 1 && (cout + 255) / 256 < L.n_tiles) {
     n_tile = 256;
     L.n_tiles = (cout + 255) / 256;
   }
@@ -609,7 +613,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   static const bool halo_res = getenv("ICP_HALO_RES") ? atoi(getenv("ICP_HALO_RES")) != 0 : false;
   static const int res_min_w = getenv("ICP_HALO_RES_MIN_W") ? atoi(getenv("ICP_HALO_RES_MIN_W")) : 30;
   static const int res_max_w = getenv("ICP_HALO_RES_MAX_W") ? atoi(getenv("ICP_HALO_RES_MAX_W")) : 50;
-  if (halo_res && allow_pair && !no_halo && !out2 && !floor && !transpose_out && stride == 1 && kh * kw > 1 && cin % 16 == 0 &&
+  if (halo_res && allow_pair && !narrow_of && !no_halo && !out2 && !floor && !transpose_out && stride == 1 && kh * kw > 1 && cin % 16 == 0 &&
       ow >= res_min_w && ow <= res_max_w && in.w + 2 * pad_w <= 256) {
     const int rb = cin <= 32 ? 64 : 128, ck = rb / 2;
     const int wp = in.w + 2 * pad_w, chunks = (cin + ck - 1) / ck, taps = kh * kw;
@@ -665,7 +669,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
       return L;
     }
   }
-  if (!no_halo && !out2 && !floor && stride == 1 && kh * kw > 1 && in.w + 2 * pad_w <= 256 &&
+  if (!no_halo && !narrow_of && !out2 && !floor && stride == 1 && kh * kw > 1 && in.w + 2 * pad_w <= 256 &&
       (tall || ow >= halo_min_w) && (!transpose_out || (tall && oh == ow))) {
     const int rb = cin <= 32 ? 64 : 128, ck = rb / 2;
     const int wp = in.w + 2 * pad_w;
@@ -771,12 +775,18 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   if (transpose_out) fail(ICP_E_INVALID, "%s: transposed output needs the halo kernel in tall mode", name.c_str());
 
   // weights (BatchNorm scale folded in) and the shift tile of the bias MMA
-  std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, ck, fmt, scale);
-  void* d_w = pool.alloc(wp.size() * 2);
-  CK(cudaMemcpy(d_w, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
-  std::vector<uint16_t> bp = pack_bias(shift, cout, fmt);
-  void* d_bias = pool.alloc(bp.size() * 2);
-  CK(cudaMemcpy(d_bias, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice));
+  const void* d_w = narrow_of ? static_cast<const void*>(narrow_of->d_w) : nullptr;
+  const void* d_bias = narrow_of ? static_cast<const void*>(narrow_of->d_bias16) : nullptr;
+  if (!narrow_of) {
+    std::vector<uint16_t> wp = pack_weights(w_hwio, kh, kw, cin, cout, ck, fmt, scale);
+    void* dw = pool.alloc(wp.size() * 2);
+    CK(cudaMemcpy(dw, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    std::vector<uint16_t> bp = pack_bias(shift, cout, fmt);
+    void* db = pool.alloc(bp.size() * 2);
+    CK(cudaMemcpy(db, bp.data(), bp.size() * 2, cudaMemcpyHostToDevice));
+    d_w = dw;
+    d_bias = db;
+  }
   L.tm_bias = make_tm_2d_rows(d_bias, cout, 16, n_tile, 32, fmt);
   L.d_w = static_cast<const uint16_t*>(d_w);
   L.d_bias16 = static_cast<const uint16_t*>(d_bias);
@@ -882,6 +892,24 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
     L.tm_o64 = make_tm_out(out.p, out_rows, out.c, fmt, 64);
     L.tm_o64_2 = out2 ? make_tm_out(out2->p, out_rows, out2->c, fmt, 64) : L.tm_o64;
   }
+  // Small-batch twin.  At batch 1 a 17x17 layer is 3 M tiles and an 8x8 layer one: with 128..256-column work items a handful
+  // of CTAs each pull the layer's whole weight matrix (up to 1.5 MB) through one SM's ~47 B/cycle L2 port while 140 SMs idle —
+  // the K loop, not the launch, is then most of the layer's ~9 us.  The twin cuts the output channels into <= 64-column items
+  // (same packed weights, other tensor-map boxes): 2-4x the CTAs, each streaming 1/2-1/4 of the weights.  launch_conv picks
+  // it when the wide layer would occupy less than half the SMs.  ICP_NARROW_NTILE=0 disables, =N sets the item width.
+  // MEASURED (u8 in, fp16, CUDA graph + PDL, device ms per batch; wide / 16 / 32 / 64 columns):
+  //   n=1 0.452 / 0.374 / 0.370 / 0.371   n=2 0.482 / 0.414 / 0.383 / 0.379   n=4 0.502 / 0.536 / 0.448 / 0.412
+  //   n=8 0.551 / 0.657 / 0.531 / 0.484   n=16 0.643 / 0.974 / 0.741 / 0.646
+  static const int narrow_nt = getenv("ICP_NARROW_NTILE") ? atoi(getenv("ICP_NARROW_NTILE")) : 64;
+  if (!narrow_of && persistent && narrow_nt >= 16 && n_tile > narrow_nt) {
+    int nt = 0;
+    for (int c = narrow_nt / 16 * 16; c >= 16; c -= 16)
+      if (cout % c == 0) { nt = c; break; }
+    if (nt)
+      L.narrow = std::make_shared<ConvLayer>(make_conv(pool, name, max_n, in, in_coff, cin, w_hwio, kh, kw, cout, stride, same, scale,
+                                                       shift, relu, out, out_coff, fmt, floor, out2, out2_coff, n_split,
+                                                       transpose_out, false, &L, nt));
+  }
   return L;
 }
 
@@ -918,6 +946,10 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
       else launch_k(conv_halo_kernel<false, false>, grid, kHaloThreads, L.smem, st, pdl, 1, L.tm_a, L.tm_a_tail, L.tm_b, L.tm_bias, h);
     }
     return;
+  }
+  if (L.narrow) {
+    const int mt = (n * L.pix_per_image + kBM - 1) / kBM;
+    if (2 * mt * L.n_tiles <= g_num_sms) { launch_conv(*L.narrow, n, st, pdl); return; }
   }
   ConvArgs a = L.args;
   a.m_total = n * L.pix_per_image;

@@ -12,16 +12,24 @@ import sys
 
 
 def rows(path):
-    """ncu --csv --log-file output is long-form (one line per launch x metric): pivot it to one dict per launch."""
+    """One dict per launch from either ncu CSV shape: `--csv --log-file` (long form, one line per launch x metric) or
+    `ncu -i report.ncu-rep --page raw --csv` (wide form: a header line, a units line, one line per launch — what a
+    `--set full` capture exports)."""
     with open(path, newline="") as f:
         lines = [l for l in f if not l.startswith("==")]
-    r = list(csv.DictReader(lines))
-    out, units = {}, {}
-    for x in r:
-        d = out.setdefault(x["ID"], {"Kernel Name": x["Kernel Name"]})
-        d[x["Metric Name"]] = x["Metric Value"]
-        units[x["Metric Name"]] = x["Metric Unit"]
-    rs = [out[k] for k in sorted(out, key=int)]
+    head = next(csv.reader(lines[:1]))
+    if "Metric Name" not in head:                       # wide form
+        table = list(csv.reader(lines))
+        units = dict(zip(table[0], table[1]))
+        rs = [dict(zip(table[0], t)) for t in table[2:] if len(t) == len(table[0])]
+    else:
+        r = list(csv.DictReader(lines))
+        out, units = {}, {}
+        for x in r:
+            d = out.setdefault(x["ID"], {"Kernel Name": x["Kernel Name"]})
+            d[x["Metric Name"]] = x["Metric Value"]
+            units[x["Metric Name"]] = x["Metric Unit"]
+        rs = [out[k] for k in sorted(out, key=int)]
     # keep the LAST forward only: a forward starts at its conv0 launch and ends at the main head_kernel
     starts = [i for i, x in enumerate(rs) if "conv0" in x["Kernel Name"]]
     if starts:
@@ -61,10 +69,10 @@ def launches(src, dst):
 
 def traffic(src, dst):
     rs, units = rows(src)
-    rs = [r for r in rs if "conv0" not in r["Kernel Name"]]
+    rs = [r for r in rs if "conv0" not in r["Kernel Name"] and "conv" in r["Kernel Name"]]    # the tcgen05 conv family
     d = {
-        "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,... -k regex:conv_ (%s), "
-                  "batch 128 bf16, one forward = %d conv launches (conv0 excluded)" % (src, len(rs)),
+        "source": "ncu (%s), batch 128, one forward = %d conv launches (conv_igemm_persistent / conv_halo / pool_conv; "
+                  "conv0 excluded)" % (src, len(rs)),
         "conv_launches_per_step": len(rs),
         "sum_gpu_time_us": sum(to_us(r["gpu__time_duration.sum"], units["gpu__time_duration.sum"]) for r in rs),
         "dram_bytes_read": sum(to_bytes(r["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) for r in rs),
@@ -97,8 +105,11 @@ def kernels(src, dst):
         if XB in r:
             a["xbar"] += to_bytes(r[XB], units[XB])
         for m in a["w"]:
-            if m in r:
-                a["w"][m] += num(r[m]) * t          # time-weighted mean over the kernel's launches
+            v = r.get(m)
+            if v is None and m == DP:               # the full set names it gpu__dram_throughput
+                v = r.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+            if v is not None:
+                a["w"][m] += num(v) * t             # time-weighted mean over the kernel's launches
     total = sum(a["us"] for a in agg.values())
     with open(dst, "w", newline="") as f:
         w = csv.writer(f)
