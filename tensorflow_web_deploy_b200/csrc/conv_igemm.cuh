@@ -408,12 +408,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // Every tile's K blocks: block -1 is the bias block (only the [n_tile x 16] shift tile travels, into the stage's
 // W slot; the A producer just arrives), blocks 0..num_kb-1 the filter taps x channel blocks.
 // ---------------------------------------------------------------------------------------------------
-// kCluster: launched as 2-CTA clusters.  The two CTAs own the two M tiles of a pair (same N tile, same K blocks); each
-// loads HALF of every weight tile and multicasts it into both CTAs' shared memory, so the weight bytes crossing
+// kCS > 1: launched as clusters of kCS CTAs.  The CTAs own kCS consecutive M tiles of a group (same N tile, same K blocks);
+// each loads 1/kCS of every weight tile and multicasts it into all the CTAs' shared memory, so the weight bytes crossing
 // L2->SM — the larger half of the traffic of the tap-heavy layers, which are bound by exactly that (profiles/
-// r01_epilogue.md) — halve.  A stage is free only when BOTH CTAs' MMAs have released it (tcgen05.commit multicast onto
-// both empty barriers), because the peer writes into it.
-template <bool kCluster>
+// r01_epilogue.md) — shrink.  A stage is free only when ALL the CTAs' MMAs have released it (tcgen05.commit multicast onto
+// every CTA's empty barrier), because the peers write into it.  kCS = 2 (default where used) and 8 (opt-in, measured
+// slower: engine.cu make_conv) are instantiated.
+template <int kCS>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                              const __grid_constant__ CUtensorMap tm_a_tail, const __grid_constant__ CUtensorMap tm_b_tail,
@@ -422,6 +423,8 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
                              const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_o2,
                              const __grid_constant__ CUtensorMap tm_o64, const __grid_constant__ CUtensorMap tm_o64_2,
                              const ConvArgs a, const int m_tiles, const int n_tiles) {
+  constexpr bool kCluster = kCS > 1;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCS) - 1u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -450,12 +453,13 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   // work item t -> (M tile or, in a cluster, pair of M tiles; N tile).  tile_of(t) = this CTA's M tile.
   uint32_t crank = 0;
   if constexpr (kCluster) crank = ptx::cluster_ctarank();
-  const int total_tiles = ((kCluster || dual) ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const int grp = kCluster ? kCS : (dual ? 2 : 1);              // M tiles per work item (cluster: one per CTA)
+  const int total_tiles = ((m_tiles + grp - 1) / grp) * n_tiles;
   const int num_kb = a.taps * a.cblocks;
   const bool narrow_tail = a.tail_rb != a.row_bytes;
-  const int first = static_cast<int>(blockIdx.x) / (kCluster ? 2 : 1);
-  const int step = static_cast<int>(gridDim.x) / (kCluster ? 2 : 1);
-  auto tile_m0 = [&](int t) { return ((t / n_tiles) * ((kCluster || dual) ? 2 : 1) + static_cast<int>(crank)) * kBM; };
+  const int first = static_cast<int>(blockIdx.x) / kCS;
+  const int step = static_cast<int>(gridDim.x) / kCS;
+  auto tile_m0 = [&](int t) { return ((t / n_tiles) * grp + static_cast<int>(crank)) * kBM; };
 
   ptx::pdl_launch();
   if (warp == 0 && lane == 0) {
@@ -472,7 +476,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     ptx::prefetch_tmap(&tm_o64_2);
     for (int s = 0; s < a.stages; ++s) {
       ptx::mbar_init(full_bar(s), 2);          // arrivals per stage: the A producer and the W producer
-      ptx::mbar_init(empty_bar(s), kCluster ? 2 : 1);   // cluster: both CTAs' MMA issuers release a stage
+      ptx::mbar_init(empty_bar(s), kCS);   // cluster: every CTA's MMA issuer releases a stage
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tmem_full(i), 1);
@@ -602,11 +606,11 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
             const bool tail = narrow_tail && cb == cb_last;
             ptx::mbar_expect_tx(full_bar(s), tail ? b_tail_bytes : b_bytes);
             if constexpr (kCluster) {
-              // this CTA's half of the weight rows, delivered to both CTAs (each barrier receives both halves' bytes)
-              const uint32_t half_rows = static_cast<uint32_t>(a.n_tile) >> 1;
-              ptx::tma_load_2d_mcast(sb + crank * half_rows * (tail ? static_cast<uint32_t>(a.tail_rb) : rb),
+              // this CTA's share of the weight rows, delivered to every CTA (each barrier receives all shares' bytes)
+              const uint32_t part_rows = static_cast<uint32_t>(a.n_tile) / kCS;
+              ptx::tma_load_2d_mcast(sb + crank * part_rows * (tail ? static_cast<uint32_t>(a.tail_rb) : rb),
                                      tail ? &tm_b_tail_half : &tm_b_half, full_bar(s), kcol,
-                                     n_base + static_cast<int>(crank * half_rows), static_cast<uint16_t>(3));
+                                     n_base + static_cast<int>(crank * part_rows), kMask);
             } else {
               ptx::tma_load_2d(sb, tail ? &tm_b_tail : &tm_b, full_bar(s), kcol, n_base);
             }
@@ -639,7 +643,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
     uint32_t ph = 0;
     uint32_t su = base_units;                                              // stage start, 16-byte units
     auto commit_empty = [&](int s_) {
-      if constexpr (kCluster) ptx::umma_commit_mcast(empty_bar(s_), static_cast<uint16_t>(3));
+      if constexpr (kCluster) ptx::umma_commit_mcast(empty_bar(s_), kMask);
       else ptx::umma_commit(empty_bar(s_));
     };
     auto advance = [&]() {

@@ -269,6 +269,7 @@ struct ConvLayer {
   CUtensorMap tm_b_half, tm_b_tail_half;   // cluster mode: half of the weight tile's rows per box (multicast by each CTA)
   bool cluster = false;    // 2-CTA clusters sharing every weight tile by multicast (maps built; used for big launches)
   int cluster_min_tiles = 16;   // ... i.e. when m_tiles >= cluster_min_tiles * SMs
+  int cluster_size = 2;         // CTAs per cluster of that mode (2 or 8)
   CUtensorMap tm_bias;       // [cout][16] (hi, lo) halves of the BatchNorm shift: B operand of the bias MMA
   CUtensorMap tm_o, tm_o2;   // destination slices (persistent kernel's TMA-store epilogue): 16-column boxes
   CUtensorMap tm_o64, tm_o64_2;   // same, 64-column (128-byte, swizzled) boxes
@@ -826,8 +827,16 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   L.tm_b_half = L.tm_b;
   L.tm_b_tail_half = L.tm_b_tail;
   if (L.cluster) {
-    L.tm_b_half = make_tm_2d(d_w, cout, kp, kp, n_tile / 2, fmt, rb);
-    L.tm_b_tail_half = tail_rb != rb ? make_tm_2d(d_w, cout, kp, kp, n_tile / 2, fmt, tail_rb) : L.tm_b_half;
+    // ICP_CLUSTER_SIZE=8: clusters of 8 where every CTA's share of the weight tile is whole swizzle periods (8 rows).
+    // MEASURED (B200, batch 128): only 15 clusters of 8 are co-resident (120 of 148 SMs) and conv4 takes 0.228 ms against 0.194
+    // with pairs and 0.202 without clusters (K=1024 N=256 GEMM 0.304 / 0.278 / 0.287; tower 2.309 vs 2.271 ms) — time scaled
+    // with the SM count although the L2 reads of the weights fell 4x: what bounds these kernels is each SM's own ~45 B/cycle
+    // L2->SM port (148 of them = the ~6.3 kB/cycle "LTS cap"), and a multicast still delivers every byte to every SM.
+    static const int cs_env = getenv("ICP_CLUSTER_SIZE") ? atoi(getenv("ICP_CLUSTER_SIZE")) : 2;
+    L.cluster_size = (cs_env == 8 && n_tile % 64 == 0) ? 8 : 2;
+    const int part = n_tile / L.cluster_size;
+    L.tm_b_half = make_tm_2d(d_w, cout, kp, kp, part, fmt, rb);
+    L.tm_b_tail_half = tail_rb != rb ? make_tm_2d(d_w, cout, kp, kp, part, fmt, tail_rb) : L.tm_b_half;
   }
 
   ConvArgs& a = L.args;
@@ -913,6 +922,37 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   return L;
 }
 
+// Clusters of `cs` persistent CTAs (one per SM, `smem` dynamic bytes) the device can hold at once: GPCs whose SM count is
+// not a multiple of the cluster size strand SMs.  Cached per (device, cs, smem).
+static int max_active_clusters(int cs, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, size_t>, int> cache;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(dev, cs, smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(cs * 64));
+  cfg.blockDim = dim3(kPersistThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cs == 8 ? cudaOccupancyMaxActiveClusters(&n, conv_igemm_persistent_kernel<8>, &cfg)
+                          : cudaOccupancyMaxActiveClusters(&n, conv_igemm_persistent_kernel<2>, &cfg);
+  if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = g_num_sms / cs; }
+  if (getenv("ICP_DEBUG_CLUSTERS")) fprintf(stderr, "[icp] max active clusters of %d (smem %zu): %d\n", cs, smem, n);
+  cache[key] = n;
+  return n;
+}
+
 static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = false) {
   if (L.pair) {
     if (n < L.pair_min_batch && L.alt) { launch_conv(*L.alt, n, st, pdl); return; }
@@ -956,11 +996,17 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
   const int m_tiles = (a.m_total + kBM - 1) / kBM;
   if (L.persistent) {
     if (L.cluster && m_tiles >= L.cluster_min_tiles * g_num_sms) {
-      const int items = ((m_tiles + 1) / 2) * L.n_tiles;
-      const int max_clusters = g_num_sms / 2;
-      launch_k(conv_igemm_persistent_kernel<true>, 2 * (items < max_clusters ? items : max_clusters), kPersistThreads, L.smem,
-               st, pdl, 2, L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2,
-               L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
+      const int cs = L.cluster_size;
+      const int items = ((m_tiles + cs - 1) / cs) * L.n_tiles;
+      int max_clusters = max_active_clusters(cs, L.smem);
+      if (max_clusters > g_num_sms / cs) max_clusters = g_num_sms / cs;
+      const unsigned grid = static_cast<unsigned>(cs * (items < max_clusters ? items : max_clusters));
+      if (cs == 8)
+        launch_k(conv_igemm_persistent_kernel<8>, grid, kPersistThreads, L.smem, st, pdl, 8, L.tm_a, L.tm_b, L.tm_a_tail,
+                 L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
+      else
+        launch_k(conv_igemm_persistent_kernel<2>, grid, kPersistThreads, L.smem, st, pdl, 2, L.tm_a, L.tm_b, L.tm_a_tail,
+                 L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64, L.tm_o64_2, a, m_tiles, L.n_tiles);
       return;
     }
     // dual-tile items when the launch has between ICP_DUAL_MIN and ICP_DUAL_MAX tiles per SM (default 1.5 .. 3: the 17x17 stage
@@ -975,13 +1021,13 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
       a.epi_teams = 2;
       a.stages = L.dual_stages;
       const int items = ((m_tiles + 1) / 2) * L.n_tiles;
-      launch_k(conv_igemm_persistent_kernel<false>, items < g_num_sms ? items : g_num_sms, kPersistThreads, L.dual_smem, st, pdl, 1,
+      launch_k(conv_igemm_persistent_kernel<1>, items < g_num_sms ? items : g_num_sms, kPersistThreads, L.dual_smem, st, pdl, 1,
                L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64,
                L.tm_o64_2, a, m_tiles, L.n_tiles);
       return;
     }
     const int total = m_tiles * L.n_tiles;
-    launch_k(conv_igemm_persistent_kernel<false>, total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st, pdl, 1,
+    launch_k(conv_igemm_persistent_kernel<1>, total < g_num_sms ? total : g_num_sms, kPersistThreads, L.smem, st, pdl, 1,
              L.tm_a, L.tm_b, L.tm_a_tail, L.tm_b_tail, L.tm_b_half, L.tm_b_tail_half, L.tm_bias, L.tm_o, L.tm_o2, L.tm_o64,
              L.tm_o64_2, a, m_tiles, L.n_tiles);
   } else {
@@ -1802,8 +1848,9 @@ static int guard(const icp_engine* e, F&& f) {
 static void set_kernel_attrs(int device) {
   const int big = 227 * 1024;
   CK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CK(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
