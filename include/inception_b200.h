@@ -99,6 +99,10 @@ int icp_profile_forward(icp_engine* e, int n, int reps, float* ms_per_op);
  * float32 [n,C] are device pointers on the engine's device; work is enqueued on `stream`
  * (a cudaStream_t, NULL = the engine's own stream) and NOT synchronised. */
 int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_dev, void* stream);
+/* Same with the uint8 entry: x_dev uint8 [n,S,S,3] (0..255, already at network size) on the engine's device — the
+ * batch a GPU decoder or a previous device stage left in HBM; the (x/255 - 0.5)*2 of PyClassification.py:152-155 is
+ * folded into conv0 as in icp_forward_u8. */
+int icp_forward_u8_device(icp_engine* e, const uint8_t* x_dev, int n, float* probs_dev, void* stream);
 
 /* One request as the reference serves it (PyClassification.py:205-215) minus JPEG entropy
  * decoding: rgb is the decoded uint8 [h,w,3] image; crop, legacy-bilinear resize and

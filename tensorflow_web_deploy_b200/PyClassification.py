@@ -69,10 +69,13 @@ class ImagenetClassifier(object):
             model_def_file = self._converted
         device = int(os.environ.get("ICP_DEVICE", "0")) if device is None else device
         precision = os.environ.get("ICP_PRECISION", "fp16") if precision is None else precision
-        self.engine = _engine.Engine(model_def_file, num_classes=len(self.label_names), device=device, max_batch=1,
-                                     precision=precision, use_cuda_graph=use_cuda_graph)
-        if self._converted:
-            os.unlink(self._converted)          # the engine has read it
+        self._engine_args = (model_def_file,)
+        self._engine_kwargs = dict(num_classes=len(self.label_names), device=device, max_batch=1, precision=precision,
+                                   use_cuda_graph=use_cuda_graph)
+        self.engine = _engine.Engine(*self._engine_args, **self._engine_kwargs)
+        if self._converted:                     # kept for a rebuild after a CUDA error (_cuda_lost); removed at exit
+            import atexit
+            atexit.register(lambda p=self._converted: os.path.exists(p) and os.unlink(p))
         self.top_k = min(NUM_TOP_CLASSES, len(self.label_names))
         # JPEG decode (ICP_JPEG): "pil" (default) = host libjpeg(-turbo) — the decoder family TF's DecodeJpeg wraps, so
         # the tower sees the pixels the reference's graph would — then icp_classify_rgb8; "nvjpeg" = on the GPU inside
@@ -112,4 +115,25 @@ class ImagenetClassifier(object):
             return names, probs[:3], end_time - start_time, sum(probs)
         except Exception as err:
             logging.info("Classification error: %s", err)
+            if getattr(err, "code", 0) == -3:       # ICP_E_CUDA: sticky — see _cuda_lost
+                self._cuda_lost(err)
             return None
+
+    def _cuda_lost(self, err):
+        """A CUDA error (a trapped kernel, a lost device) poisons this process's CUDA context: every later call fails too,
+        and the reference's own recovery is gunicorn re-forking a worker that died.  One rebuild of the engine is tried (it
+        succeeds for errors that were not sticky); if that fails and ICP_EXIT_ON_CUDA_ERROR=1 the process exits with status 3
+        so that the pre-fork server replaces it, otherwise the failure is logged once more and the calls keep returning None."""
+        with self._lock:
+            try:
+                self.engine.close()
+            except Exception:
+                pass
+            try:
+                self.engine = _engine.Engine(*self._engine_args, **self._engine_kwargs)
+                logger.warning("engine rebuilt after a CUDA error (%s)", err)
+                return
+            except Exception as err2:
+                logger.error("CUDA context lost (%s; rebuild failed: %s): this worker process must be restarted", err, err2)
+        if os.environ.get("ICP_EXIT_ON_CUDA_ERROR", "0") == "1":
+            os._exit(3)

@@ -2013,6 +2013,16 @@ int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_de
   });
 }
 
+int icp_forward_u8_device(icp_engine* e, const uint8_t* x_dev, int n, float* probs_dev, void* stream) {
+  if (!e) return ICP_E_INVALID;
+  return guard(e, [&] {
+    if (!x_dev) fail(ICP_E_INVALID, "null input");
+    CK(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : e->stream;
+    run_tower(*e, x_dev, true, n, e->graph_k, probs_dev, st, false);
+  });
+}
+
 static void reserve_rgb(icp_engine* e, size_t bytes) {
   if (bytes <= e->d_rgb_cap) return;
   CK(cudaStreamSynchronize(e->stream));       // earlier work may still read the old buffer

@@ -54,6 +54,7 @@ SIGNATURES = {
                               C.POINTER(C.c_double)]),
     "icp_profile_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p]),
     "icp_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "icp_forward_u8_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "icp_classify_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _f32p, _i32p]),
     "icp_preprocess_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p]),
     "icp_classify_jpeg": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, _f32p, _i32p]),
@@ -216,10 +217,11 @@ class Engine:
         _check(self._lib.icp_profile_forward(self._h, n, reps, _f32(ms)), self._h)
         return ms
 
-    def forward_device(self, x_ptr: int, n: int, probs_ptr: int = 0, stream: int = 0) -> None:
-        """Enqueue (no sync) on device pointers; see icp_forward_device."""
-        _check(self._lib.icp_forward_device(self._h, C.c_void_p(x_ptr), n, C.c_void_p(probs_ptr or None),
-                                            C.c_void_p(stream or None)), self._h)
+    def forward_device(self, x_ptr: int, n: int, probs_ptr: int = 0, stream: int = 0, u8: bool = False) -> None:
+        """Enqueue (no sync) on device pointers; see icp_forward_device / icp_forward_u8_device (u8=True: the input is
+        uint8 [n,S,S,3] 0..255)."""
+        fn = self._lib.icp_forward_u8_device if u8 else self._lib.icp_forward_device
+        _check(fn(self._h, C.c_void_p(x_ptr), n, C.c_void_p(probs_ptr or None), C.c_void_p(stream or None)), self._h)
 
     def classify_rgb8(self, rgb: np.ndarray, k: int = 5) -> Tuple[np.ndarray, np.ndarray]:
         rgb = np.ascontiguousarray(rgb, np.uint8)

@@ -79,6 +79,10 @@ class GpuOwner:
         self.q: "queue.Queue[_Pending]" = queue.Queue()
         self.stop_ev = threading.Event()
         self.stats = {"requests": 0, "batches": 0, "max_batch_seen": 0, "errors": 0, "batch_hist": {}}
+        # set when the engine reports a CUDA error: a trapped kernel or a lost device poisons the process's CUDA context,
+        # every later call would fail too, and only a new process gets a new context — owner_main exits on it and
+        # serving/server.py starts a replacement owner on the same socket
+        self.fatal = threading.Event()
         self._threads: List[threading.Thread] = []
         self._listener: Optional[socket.socket] = None
 
@@ -182,15 +186,18 @@ class GpuOwner:
                     results[i] = (vals[j], idx[j])
             except Exception as err:
                 log.info("Classification error: %s", err)
+                self._note(err)
         if jpg:
             try:
                 vals, idx = self.engine.classify_batch_jpeg([batch[i].data for i in jpg], TOP_K)
                 for j, i in enumerate(jpg):
                     results[i] = (vals[j], idx[j])
             except Exception as err:                    # one undecodable stream fails the batched call: go one by one
-                log.info("batched call failed (%s); retrying the %d requests individually", err, len(jpg))
-                for i in jpg:
-                    results[i] = self._single(batch[i].data)
+                self._note(err)
+                if not self.fatal.is_set():
+                    log.info("batched call failed (%s); retrying the %d requests individually", err, len(jpg))
+                    for i in jpg:
+                        results[i] = self._single(batch[i].data)
         for p, r in zip(batch, results):
             if r is None:
                 st["errors"] += 1
@@ -204,6 +211,12 @@ class GpuOwner:
                     p.conn.sendall(payload)
             except OSError:
                 pass
+
+    def _note(self, err: Exception):
+        if getattr(err, "code", 0) == -3:               # ICP_E_CUDA (include/inception_b200.h)
+            if not self.fatal.is_set():
+                log.error("CUDA error in the GPU owner (%s): the context is lost, this process will be replaced", err)
+            self.fatal.set()
 
     def _single(self, data: bytes):
         try:
@@ -365,7 +378,9 @@ def owner_main(socket_path: str, weights_path: str, num_classes: int, device: in
     import json
     try:
         while True:
-            time.sleep(0.5)
+            if owner.fatal.wait(0.5):      # sticky CUDA error: answer nothing more from this context
+                log.error("GPU owner pid %d on device %d exits after a CUDA error (exit code 3)", os.getpid(), device)
+                os._exit(3)                # no destructors: they would call into the dead context
             if os.getppid() == 1:          # parent gone
                 break
             try:                           # batch statistics for the load test (tools/http_bench.py)

@@ -75,12 +75,20 @@ def main(argv=None):
     gpus = [int(g) for g in args.gpus.split(",") if g != ""]
     owners, paths = [], []
     from .batcher import owner_main
-    for g in gpus:
+
+    def start_owner(g):
         path = os.path.join(run_dir, "gpu%d.sock" % g)
         ready = path + ".ready"
+        for stale in (ready,):
+            if os.path.exists(stale):
+                os.unlink(stale)
         p = ctx.Process(target=owner_main, args=(path, args.model, len(label_names), g, args.max_batch, args.window_ms,
                                                  args.precision, ready), daemon=True)
         p.start()
+        return p, ready, path
+
+    for g in gpus:
+        p, ready, path = start_owner(g)
         owners.append((p, ready))
         paths.append(path)
     t0 = time.time()
@@ -123,6 +131,13 @@ def main(argv=None):
             pid, status = os.wait()
         except ChildProcessError:
             break
+        dead = [i for i, (p, _) in enumerate(owners) if p.pid == pid]
+        if dead:                                           # a GPU owner exited (exit code 3 = CUDA error, batcher.py): its CUDA
+            i = dead[0]                                    # context is gone with it; a fresh process on the same socket
+            log.error("GPU owner %d (gpu %d) exited with status %d; starting a replacement", pid, gpus[i], status)
+            p, ready, _ = start_owner(gpus[i])             # takes over (workers' pooled connections reconnect on error)
+            owners[i] = (p, ready)
+            continue
         if pid in workers:                                 # gunicorn re-forks dead workers; so do we
             workers.remove(pid)
             log.warning("worker %d exited (status %d); re-forking", pid, status)

@@ -119,8 +119,8 @@ class ShardedTower:
         return self._bufs
 
     def step_device(self, x_rows_dev, stream=None) -> GatherHandle:
-        """x_rows_dev: float32 [rows, S, S, 3] CUDA tensor holding THIS rank's rows (every rank passes the same
-        number of rows).  Enqueues the tower on `stream` (default: torch's current stream) and the all-gather on the
+        """x_rows_dev: float32 (normalised) or uint8 (0..255) [rows, S, S, 3] CUDA tensor holding THIS rank's rows (every
+        rank passes the same number of rows).  Enqueues the tower on `stream` (default: torch's current stream) and the all-gather on the
         side stream; returns at once."""
         import torch
         if self.engine is None:
@@ -133,7 +133,8 @@ class ShardedTower:
         if st["busy"][i]:
             stream.wait_event(st["gather_done"][i])             # the gather that last read probs[i] has finished
         probs = st["probs"][i]
-        self.engine.forward_device(x_rows_dev.data_ptr(), rows, probs.data_ptr(), stream.cuda_stream)
+        self.engine.forward_device(x_rows_dev.data_ptr(), rows, probs.data_ptr(), stream.cuda_stream,
+                                   u8=(x_rows_dev.dtype == torch.uint8))
         if self.world == 1:
             st["tower_done"][i].record(stream)
             st["busy"][i] = False

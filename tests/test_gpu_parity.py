@@ -249,6 +249,30 @@ def test_u8_entry_matches_float_entry(eng_mod, synth6):
     eng.close()
 
 
+def test_device_resident_entries_match_host_entries(eng_mod, synth6):
+    """icp_forward_device / icp_forward_u8_device (device pointers, caller's stream, no sync) == the host-buffer calls."""
+    import torch
+    rng = np.random.default_rng(16)
+    u8 = rng.integers(0, 256, (5, 299, 299, 3), dtype=np.uint8)
+    xf = (u8.astype(np.float32) * np.float32(1.0 / 255) - np.float32(0.5)) * np.float32(2.0)
+    eng = eng_mod.Engine(synth6[0], 6, max_batch=5, precision="fp16", use_cuda_graph=True)
+    want_u8 = eng.forward_u8(u8, 5)[0]
+    want_f = eng.forward(xf)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        xu = torch.from_numpy(u8).to(dev)
+        xd = torch.from_numpy(xf).to(dev)
+        pu = torch.zeros((5, 6), device=dev)
+        pf = torch.zeros((5, 6), device=dev)
+        eng.forward_device(xu.data_ptr(), 5, pu.data_ptr(), st.cuda_stream, u8=True)
+        eng.forward_device(xd.data_ptr(), 5, pf.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    np.testing.assert_array_equal(pu.cpu().numpy(), want_u8)
+    np.testing.assert_array_equal(pf.cpu().numpy(), want_f)
+    eng.close()
+
+
 def test_async_slots_match_sync_call(eng_mod, synth6):
     """icp_submit_u8 / icp_collect (copy of batch i+1 overlapping tower i) returns exactly what the blocking call does."""
     rng = np.random.default_rng(12)

@@ -74,6 +74,22 @@ def test_errors_return_none(clf, monkeypatch):
     assert clf.classify_image(_jpeg()) is None
 
 
+def test_cuda_error_rebuilds_the_engine_once(clf, monkeypatch):
+    """ICP_E_CUDA (-3) is sticky for the context: the classifier answers None, rebuilds its engine (which works when the
+    error was not fatal), and the next request is served by the new engine."""
+    first = clf.engine
+    first.close = lambda: first.calls.append("closed")
+
+    def boom(*a):
+        raise P._engine.EngineError(-3, "an illegal memory access was encountered")
+
+    monkeypatch.setattr(first, "classify_rgb8", boom)
+    assert clf.classify_image(_jpeg()) is None
+    assert clf.engine is not first and first.calls[-1] == "closed"
+    assert clf.engine.kw["num_classes"] == 6 and clf.engine.kw["max_batch"] == 1
+    assert clf.classify_image(_jpeg()) is not None
+
+
 def test_missing_files_raise(monkeypatch, tmp_path):
     monkeypatch.setattr(P._engine, "Engine", FakeEngine)
     with pytest.raises(Exception, match="missing"):

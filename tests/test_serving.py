@@ -205,6 +205,29 @@ def test_worker_side_decode_hands_over_pixels(tmp_path):
     owner.stop()
 
 
+def test_cuda_error_marks_the_owner_fatal(tmp_path):
+    """An engine error with code ICP_E_CUDA (-3) = the owner's CUDA context is lost: the waiting requests get the error
+    answer (-> None, like PyClassification.py:216-218), nothing is retried on the dead context, and `fatal` is set so that
+    owner_main exits and serving/server.py starts a replacement."""
+    class CudaErr(Exception):
+        code = -3
+
+    class DeadEngine(FakeEngine):
+        def classify_batch_jpeg(self, jpegs, k):
+            with self.lock:
+                self.batches.append(len(jpegs))
+            raise CudaErr("unspecified launch failure")
+
+    eng = DeadEngine()
+    owner = B.GpuOwner(eng, str(tmp_path / "o.sock"), max_batch=4, window_ms=1.0).start()
+    cli = B.BatcherClient([owner.path], LABELS, decode="owner")
+    assert cli.classify_image(b"x" * 50) is None
+    assert owner.fatal.wait(2.0)
+    assert eng.batches == [1]                              # no one-by-one retry on a dead context
+    cli.close()
+    owner.stop()
+
+
 def test_connections_are_pooled_not_per_thread(tmp_path):
     """A threaded WSGI server runs every request on a fresh thread: the client must reuse its connections (one shared-memory
     segment + socket each), growing the pool only to the number of requests in flight."""
