@@ -161,9 +161,11 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
             "steps": done_steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(done_steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "classify path, batch 1 x %d images per step, CPU oracle port of the reference "
-                                   "TF graph (reference itself not runnable: no TensorFlow/Python2/checkpoint)" % per_step,
-                       "num_classes": NUM_CLASSES},
+            "config": {"workload": "batch=%d/GPU synthetic 299x299x3, full Inception-v3 tower + softmax + top-5 (BASELINE configs[2]); "
+                                   "bounded sample: %d images per step, batch 1 each as the reference serves, CPU oracle port of the "
+                                   "reference TF graph on all host threads (the reference itself is not runnable: no "
+                                   "TensorFlow/Python2/checkpoint)" % (args.batch, per_step),
+                       "global_batch": args.batch * max(1, args.gpus), "num_classes": NUM_CLASSES, "parallelism": "cpu"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "%d steps x %d images, batch 1, torch fp32 CPU" % (args.steps, per_step)},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
