@@ -24,6 +24,7 @@ cpu_baseline / --impl reference : the CPU oracle (torch fp32 restatement of the 
 from __future__ import annotations
 
 import argparse
+import math
 import json
 import os
 import subprocess
@@ -203,6 +204,7 @@ def main():
     ap.add_argument("--strong", action="store_true", help="fixed global batch of 1024 (BASELINE configs[3]) split over the GPUs")
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the extra sustained run (0 = skip)")
     ap.add_argument("--input", default="u8", choices=["u8", "f32"], help="dtype of the HBM-resident timed batch")
+    ap.add_argument("--depth", type=int, default=2, help="output / gather buffers in rotation (ShardedTower depth)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--http", action="store_true",
@@ -264,7 +266,7 @@ def main():
 
     stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: the engine enqueues on the handle we pass
     torch.cuda.set_stream(stream)
-    tower = sharding.ShardedTower(None, C, dist=dist if world > 1 else None, device=dev, engine=eng)
+    tower = sharding.ShardedTower(None, C, dist=dist if world > 1 else None, device=dev, engine=eng, depth=args.depth)
 
     last = [None]
     turn = [0]
@@ -281,7 +283,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(-(-n_in // chunks)):             # setup, not warm-up: every input buffer's CUDA graph is captured once
+    # setup, not warm-up: one CUDA graph exists per (input buffer, output buffer) pair — capture them all once
+    for _ in range(-(-(n_in * tower.depth // math.gcd(n_in, tower.depth)) // chunks)):
         step()
     sync_all()
     for _ in range(args.warmup):

@@ -63,9 +63,14 @@ class ShardedTower:
     step_device().  `dist` is torch.distributed (already initialised) or None for one process."""
 
     def __init__(self, forward_fn: Optional[Callable[[np.ndarray], np.ndarray]], num_classes: int, dist=None, device=None,
-                 sweet_spot: int = SWEET_SPOT, engine=None):
+                 sweet_spot: int = SWEET_SPOT, engine=None, depth: int = 2):
         self.forward_fn, self.C, self.dist, self.device, self.sweet_spot = forward_fn, num_classes, dist, device, sweet_spot
         self.engine = engine
+        # step_device keeps `depth` output / gather buffers in rotation: a rank may run that many steps ahead of the slowest
+        # one before it has to wait for a gather.  A GatherHandle stays valid for depth - 1 further steps.  MEASURED on 2 GPUs
+        # (30-step runs): depth 2 2.301 / 2.264 ms per step, 4 2.254, 8 2.350 / 2.277, one GPU 2.267 / 2.238 — all inside the
+        # run-to-run spread of power-capped boards, so the default stays 2.
+        self.depth = max(2, int(depth))
         if forward_fn is None and engine is not None:
             self.forward_fn = engine.forward
         self._bufs = None
@@ -109,12 +114,12 @@ class ShardedTower:
             dev = self.device
             self._bufs = {
                 "rows": rows,
-                "probs": [torch.empty((rows, self.C), dtype=torch.float32, device=dev) for _ in range(2)],
-                "gathered": [torch.empty((rows * self.world, self.C), dtype=torch.float32, device=dev) for _ in range(2)],
-                "tower_done": [torch.cuda.Event() for _ in range(2)],
-                "gather_done": [torch.cuda.Event() for _ in range(2)],
+                "probs": [torch.empty((rows, self.C), dtype=torch.float32, device=dev) for _ in range(self.depth)],
+                "gathered": [torch.empty((rows * self.world, self.C), dtype=torch.float32, device=dev) for _ in range(self.depth)],
+                "tower_done": [torch.cuda.Event() for _ in range(self.depth)],
+                "gather_done": [torch.cuda.Event() for _ in range(self.depth)],
                 "comm": torch.cuda.Stream(device=dev),
-                "busy": [False, False],
+                "busy": [False] * self.depth,
             }
         return self._bufs
 
@@ -127,7 +132,7 @@ class ShardedTower:
             raise RuntimeError("step_device needs an engine")
         rows = int(x_rows_dev.shape[0])
         st = self._device_state(rows)
-        i = self._step & 1
+        i = self._step % self.depth
         self._step += 1
         stream = stream or torch.cuda.current_stream()
         if st["busy"][i]:

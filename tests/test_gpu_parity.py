@@ -187,6 +187,18 @@ OPT_IN_ENVS = [
     pytest.param({"ICP_CLUSTER_ALL": "1"}, id="two_cta_clusters_everywhere"),
     pytest.param({"ICP_HALO_DIRECT": "1", "ICP_HALO_MIN_W": "30"}, id="halo_direct_stores"),
     pytest.param({"ICP_HALO_DIRECT": "0"}, id="halo_staged_stores"),
+    # round 2: every measured-and-not-adopted path stays correct
+    pytest.param({"ICP_PAIR": "1", "ICP_PAIR_MIN_BATCH": "1"}, id="cta_pair_weight_resident_kernel"),
+    pytest.param({"ICP_HALO_RES": "1", "ICP_HALO_RES_MIN_BATCH": "1"}, id="weight_resident_strips_n_split"),
+    pytest.param({"ICP_DUAL": "1", "ICP_DUAL_MIN": "0", "ICP_DUAL_MAX": "100000", "ICP_DUAL_MIN_TAPS": "1"}, id="dual_tile_items"),
+    pytest.param({"ICP_CLUSTER_ALL": "1", "ICP_CLUSTER_SIZE": "8"}, id="clusters_of_eight"),
+    pytest.param({"ICP_HALO_CP": "1"}, id="strips_by_cp_async"),
+    pytest.param({"ICP_HALO_BOX_ROWS": "2"}, id="strips_in_several_boxes"),
+    pytest.param({"ICP_HALO_MAX_STRIPS": "3"}, id="three_strips"),
+    pytest.param({"ICP_NARROW_NTILE": "16"}, id="narrow_twins_16_columns"),
+    pytest.param({"ICP_NARROW_NTILE": "0", "ICP_PDL_MAX_BATCH": "0"}, id="no_twins_no_pdl"),
+    pytest.param({"ICP_RESERVE_SMS": "2", "ICP_EPI_TEAMS": "1"}, id="reserved_sms_one_epilogue_team"),
+    pytest.param({"ICP_EPI_TEAMS": "2"}, id="two_epilogue_teams_everywhere"),
 ]
 
 

@@ -25,10 +25,10 @@ path = os.path.join(%(tmp)r, "w%%d.icpw" %% rank)
 weights.save_blob(path, weights.synthetic_weights(C))
 eng = engine.Engine(path, C, device=lr, max_batch=B, precision="fp16", use_cuda_graph=True)
 dev = torch.device("cuda", lr)
-tower = sharding.ShardedTower(None, C, dist=dist, device=dev, engine=eng, sweet_spot=B)
-# device path: every rank owns B rows; three steps in flight, gathers on the side stream
+tower = sharding.ShardedTower(None, C, dist=dist, device=dev, engine=eng, sweet_spot=B, depth=2)
+# device path: every rank owns B rows; five steps through two rotating buffers, gathers on the side stream
 rng = np.random.default_rng(100 + rank)
-xs = [torch.from_numpy(rng.uniform(-1, 1, (B, 299, 299, 3)).astype(np.float32)).to(dev) for _ in range(3)]
+xs = [torch.from_numpy(rng.uniform(-1, 1, (B, 299, 299, 3)).astype(np.float32)).to(dev) for _ in range(5)]
 stream = torch.cuda.Stream(device=dev)
 with torch.cuda.stream(stream):
     handles = [tower.step_device(x, stream) for x in xs]
