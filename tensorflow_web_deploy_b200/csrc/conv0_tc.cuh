@@ -48,7 +48,7 @@ __device__ __forceinline__ uint16_t conv0_tc_cvt<uint8_t>(uint8_t v, int fmt) {
 template <typename TIn>
 __global__ void __launch_bounds__(kConv0TcThreads, 1)
 conv0_tc_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_constant__ Conv0TcParams p,
-                uint16_t* __restrict__ out, int OH, int OW, int fmt) {
+                uint16_t* __restrict__ out, int OH, int OW, int fmt, int pdl_late) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -90,7 +90,7 @@ conv0_tc_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_co
     *reinterpret_cast<uint4*>(gbase + (w_base - base) + n * 64 + ((c ^ ((n >> 1) & 3)) << 4)) = v;
     ptx::fence_proxy_async_smem();
   }
-  ptx::pdl_launch();
+  if (!pdl_late) ptx::pdl_launch();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -273,6 +273,7 @@ conv0_tc_kernel(const TIn* __restrict__ in, int N, int H, int W, const __grid_co
       __syncwarp();
       if (++s == kConv0Stages) { s = 0; ph ^= 1u; }
     }
+    if (pdl_late) ptx::pdl_launch();
   } else {
     // ---------------- epilogue: + shift, ReLU, 64 contiguous bytes per pixel ----------------
     // (a second epilogue team — 8 warps, alternate tiles — was MEASURED: 0.098 -> 0.105 ms; this chain is not the bound)

@@ -64,6 +64,7 @@ struct HaloArgs {
   long long* dbg;       // optional timeline buffer (CTA 0 only), same rows as the persistent kernel (tools/timeline.py)
   // strip = nbox boxes of box_rows rows (+ one of rem_rows through tm_a_rem): several boxes in flight per strip
   int box_rows, nbox, rem_rows;
+  int pdl_late;         // 1: launch_dependents when this CTA's last band's MMAs are issued, not at kernel start (conv_igemm.cuh)
   // kCp (strips copied by cp.async instead of TMA): the input tensor itself
   const uint16_t* in;   // first channel of this layer's input slice
   int ih, iw, ldi;      // input height, width, channels per pixel of the buffer (elements)
@@ -150,7 +151,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     write_ones_row(gbase + (ones_base - base), static_cast<int>(threadIdx.x) - 64, a.fmt);
     ptx::fence_proxy_async_smem();
   }
-  ptx::pdl_launch();
+  if (!a.pdl_late) ptx::pdl_launch();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -412,6 +413,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       __syncwarp();
       if (++as == static_cast<uint32_t>(a.acc_sets)) { as = 0; pha ^= 1u; }
     }
+    if (a.pdl_late) ptx::pdl_launch();
   } else {
     // ---------------- epilogue (warps 2..5 and 7..10) ----------------
     // TWO independent teams of four warps (one warp per TMEM lane quarter each).  Units = (sub-tile, <= 64-column chunk)

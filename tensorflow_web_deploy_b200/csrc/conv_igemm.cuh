@@ -87,6 +87,7 @@ struct ConvArgs {
   int relu_lo, relu_hi;
   int epi_staged;      // one-tile kernel: 1 = epilogue through shared staging + coalesced stores, 0 = row-per-thread stores
   int epi_teams;       // persistent kernel: 2 = two independent 4-warp epilogue teams (own staging each), 1 = one 8-warp team
+  int pdl_late;        // 1: griddepcontrol.launch_dependents is issued when this CTA's LAST tile's MMAs are in flight (not at kernel start)
   int dual;            // persistent kernel (epi_teams == 2 only): 1 = a work item is TWO consecutive M tiles that share every
                        //   weight tile (stage = A0 | A1 | W); the two TMEM halves are simultaneous accumulators, not a double buffer
   long long* dbg;      // optional timeline buffer (CTA 0 only): [role][event] clock64 stamps, see tools/timeline.py
@@ -461,7 +462,7 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   const int step = static_cast<int>(gridDim.x) / kCS;
   auto tile_m0 = [&](int t) { return ((t / n_tiles) * grp + static_cast<int>(crank)) * kBM; };
 
-  ptx::pdl_launch();
+  if (!a.pdl_late) ptx::pdl_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a);
     ptx::prefetch_tmap(&tm_b);
@@ -734,6 +735,10 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
       if (ptx::elect_one()) ptx::umma_commit(tmem_full(as));
       __syncwarp();
     }
+    // late trigger: this CTA has issued all its MMAs; what is left is the last tile's epilogue.  The successor grid may now
+    // be scheduled (once every CTA got here or exited): its launch latency and prologue overlap these final epilogues
+    // without its CTAs having occupied SMs during the main loop (the cost of triggering at kernel start, engine.cu).
+    if (a.pdl_late) ptx::pdl_launch();
   } else {
     if (a.epi_teams == 2) {
       // ---------------- epilogue (warps 2..5 and 7..10) ----------------

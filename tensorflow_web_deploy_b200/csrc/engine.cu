@@ -296,6 +296,12 @@ struct ConvLayer {
 };
 
 static int g_num_sms = 148;
+// Where a kernel issues griddepcontrol.launch_dependents: at its start (0) or when a CTA has issued its last MMAs (1, default).
+static bool pdl_late() {
+  static const bool v = getenv("ICP_PDL_LATE") ? atoi(getenv("ICP_PDL_LATE")) != 0 : true;
+  return v;
+}
+
 
 // Every tower kernel goes through cudaLaunchKernelEx so that it can carry the programmatic-dependent-launch
 // attribute (ptx.cuh pdl_wait / pdl_launch): `pdl` is set when the previous operation enqueued on the same stream
@@ -864,6 +870,7 @@ static ConvLayer make_conv(DevicePool& pool, const std::string& name, int max_n,
   static const bool v1_staged = getenv("ICP_V1_STAGED") != nullptr;
   a.epi_staged = v1_staged ? 1 : 0;
   a.epi_teams = persistent ? epi_teams : 1;
+  a.pdl_late = 0;          // set per launch (launch_conv)
   a.dbg = nullptr;
   // ReLU column range: everything, nothing, or (fused siblings) the leading run of channels whose floor is 0
   a.relu_lo = 0;
@@ -968,6 +975,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
     if (L.alt && n < L.pair_min_batch) { launch_conv(*L.alt, n, st, pdl); return; }
     HaloArgs h = L.hargs;
     h.n_images = n;
+    h.pdl_late = pdl_late() ? 1 : 0;
     const int bands = h.tall ? (n * h.oh * h.wp + kBM * h.T - 1) / (kBM * h.T) : h.bands_per_image * n;
     const int items = bands * h.n_tiles;
     unsigned grid = static_cast<unsigned>(items < g_num_sms ? items : g_num_sms);
@@ -993,6 +1001,7 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
   }
   ConvArgs a = L.args;
   a.m_total = n * L.pix_per_image;
+  a.pdl_late = pdl_late() ? 1 : 0;
   const int m_tiles = (a.m_total + kBM - 1) / kBM;
   if (L.persistent) {
     if (L.cluster && m_tiles >= L.cluster_min_tiles * g_num_sms) {
@@ -1564,13 +1573,15 @@ struct Builder {
   }
 };
 
-// Programmatic dependent launch is used for batches up to ICP_PDL_MAX_BATCH (default 16; 0 = never).  MEASURED at
-// batch 128: 2.347 ms/step with it against 2.324 without — an early-launched CTA parks on its SM until the
-// predecessor has finished, and at large batches that SM would otherwise run a kernel of another branch lane; at
-// small batches (a handful of CTAs per launch) the launch latency and prologue it hides are most of a layer's time.
+// Programmatic dependent launch between consecutive kernels of a stream, for batches up to ICP_PDL_MAX_BATCH (0 = never).
+// WHERE the predecessor triggers matters.  At its start (ICP_PDL_LATE=0; then the default limit is batch 16): MEASURED at batch 128
+// 2.347 ms/step against 2.324 without PDL — the successor's CTAs are placed on SMs as they free up and park there until the
+// predecessor has finished, SMs that would otherwise run a kernel of another branch lane.  When a CTA has issued its last MMAs
+// (ICP_PDL_LATE=1, the default, every batch size): the successor's launch latency and prologue overlap only the final epilogues —
+// MEASURED 2.275 -> 2.257 ms at batch 128, 0.988 -> 0.938 at 32, 0.487 -> 0.477 at 8, 0.370 -> 0.368 at 1.
 static thread_local int g_pdl_batch = 0;      // batch of the tower being enqueued
 static bool pdl_enabled() {
-  static const int max_batch = getenv("ICP_PDL_MAX_BATCH") ? atoi(getenv("ICP_PDL_MAX_BATCH")) : 16;
+  static const int max_batch = getenv("ICP_PDL_MAX_BATCH") ? atoi(getenv("ICP_PDL_MAX_BATCH")) : (pdl_late() ? (1 << 30) : 16);
   return g_pdl_batch <= max_batch;
 }
 // Which streams' most recent operation was one of our kernels (only then may the next launch on that stream be
@@ -1698,10 +1709,10 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
       const unsigned tgrid = grid < static_cast<unsigned>(g_num_sms) ? grid : static_cast<unsigned>(g_num_sms);
       if (x_is_u8)
         launch_k(conv0_tc_kernel<uint8_t>, tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st, p0, 1,
-                 static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_u8, o.p, o.h, o.w, fmt);
+                 static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_u8, o.p, o.h, o.w, fmt, pdl_late() ? 1 : 0);
       else
         launch_k(conv0_tc_kernel<float>, tgrid, kConv0TcThreads, conv0_tc_smem_bytes(), st, p0, 1,
-                 static_cast<const float*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_f, o.p, o.h, o.w, fmt);
+                 static_cast<const float*>(x_dev) + in_off, nc, e.S, e.S, e.conv0_tc_f, o.p, o.h, o.w, fmt, pdl_late() ? 1 : 0);
     } else if (x_is_u8) {
       conv0_kernel<uint8_t><<<grid, 128, 0, st>>>(static_cast<const uint8_t*>(x_dev) + in_off, nc, e.S, e.S, e.conv0,
                                                   o.p, o.h, o.w, fmt);
@@ -1729,6 +1740,7 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
         pa.w = fc->conv.d_w; pa.bias16 = fc->conv.d_bias16; pa.cout = fc->conv.cout;
         pa.out = static_cast<uint16_t*>(fc->conv.args.out); pa.OH = po.out.h; pa.OW = po.out.w; pa.ldo = fc->conv.args.ldo;
         pa.coff = fc->conv.args.coff; pa.relu = fc->conv.args.relu_hi > 0 ? 1 : 0; pa.fmt = fmt;
+        pa.pdl_late = pdl_late() ? 1 : 0;
         const int tiles = (nc * pa.OH * pa.OW + kBM - 1) / kBM;
         launch_k(pool_conv_kernel, tiles < g_num_sms ? tiles : g_num_sms, kPoolConvThreads, pool_conv_smem_bytes(), st, pdl.take(st), 1, pa);
         ++launches;
@@ -1874,6 +1886,10 @@ static void set_kernel_attrs(int device) {
   if (const char* v = getenv("ICP_RESERVE_SMS")) {
     const int r = atoi(v);
     if (r > 0 && r < g_num_sms / 2) g_num_sms -= r;
+  }
+  {
+    const int late = pdl_late() ? 1 : 0;
+    CK(cudaMemcpyToSymbol(ptx::g_pdl_late, &late, sizeof late));
   }
   if (const char* v = getenv("ICP_MBAR_TIMEOUT_MS")) {
     const long long cycles = atoll(v) * 1900000LL;     // ~1.9 GHz SM clock

@@ -31,6 +31,7 @@ struct PoolConvArgs {
   uint16_t* out;           // [N, OH, OW, ldo]
   int OH, OW, ldo, coff;
   int relu, fmt;
+  int pdl_late;            // see conv_igemm.cuh
 };
 
 __global__ void __launch_bounds__(kPoolConvThreads, 1) pool_conv_kernel(const PoolConvArgs a) {
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(kPoolConvThreads, 1) pool_conv_kernel(const Po
   const int total = a.N * a.OH * a.OW;
   const int tiles = (total + kBM - 1) / kBM;
 
-  ptx::pdl_launch();
+  if (!a.pdl_late) ptx::pdl_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kPoolConvStages; ++s) {
       ptx::mbar_init(full_bar(s), 128);          // every builder thread of the group arrives
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kPoolConvThreads, 1) pool_conv_kernel(const Po
       __syncwarp();
       if (++s == kPoolConvStages) { s = 0; ph ^= 1u; }
     }
+    if (a.pdl_late) ptx::pdl_launch();
   } else {
     // ---------------- epilogue: ReLU, 16-bit NHWC; two warps per lane quarter split the 16-column pieces ----------------
     const int ew = warp - 17;                   // 0..7

@@ -72,6 +72,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // latency.  Both are no-ops in a launch without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The pool / head kernels: trigger at their start only in the early-trigger mode (engine.cu pdl_late(); set at device
+// setup).  In the late mode they do not trigger explicitly — a CTA that exits counts as triggered — so a successor never
+// takes SMs away from their remaining CTAs.
+__device__ int g_pdl_late = 1;
+__device__ __forceinline__ void pdl_launch_if_early() {
+  if (!*reinterpret_cast<volatile int*>(&g_pdl_late)) pdl_launch();
+}
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {

@@ -149,7 +149,7 @@ __device__ __forceinline__ uint4 max8_h16(const uint4& a, const uint4& b, int fm
 }
 __global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, int N, int H, int W, int C, int ldi, int cin_off,
                                   uint16_t* __restrict__ out, int OH, int OW, int ldo, int coff, int fmt) {
-  ptx::pdl_launch();
+  ptx::pdl_launch_if_early();
   ptx::pdl_wait();
   const unsigned cg = static_cast<unsigned>(C) >> 3;
   const unsigned pairs = (static_cast<unsigned>(OW) + 1u) >> 1;
@@ -193,7 +193,7 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, int N, int H, in
                                uint16_t* __restrict__ out, int OH, int OW, int ldo, int coff, int k, int stride,
                                int pad, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                                int fmt) {
-  ptx::pdl_launch();
+  ptx::pdl_launch_if_early();
   ptx::pdl_wait();
   // scale/shift (nullable): the pool runs AFTER a linear 1x1 projection (avg-pool and a 1x1 conv
   // commute), so the projection's BatchNorm + ReLU (ops.py:231-245) are applied here, on the pooled value.
@@ -284,7 +284,7 @@ template <int CG>
 __global__ void __launch_bounds__(512)
 avgpool3_relu_kernel(const uint16_t* __restrict__ in, int H, int W, int C, int ldi, int cin_off,
                      uint16_t* __restrict__ out, int ldo, int coff, int band_rows, int bands, int relu, int fmt) {
-  ptx::pdl_launch();
+  ptx::pdl_launch_if_early();
   ptx::pdl_wait();
   extern __shared__ uint4 pool_tile[];          // [(band_rows + 2)][(W + 2)][C / 8] 16-byte vectors
   const int cg = CG ? CG : (C >> 3);
@@ -358,7 +358,7 @@ constexpr int kHeadSlice = 256;      // channels per head_pool CTA
 __global__ void __launch_bounds__(256)
 head_pool_kernel(const uint16_t* __restrict__ feat_map, int hw, int F, int ld, float* __restrict__ feat,
                  const float* __restrict__ fc_w /*[F][C]*/, int C, float* __restrict__ part /*[n][F/256][C]*/, int fmt) {
-  ptx::pdl_launch();
+  ptx::pdl_launch_if_early();
   ptx::pdl_wait();
   __shared__ float red[8][kHeadSlice];
   __shared__ float fs[kHeadSlice];
@@ -400,7 +400,7 @@ head_pool_kernel(const uint16_t* __restrict__ feat_map, int hw, int F, int ld, f
 __global__ void __launch_bounds__(256)
 head_fc_kernel(const float* __restrict__ feat, int n, int F, const float* __restrict__ fc_w, const float* __restrict__ fc_b,
                int C, float* __restrict__ logits) {
-  ptx::pdl_launch();
+  ptx::pdl_launch_if_early();
   ptx::pdl_wait();
   __shared__ float fs[16][256];
   __shared__ float red[4][16][64];
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(256)
 head_finish_kernel(const float* __restrict__ part, int slices, const float* __restrict__ fc_b, int C,
                    float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ topk_val,
                    int* __restrict__ topk_idx, int k) {
-  ptx::pdl_launch();
+  ptx::pdl_launch_if_early();
   ptx::pdl_wait();
   extern __shared__ float lg[];      // [C]
   __shared__ float red[32];
