@@ -498,7 +498,9 @@ conv_igemm_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __g
   if constexpr (kCluster) ptx::cluster_sync();   // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
-  ptx::pdl_wait();            // prologue above overlapped the predecessor's tail; its output is complete from here on
+  // prologue above overlapped the predecessor's tail; its output is complete from here on.  (Letting the weight producers
+  // skip this wait — weights do not depend on the predecessor — was MEASURED neutral: 2.274 vs 2.272 ms/step.)
+  ptx::pdl_wait();
 
   if (warp == 0 || warp == 11) {
     // ---------------- TMA producers #1: A tiles (warp-converged; one elected lane issues) ----------------
