@@ -1765,7 +1765,10 @@ static int enqueue_tower(icp_engine& e, const void* x_dev, bool x_is_u8, int n, 
         if (lane_live[i]) {
           CK(cudaEventRecord(e.join_ev[i], e.lane_stream[i]));
           CK(cudaStreamWaitEvent(st, e.join_ev[i], 0));
-          pdl.barrier(st);
+          // The next block's first kernel keeps its programmatic edge to this stream's last kernel (the block's longest
+          // branch runs on this stream) next to the full edges from the side lanes; ICP_PDL_JOIN=0 drops it.
+          static const bool pdl_join = getenv("ICP_PDL_JOIN") ? atoi(getenv("ICP_PDL_JOIN")) != 0 : true;
+          if (!pdl_join) pdl.barrier(st);
           lane_live[i] = false;
         }
       continue;
