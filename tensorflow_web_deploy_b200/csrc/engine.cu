@@ -1001,7 +1001,8 @@ static void launch_conv(const ConvLayer& L, int n, cudaStream_t st, bool pdl = f
   }
   ConvArgs a = L.args;
   a.m_total = n * L.pix_per_image;
-  a.pdl_late = pdl_late() ? 1 : 0;
+  static const int pdl_point = getenv("ICP_PDL_POINT") ? atoi(getenv("ICP_PDL_POINT")) : 1;   // 2: before the last tile (experiment)
+  a.pdl_late = pdl_late() ? pdl_point : 0;
   const int m_tiles = (a.m_total + kBM - 1) / kBM;
   if (L.persistent) {
     if (L.cluster && m_tiles >= L.cluster_min_tiles * g_num_sms) {
