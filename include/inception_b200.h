@@ -104,6 +104,13 @@ int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_de
  * folded into conv0 as in icp_forward_u8. */
 int icp_forward_u8_device(icp_engine* e, const uint8_t* x_dev, int n, float* probs_dev, void* stream);
 
+/* Page-lock (and later release) a host buffer the caller will pass to the batch / submit calls repeatedly — e.g. the
+ * shared-memory segments through which the serving workers hand decoded pixels to the GPU-owner process — so that
+ * the per-image host->device copies are true asynchronous DMA instead of staged pageable copies.  Registered on the
+ * engine's device (portable to every context).  ICP_E_CUDA if the range cannot be registered; the buffer stays usable. */
+int icp_host_register(icp_engine* e, void* host_ptr, size_t bytes);
+int icp_host_unregister(icp_engine* e, void* host_ptr);
+
 /* One request as the reference serves it (PyClassification.py:205-215) minus JPEG entropy
  * decoding: rgb is the decoded uint8 [h,w,3] image; crop, legacy-bilinear resize and
  * normalisation run on the GPU, then the tower, softmax and top-k. */

@@ -2040,6 +2040,31 @@ int icp_forward_device(icp_engine* e, const float* x_dev, int n, float* probs_de
   });
 }
 
+int icp_host_register(icp_engine* e, void* host_ptr, size_t bytes) {
+  if (!e || !host_ptr || !bytes) return ICP_E_INVALID;
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess) { (void)cudaGetLastError(); return ICP_E_CUDA; }
+  cudaError_t err = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    char msg[160];
+    snprintf(msg, sizeof msg, "cudaHostRegister(%p, %zu): %s", host_ptr, bytes, cudaGetErrorString(err));
+    g_tls_error = msg;
+    return ICP_E_CUDA;
+  }
+  return ICP_OK;
+}
+
+int icp_host_unregister(icp_engine* e, void* host_ptr) {
+  if (!e || !host_ptr) return ICP_E_INVALID;
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess) { (void)cudaGetLastError(); return ICP_E_CUDA; }
+  cudaError_t err = cudaHostUnregister(host_ptr);
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    return ICP_E_CUDA;
+  }
+  return ICP_OK;
+}
+
 int icp_forward_u8_device(icp_engine* e, const uint8_t* x_dev, int n, float* probs_dev, void* stream) {
   if (!e) return ICP_E_INVALID;
   return guard(e, [&] {

@@ -55,6 +55,8 @@ SIGNATURES = {
     "icp_profile_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f32p]),
     "icp_forward_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "icp_forward_u8_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "icp_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "icp_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "icp_classify_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, _f32p, _i32p]),
     "icp_preprocess_rgb8": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, _f32p]),
     "icp_classify_jpeg": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, _f32p, _i32p]),
@@ -259,6 +261,14 @@ class Engine:
         return self.JPEG_BACKENDS.get(v.value, str(v.value))
 
     # ------------------------------------------------------------------ micro-batched requests
+    def host_register(self, address: int, nbytes: int) -> bool:
+        """Page-lock a host range that will be handed to the batch calls repeatedly (icp_host_register); False if the
+        driver refuses (the range stays usable, copies are then staged)."""
+        return self._lib.icp_host_register(self._h, C.c_void_p(address), C.c_size_t(nbytes)) == 0
+
+    def host_unregister(self, address: int) -> None:
+        self._lib.icp_host_unregister(self._h, C.c_void_p(address))
+
     def classify_batch_rgb8(self, images, k: int = 5) -> Tuple[np.ndarray, np.ndarray]:
         """images: sequence of uint8 [h,w,3] arrays of any sizes -> (vals [n,k], idx [n,k]) from ONE tower launch."""
         imgs = [np.ascontiguousarray(im, np.uint8) for im in images]

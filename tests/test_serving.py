@@ -167,20 +167,34 @@ def test_round_robin_over_owners_and_reconnect(tmp_path):
     [o.stop() for o in owners]
 
 
-def test_worker_side_decode_hands_over_pixels(tmp_path):
+@pytest.mark.parametrize("pin", ["0", "1"])
+def test_worker_side_decode_hands_over_pixels(tmp_path, monkeypatch, pin):
     """decode="worker" (default): libjpeg in the worker, uint8 [h,w,3] pixels through the segment, ONE
-    classify_batch_rgb8 call for the merged requests; a non-JPEG body never reaches the owner."""
+    classify_batch_rgb8 call for the merged requests; a non-JPEG body never reaches the owner.  pin=1 (ICP_SERVE_PIN): the
+    segments are page-locked through the engine and the engine sees views into them instead of copies."""
     from PIL import Image
+    monkeypatch.setenv("ICP_SERVE_PIN", pin)
+    registered = []
 
     class RgbEngine(FakeEngine):
         def __init__(self):
             super().__init__(delay=0.02)
             self.shapes = []
+            self.owned = []
+
+        def host_register(self, address, nbytes):
+            registered.append((address, nbytes))
+            return True
+
+        def host_unregister(self, address):
+            registered.append((address, -1))
 
         def classify_batch_rgb8(self, imgs, k):
             with self.lock:
                 self.batches.append(len(imgs))
                 self.shapes += [im.shape for im in imgs]
+                self.owned += [bool(im.flags["OWNDATA"]) or im.base is None or isinstance(im.base, bytes) or
+                               (isinstance(im.base, np.ndarray) and isinstance(im.base.base, bytes)) for im in imgs]
             time.sleep(self.delay)
             vals = np.stack([np.float32([int(im[0, 0, 0]) % 50, 4, 3, 2, 1]) / 100 for im in imgs])
             idx = np.stack([np.int32([im.shape[0] % 6, 1, 2, 3, 4]) for im in imgs])
@@ -203,6 +217,10 @@ def test_worker_side_decode_hands_over_pixels(tmp_path):
     assert cli.classify_image(b"definitely not a jpeg") is None and owner.stats["requests"] == 6
     cli.close()
     owner.stop()
+    if pin == "1":
+        assert any(n > 0 for _, n in registered) and not any(eng.owned)      # segments registered, views (not copies) handed over
+    else:
+        assert not registered and all(eng.owned)
 
 
 def test_cuda_error_marks_the_owner_fatal(tmp_path):
